@@ -1,0 +1,13 @@
+"""polgen-rvc_b200: B200-native (sm_100a) RVC synthesizer decode.
+
+Drop-in for the reference ``rvc.lib.algorithm.synthesizers.Synthesizer``
+(``rvc/lib/algorithm/synthesizers.py:13``): same constructor, same
+``infer(phone, phone_lengths, pitch, nsff0, sid)`` call, same state-dict keys.
+The compute is hand-written CUDA behind the C ABI in ``include/polgen_rvc.h``;
+there is no CPU or PyTorch fallback -- importing the synthesizer without the
+built extension raises.
+"""
+from .configs import CONFIGS, SynthConfig, config_from_ctor, synth_inputs, synth_noise, synth_weights
+
+__all__ = ["CONFIGS", "SynthConfig", "config_from_ctor", "synth_inputs", "synth_noise",
+           "synth_weights"]
