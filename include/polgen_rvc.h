@@ -1,0 +1,179 @@
+/*
+ * polgen_rvc.h -- C ABI of the B200-native RVC synthesizer decode.
+ *
+ * The reference (Bebra777228/PolGen-RVC) is pure Python and has no FFI; its
+ * boundary for this path is the module-object contract between the callers in
+ * rvc/infer/{infer,pipeline}.py and rvc/lib/algorithm/synthesizers.Synthesizer
+ * (SURVEY.md 8(b)).  Each entry point below names the reference interface it
+ * stands in for.  All functions return 0 on success and a negative pg_status
+ * otherwise; pg_last_error() returns a thread-local message for the last
+ * failure.  Pointers marked "dev" are CUDA device pointers owned by the caller,
+ * "host" are host pointers.  One handle belongs to one GPU and is not
+ * thread-safe; independent handles may run concurrently.
+ *
+ * Tensor layouts at this boundary are time-major ("NLC"):
+ *   phone   [B][T][input_dim] f32   (== the reference's (B,T,D) layout)
+ *   pitch   [B][T] i64 in 1..255, f0 [B][T] f32 Hz (0 = unvoiced)
+ *   lengths [B] i64, sid [B] i64
+ *   eps_zp  [B][T][inter] f32  -- N(0,1) draw of synthesizers.py:174 (nullable)
+ *   eps_src [B][T*upp]    f32  -- N(0,1) draw of generators.py:154   (nullable)
+ *   wave    [B][T*upp]    f32  (== the reference's o[:,0,:])
+ *   aux     4 x [B][T][inter] f32 : z, z_p, m_p, logs_p (nullable)
+ * The Python host class hands the (B,C,T) views the reference returns back as
+ * transposed views of these buffers.
+ */
+#ifndef POLGEN_RVC_H_
+#define POLGEN_RVC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_ABI_VERSION 1
+#define PG_MAX_UPS 8
+#define PG_MAX_RESBLOCK_KERNELS 4
+#define PG_MAX_DILATIONS 4
+
+typedef enum pg_status {
+  PG_OK = 0,
+  PG_ERR_INVALID = -1,   /* bad argument / unknown tensor name / shape mismatch */
+  PG_ERR_CUDA = -2,      /* CUDA runtime or driver error */
+  PG_ERR_STATE = -3,     /* call order violated (e.g. infer before finalize) */
+  PG_ERR_UNSUPPORTED = -4
+} pg_status;
+
+typedef enum pg_dtype { PG_F32 = 0, PG_F16 = 1, PG_I64 = 2 } pg_dtype;
+
+/* Mirrors the reference constructor
+ *   Synthesizer(spec_channels, segment_size, inter_channels, hidden_channels,
+ *               filter_channels, n_heads, n_layers, kernel_size, p_dropout,
+ *               resblock, resblock_kernel_sizes, resblock_dilation_sizes,
+ *               upsample_rates, upsample_initial_channel, upsample_kernel_sizes,
+ *               spk_embed_dim, gin_channels, sr, use_f0, input_dim, is_half)
+ * (rvc/lib/algorithm/synthesizers.py:14-37).  Only the values the inference
+ * path reads are carried; use_f0 must be 1 and resblock "1" (the non-F0
+ * Generator is broken in the reference, generators.py:57). */
+typedef struct pg_config {
+  int32_t input_dim;                 /* 768 (v2) | 256 (v1) */
+  int32_t inter_channels;            /* 192 */
+  int32_t hidden_channels;           /* 192 */
+  int32_t filter_channels;           /* 768 */
+  int32_t n_heads;                   /* 2 */
+  int32_t n_layers;                  /* 6 */
+  int32_t kernel_size;               /* FFN kernel size, 3 */
+  int32_t attn_window;               /* 10 (encoders.py:22) */
+  int32_t gin_channels;              /* 256 */
+  int32_t spk_embed_dim;             /* rows of emb_g */
+  int32_t sr;                        /* 32000 | 40000 | 48000 */
+  int32_t upsample_initial_channel;  /* 512 */
+  int32_t n_ups;
+  int32_t upsample_rates[PG_MAX_UPS];
+  int32_t upsample_kernel_sizes[PG_MAX_UPS];
+  int32_t n_resblock_kernels;        /* 3 */
+  int32_t resblock_kernel_sizes[PG_MAX_RESBLOCK_KERNELS];
+  int32_t n_dilations;               /* 3 */
+  int32_t resblock_dilations[PG_MAX_RESBLOCK_KERNELS][PG_MAX_DILATIONS];
+  int32_t flow_n_flows;              /* 4  (residuals.py:116) */
+  int32_t flow_wn_layers;            /* 3  (synthesizers.py:104) */
+  int32_t flow_wn_kernel;            /* 5 */
+  int32_t flags;                     /* PG_FLAG_* */
+} pg_config;
+
+#define PG_FLAG_FORCE_SIMT 1   /* run every conv on the CUDA-core fp32 kernels (validation aid) */
+#define PG_FLAG_KEEP_TAPS 2    /* keep copies of intermediates for pg_debug_fetch */
+
+typedef struct pg_handle_s* pg_handle;
+
+const char* pg_last_error(void);
+int pg_abi_version(void);
+
+/* Synthesizer.__init__ (synthesizers.py:14-112) on CUDA device `device`. */
+int pg_create(const pg_config* cfg, int device, pg_handle* out);
+
+/* load_state_dict (infer.py:100): one call per tensor, reference key names with
+ * weight-norm already folded by the caller into plain "<module>.weight"
+ * (w = g*v/||v||).  `data` is a HOST pointer to contiguous f32. */
+int pg_load_tensor(pg_handle h, const char* name, const void* data,
+                   const int64_t* shape, int ndim, int dtype);
+
+/* .eval().to(device) (infer.py:101): checks every tensor arrived, repacks the
+ * weights into the kernels' layouts (tap-major fp16 K-major tiles for the
+ * tcgen05 convs, polyphase form for ConvTranspose1d) and uploads them. */
+int pg_finalize(pg_handle h);
+
+/* bytes of device workspace pg_infer(B,T) will hold (grown lazily). */
+size_t pg_workspace_bytes(pg_handle h, int B, int T);
+
+/* Synthesizer.infer(phone, phone_lengths, pitch, nsff0, sid)
+ * (synthesizers.py:162-188) as called from rvc/infer/pipeline.py:275.
+ * All rows of the batch share T; lengths[b] <= T mask the encoder/flow exactly
+ * as sequence_mask does (commons.py:89-93).  eps_* == NULL draws the noise on
+ * device from Philox(seed).  Enqueued on `stream` (a cudaStream_t); returns
+ * without synchronising. */
+int pg_infer(pg_handle h, void* stream, int B, int T,
+             const float* phone_dev, const int64_t* lengths_dev,
+             const int64_t* pitch_dev, const float* f0_dev, const int64_t* sid_dev,
+             const float* eps_zp_dev, const float* eps_src_dev, uint64_t seed,
+             float* wave_dev, float* aux_dev);
+
+/* Same call with HOST buffers (pinned recommended): copies the inputs to the
+ * device, runs pg_infer, copies the waveform back and synchronises -- the
+ * `.data.cpu().float().numpy()` round trip of pipeline.py:275-279. */
+int pg_infer_host(pg_handle h, int B, int T,
+                  const float* phone, const int64_t* lengths, const int64_t* pitch,
+                  const float* f0, const int64_t* sid, uint64_t seed, float* wave);
+
+/* Module-level entry points (the submodules a caller of the reference can
+ * invoke on their own).  Same layouts/conventions as pg_infer. */
+
+/* TextEncoder.forward (encoders.py:111-126): m_p, logs_p [B][T][inter]. */
+int pg_text_encoder(pg_handle h, void* stream, int B, int T,
+                    const float* phone_dev, const int64_t* lengths_dev,
+                    const int64_t* pitch_dev, float* m_p_dev, float* logs_p_dev);
+
+/* ResidualCouplingBlock.forward(reverse=True) (residuals.py:144-157):
+ * z_p [B][T][inter] -> z [B][T][inter]. */
+int pg_flow_reverse(pg_handle h, void* stream, int B, int T,
+                    const float* z_p_dev, const int64_t* lengths_dev,
+                    const int64_t* sid_dev, float* z_dev);
+
+/* SourceModuleHnNSF.forward (nsf.py:36-40) over SineGen.forward
+ * (generators.py:117-156): f0 [B][T] -> source [B][T*upp].  sine_dev
+ * (nullable) receives the deterministic sine_waves*uv before noise. */
+int pg_source(pg_handle h, void* stream, int B, int T, const float* f0_dev,
+              const float* eps_src_dev, uint64_t seed, float* source_dev, float* sine_dev);
+
+/* GeneratorNSF.forward (nsf.py:120-144): z [B][T][inter] (already masked),
+ * source [B][T*upp], sid -> wave [B][T*upp]. */
+int pg_generator(pg_handle h, void* stream, int B, int T, const float* z_dev,
+                 const float* source_dev, const int64_t* sid_dev, float* wave_dev);
+
+/* Copy an intermediate of the LAST pg_infer/pg_generator call to `dst_dev`
+ * as f32 (parity tests tap the same points the oracle exposes: "enc.x0",
+ * "enc.layer<i>", "flow.<f>", "dec.conv_pre", "dec.ups<i>", "dec.stage<i>").
+ * shape_out receives up to 3 dims [B][L][C]; returns element count or <0. */
+int64_t pg_debug_fetch(pg_handle h, void* stream, const char* tap, float* dst_dev,
+                       int64_t capacity, int64_t* shape_out);
+
+/* Statistics of the last call: number of kernels this library launched. */
+int64_t pg_launch_count(pg_handle h);
+
+/* Single-layer entry used by the op-level parity tests and micro-benchmarks:
+ * y[b][t][co] = sum_{tap,ci} w[co][ci][tap] * lrelu(x[b][t + tap*dil - pad][ci], in_slope) + bias
+ * x, y are f16 [B][L][C] device buffers, w f32 host [Cout][Cin][K] (Conv1d
+ * layout).  impl: 0 = CUDA-core fp32, 1 = tcgen05.  Returns elapsed ms of
+ * `iters` launches (CUDA events) in *ms_out when non-NULL. */
+int pg_op_conv1d_f16(int device, int impl, int B, int L, int Cin, int Cout, int K, int dil,
+                     const void* x_dev, const float* w_host, const float* bias_host,
+                     float in_slope, float out_slope, const void* res_dev, void* y_dev,
+                     int iters, float* ms_out);
+
+int pg_destroy(pg_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLGEN_RVC_H_ */

@@ -1,0 +1,1025 @@
+// C ABI of polgen-rvc_b200 (include/polgen_rvc.h): handle, weight store and
+// repacking, workspace, and the orchestration of Synthesizer.infer
+// (reference rvc/lib/algorithm/synthesizers.py:162-188) as a sequence of
+// kernel launches on the caller's stream.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/polgen_rvc.h"
+#include "pg_common.cuh"
+
+namespace pg {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+// one conv layer's device weights
+struct ConvW {
+  float* w = nullptr;      // [K][Cin][Cout] f32   (CUDA-core path)
+  __half* w16 = nullptr;   // [K][Cout][Cin] f16   (tcgen05 path)
+  float* bias = nullptr;   // [Cout]
+  int Cin = 0, Cout = 0, K = 1;
+};
+
+struct EncLayerW {
+  ConvW qkv, o, ffn1, ffn2;
+  float *rel_k = nullptr, *rel_v = nullptr;
+  float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
+};
+
+struct FlowW {
+  bool flipped = false;
+  ConvW pre, post;
+  float *cond_w = nullptr, *cond_b = nullptr;   // [2H*nl][gin]
+  std::vector<ConvW> in_layers, res, skip;     // res.size() == nl-1, skip.size() == nl
+};
+
+struct StageW {
+  ConvW up;            // polyphase conv: K taps over input frames, Cout' = u*Cout
+  int up_pad = 0;      // left pad (frames) of the polyphase conv
+  float *noise_w = nullptr, *noise_b = nullptr;   // [k][C], [C]
+  int noise_k = 1, noise_stride = 1, noise_pad = 0;
+  int C = 0, u = 1;
+  std::vector<ConvW> c1, c2;   // [n_kernels * n_dil]
+};
+
+struct Tap {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int dtype = DT_F32;
+  int64_t shape[3] = {0, 0, 0};
+};
+
+}  // namespace pg
+
+using namespace pg;
+
+struct pg_handle_s {
+  pg_config cfg;
+  int device = 0;
+  bool finalized = false;
+  std::map<std::string, HostTensor> host;
+  std::vector<void*> dev_allocs;
+
+  // packed weights
+  ConvW emb_phone;
+  float* emb_pitch = nullptr;
+  float* emb_g = nullptr;
+  std::vector<EncLayerW> enc;
+  ConvW proj;
+  std::vector<FlowW> flows;
+  float src_w = 0.f, src_b = 0.f;
+  ConvW conv_pre;
+  float *dec_cond_w = nullptr, *dec_cond_b = nullptr;
+  std::vector<StageW> stages;
+  float* conv_post_w = nullptr;   // [7][C_last]
+  int upp = 1;
+
+  // workspace
+  DevBuf ws;
+  size_t ws_off = 0;
+  std::map<std::string, Tap> taps;
+  int64_t launches = 0;
+
+  // pinned/device staging for pg_infer_host
+  DevBuf host_stage;
+};
+
+namespace {
+
+int fail(int code, const std::string& msg) {
+  set_error(msg);
+  return code;
+}
+
+struct Guard {
+  int prev = -1;
+  explicit Guard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~Guard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+template <typename T>
+int upload(pg_handle h, const std::vector<T>& v, T** out) {
+  void* p = nullptr;
+  PG_CUDA_CHECK(cudaMalloc(&p, v.size() * sizeof(T) + 16));
+  PG_CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  h->dev_allocs.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return PG_OK;
+}
+
+const HostTensor* find(pg_handle h, const std::string& name, std::initializer_list<int64_t> shape) {
+  auto it = h->host.find(name);
+  if (it == h->host.end()) {
+    set_error("missing tensor: " + name);
+    return nullptr;
+  }
+  int64_t want = 1;
+  for (auto s : shape) want *= s;
+  if (it->second.numel() != want) {
+    set_error("shape mismatch for " + name + ": got " + std::to_string(it->second.numel()) +
+              " elements, want " + std::to_string(want));
+    return nullptr;
+  }
+  return &it->second;
+}
+
+// Conv1d weight W[Cout][Cin][K] (rows co_begin..co_begin+co_count) ->
+//   w   [K][Cin][co_count] f32,  w16 [K][co_count][Cin] f16,  bias [co_count]
+int pack_conv(pg_handle h, const std::string& wname, const std::string& bname, int Cout, int Cin,
+              int K, int co_begin, int co_count, bool flip_ci, bool flip_co, bool want16, ConvW* out) {
+  const HostTensor* W = find(h, wname, {Cout, Cin, K});
+  if (!W) return PG_ERR_INVALID;
+  std::vector<float> w((size_t)K * Cin * co_count);
+  std::vector<__half> w16;
+  if (want16) w16.resize(w.size());
+  for (int co = 0; co < co_count; ++co) {
+    const int src_co = co_begin + (flip_co ? co_count - 1 - co : co);
+    for (int ci = 0; ci < Cin; ++ci) {
+      const int src_ci = flip_ci ? Cin - 1 - ci : ci;
+      for (int k = 0; k < K; ++k) {
+        const float v = W->data[((size_t)src_co * Cin + src_ci) * K + k];
+        w[((size_t)k * Cin + ci) * co_count + co] = v;
+        if (want16) w16[((size_t)k * co_count + co) * Cin + ci] = __float2half_rn(v);
+      }
+    }
+  }
+  int rc = upload(h, w, &out->w);
+  if (rc) return rc;
+  if (want16) {
+    rc = upload(h, w16, &out->w16);
+    if (rc) return rc;
+  }
+  if (!bname.empty()) {
+    const HostTensor* Bv = find(h, bname, {Cout});
+    if (!Bv) return PG_ERR_INVALID;
+    std::vector<float> b(co_count);
+    for (int co = 0; co < co_count; ++co)
+      b[co] = Bv->data[co_begin + (flip_co ? co_count - 1 - co : co)];
+    rc = upload(h, b, &out->bias);
+    if (rc) return rc;
+  }
+  out->Cin = Cin;
+  out->Cout = co_count;
+  out->K = K;
+  return PG_OK;
+}
+
+int upload_named(pg_handle h, const std::string& name, std::initializer_list<int64_t> shape,
+                 float** out) {
+  const HostTensor* t = find(h, name, shape);
+  if (!t) return PG_ERR_INVALID;
+  return upload(h, t->data, out);
+}
+
+// ConvTranspose1d(Cin, Cout, k, stride u, padding (k-u)/2) as a dense conv over
+// input frames with Cout' = u*Cout (nsf.py:80-91):
+//   y[u*q + r][co] = sum_ci sum_{j == p (mod u)} W[ci][co][j] * x[q + c - (j-p)/u][ci]
+//   p = (r + pad) % u, c = (r + pad) / u.
+// Output row q of the dense conv is rows u*q .. u*q+u-1 of the time-major result.
+int pack_conv_transpose(pg_handle h, const std::string& wname, const std::string& bname, int Cin,
+                        int Cout, int k, int u, StageW* st) {
+  const HostTensor* W = find(h, wname, {Cin, Cout, k});
+  const HostTensor* Bv = find(h, bname, {Cout});
+  if (!W || !Bv) return PG_ERR_INVALID;
+  const int pad = (k - u) / 2;
+  int dmin = 0, dmax = 0;
+  for (int r = 0; r < u; ++r) {
+    const int p = (r + pad) % u, c = (r + pad) / u;
+    for (int j = p, m = 0; j < k; j += u, ++m) {
+      dmin = std::min(dmin, c - m);
+      dmax = std::max(dmax, c - m);
+    }
+  }
+  const int taps = dmax - dmin + 1;
+  const int N = u * Cout;
+  std::vector<float> w((size_t)taps * Cin * N, 0.f);
+  for (int r = 0; r < u; ++r) {
+    const int p = (r + pad) % u, c = (r + pad) / u;
+    for (int j = p, m = 0; j < k; j += u, ++m) {
+      const int tap = (c - m) - dmin;
+      for (int ci = 0; ci < Cin; ++ci)
+        for (int co = 0; co < Cout; ++co)
+          w[((size_t)tap * Cin + ci) * N + r * Cout + co] = W->data[((size_t)ci * Cout + co) * k + j];
+    }
+  }
+  std::vector<float> b(N);
+  for (int r = 0; r < u; ++r)
+    for (int co = 0; co < Cout; ++co) b[r * Cout + co] = Bv->data[co];
+  int rc = upload(h, w, &st->up.w);
+  if (rc) return rc;
+  rc = upload(h, b, &st->up.bias);
+  if (rc) return rc;
+  st->up.Cin = Cin;
+  st->up.Cout = N;
+  st->up.K = taps;
+  st->up_pad = -dmin;
+  return PG_OK;
+}
+
+// ---- workspace -------------------------------------------------------------
+struct Plan {
+  size_t total = 0;
+  size_t take(size_t bytes) {
+    const size_t off = total;
+    total += (bytes + 255) & ~size_t(255);
+    return off;
+  }
+};
+
+struct Ws {
+  // offsets into the workspace
+  size_t lens, pitch, sid, x, y, qkv, att, ffn, stats, m_p, logs_p, z_p, z, fh, fa, facts, fskip,
+      gcond, dcond, source, phase, stage[5];
+  size_t stage_elems = 0;
+  size_t total = 0;
+};
+
+Ws plan_ws(const pg_config& c, int B, int T) {
+  Ws w;
+  Plan p;
+  const size_t BT = (size_t)B * T;
+  const int H = c.hidden_channels, F = c.filter_channels, C = c.inter_channels;
+  w.lens = p.take(sizeof(int) * B);
+  w.pitch = p.take(sizeof(int) * BT);
+  w.sid = p.take(sizeof(int) * B);
+  w.x = p.take(sizeof(float) * BT * H);
+  w.y = p.take(sizeof(float) * BT * H);
+  w.qkv = p.take(sizeof(float) * BT * 3 * H);
+  w.att = p.take(sizeof(float) * BT * H);
+  w.ffn = p.take(sizeof(float) * BT * F);
+  w.stats = p.take(sizeof(float) * BT * 2 * C);
+  w.m_p = p.take(sizeof(float) * BT * C);
+  w.logs_p = p.take(sizeof(float) * BT * C);
+  w.z_p = p.take(sizeof(float) * BT * C);
+  w.z = p.take(sizeof(float) * BT * C);
+  w.fh = p.take(sizeof(float) * BT * H);
+  w.fa = p.take(sizeof(float) * BT * 2 * H);
+  w.facts = p.take(sizeof(float) * BT * H);
+  w.fskip = p.take(sizeof(float) * BT * H);
+  w.gcond = p.take(sizeof(float) * c.flow_n_flows * B * 2 * H * c.flow_wn_layers);
+  w.dcond = p.take(sizeof(float) * B * c.upsample_initial_channel);
+  size_t L = T;
+  size_t max_elems = BT * c.upsample_initial_channel;
+  int ch = c.upsample_initial_channel;
+  for (int i = 0; i < c.n_ups; ++i) {
+    L *= c.upsample_rates[i];
+    ch /= 2;
+    max_elems = std::max(max_elems, (size_t)B * L * ch);
+  }
+  w.source = p.take(sizeof(float) * B * L);
+  w.phase = p.take(sizeof(double) * BT);
+  w.stage_elems = max_elems;
+  for (int i = 0; i < 5; ++i) w.stage[i] = p.take(sizeof(__half) * max_elems + 4096);
+  w.total = p.total;
+  return w;
+}
+
+int ensure_ws(pg_handle h, size_t bytes) {
+  if (h->ws.bytes >= bytes) return PG_OK;
+  if (h->ws.p) PG_CUDA_CHECK(cudaFree(h->ws.p));
+  h->ws.p = nullptr;
+  h->ws.bytes = 0;
+  PG_CUDA_CHECK(cudaMalloc(&h->ws.p, bytes));
+  h->ws.bytes = bytes;
+  return PG_OK;
+}
+
+template <typename T>
+T* at(pg_handle h, size_t off) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(h->ws.p) + off);
+}
+
+int record_tap(pg_handle h, cudaStream_t s, const std::string& name, const void* src, int dtype,
+               int64_t B, int64_t L, int64_t C) {
+  if (!(h->cfg.flags & PG_FLAG_KEEP_TAPS)) return PG_OK;
+  Tap& t = h->taps[name];
+  const size_t bytes = (size_t)B * L * C * (dtype == DT_F16 ? 2 : 4);
+  if (t.bytes < bytes) {
+    if (t.p) PG_CUDA_CHECK(cudaFree(t.p));
+    PG_CUDA_CHECK(cudaMalloc(&t.p, bytes));
+    t.bytes = bytes;
+  }
+  t.dtype = dtype;
+  t.shape[0] = B;
+  t.shape[1] = L;
+  t.shape[2] = C;
+  PG_CUDA_CHECK(cudaMemcpyAsync(t.p, src, bytes, cudaMemcpyDeviceToDevice, s));
+  return PG_OK;
+}
+
+#define PG_LAUNCH(h, expr)                                                          \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    ++(h)->launches;                                                                \
+    if (_e != cudaSuccess) {                                                        \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+      return PG_ERR_CUDA;                                                           \
+    }                                                                               \
+  } while (0)
+
+#define PG_TRY(expr)          \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != PG_OK) return _rc; \
+  } while (0)
+
+int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_dt, DType out_dt) {
+  a.w = w.w;
+  a.w16 = w.w16;
+  a.bias = w.bias;
+  a.Cin = w.Cin;
+  a.Cout = w.Cout;
+  a.K = w.K;
+  const bool force_simt = (h->cfg.flags & PG_FLAG_FORCE_SIMT) != 0;
+  if (!force_simt && in_dt == DT_F16 && out_dt == DT_F16 && w.w16 && umma_conv_supported(a)) {
+    PG_LAUNCH(h, launch_conv_umma(a, s));
+  } else {
+    PG_LAUNCH(h, launch_conv_simt(a, in_dt, out_dt, s));
+  }
+  return PG_OK;
+}
+
+// ---- TextEncoder.forward (encoders.py:111-126) -----------------------------
+int run_text_encoder(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const float* phone) {
+  const pg_config& c = h->cfg;
+  const int H = c.hidden_channels, F = c.filter_channels;
+  const int* lens = at<int>(h, w.lens);
+  float* x = at<float>(h, w.x);
+  float* y = at<float>(h, w.y);
+  {
+    ConvArgs a;
+    a.x = phone; a.x_ld = c.input_dim; a.B = B; a.L_in = T; a.L_out = T;
+    a.y = x; a.y_ld = H;
+    PG_TRY(run_conv(h, s, a, h->emb_phone, DT_F32, DT_F32));
+    PG_LAUNCH(h, launch_embed_finish(x, h->emb_pitch, at<int>(h, w.pitch), lens, B, T, H,
+                                     sqrtf((float)H), s));
+  }
+  PG_TRY(record_tap(h, s, "enc.x0", x, DT_F32, B, T, H));
+  const int ksz = c.kernel_size;
+  for (int i = 0; i < c.n_layers; ++i) {
+    const EncLayerW& L = h->enc[i];
+    float* qkv = at<float>(h, w.qkv);
+    float* att = at<float>(h, w.att);
+    float* ffn = at<float>(h, w.ffn);
+    ConvArgs a;
+    a.B = B; a.L_in = T; a.L_out = T; a.lens = lens;
+    // q, k, v 1x1 convs fused into one GEMM (attentions.py:64-66)
+    a.x = x; a.x_ld = H; a.y = qkv; a.y_ld = 3 * H;
+    PG_TRY(run_conv(h, s, a, L.qkv, DT_F32, DT_F32));
+    PG_LAUNCH(h, launch_rel_attention(qkv, L.rel_k, L.rel_v, lens, att, B, T, H, c.n_heads,
+                                      c.attn_window, s));
+    a.x = att; a.x_ld = H; a.y = y; a.y_ld = H;
+    PG_TRY(run_conv(h, s, a, L.o, DT_F32, DT_F32));
+    PG_LAUNCH(h, launch_add_layernorm(x, y, L.g1, L.b1, B * T, H, s));
+    // FFN (attentions.py:195-203): conv(x*m) -> relu -> conv(.*m) -> *m, same padding
+    ConvArgs f1 = a;
+    f1.x = x; f1.x_ld = H; f1.y = ffn; f1.y_ld = F; f1.in_mask = 1; f1.pad = (ksz - 1) / 2;
+    f1.act = ACT_RELU;
+    PG_TRY(run_conv(h, s, f1, L.ffn1, DT_F32, DT_F32));
+    ConvArgs f2 = a;
+    f2.x = ffn; f2.x_ld = F; f2.y = y; f2.y_ld = H; f2.in_mask = 1; f2.pad = (ksz - 1) / 2;
+    f2.out_mask = 1;
+    PG_TRY(run_conv(h, s, f2, L.ffn2, DT_F32, DT_F32));
+    PG_LAUNCH(h, launch_add_layernorm(x, y, L.g2, L.b2, B * T, H, s));
+    PG_TRY(record_tap(h, s, "enc.layer" + std::to_string(i), x, DT_F32, B, T, H));
+  }
+  // proj(x * mask) * mask (encoders.py:72,123)
+  ConvArgs a;
+  a.B = B; a.L_in = T; a.L_out = T; a.lens = lens; a.in_mask = 1; a.out_mask = 1;
+  a.x = x; a.x_ld = H; a.y = at<float>(h, w.stats); a.y_ld = 2 * c.inter_channels;
+  PG_TRY(run_conv(h, s, a, h->proj, DT_F32, DT_F32));
+  return PG_OK;
+}
+
+// ---- ResidualCouplingBlock.forward(reverse=True) (residuals.py:144-157) ----
+// z (in place, [B][T][C]).  Channel flips are folded into the weights at
+// pg_finalize, so flows alternate which half is x0 instead of moving data.
+int run_flow(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, float* z) {
+  const pg_config& c = h->cfg;
+  const int H = c.hidden_channels, C = c.inter_channels, half = C / 2, nl = c.flow_wn_layers;
+  const int* lens = at<int>(h, w.lens);
+  float* fh = at<float>(h, w.fh);
+  float* fa = at<float>(h, w.fa);
+  float* acts = at<float>(h, w.facts);
+  float* skip = at<float>(h, w.fskip);
+  const int gl = 2 * H * nl;
+  for (int f = c.flow_n_flows - 1; f >= 0; --f) {
+    const FlowW& F = h->flows[f];
+    float* gc = at<float>(h, w.gcond) + (size_t)f * B * gl;
+    PG_LAUNCH(h, launch_cond_gemv(h->emb_g, at<int>(h, w.sid), F.cond_w, F.cond_b, gc, B,
+                                  c.gin_channels, gl, s));
+    const int x0_off = F.flipped ? half : 0, x1_off = F.flipped ? 0 : half;
+    ConvArgs a;
+    a.B = B; a.L_in = T; a.L_out = T; a.lens = lens;
+    // h = pre(x0) * mask
+    ConvArgs pre = a;
+    pre.x = z; pre.x_ld = C; pre.x_coff = x0_off; pre.y = fh; pre.y_ld = H; pre.out_mask = 1;
+    PG_TRY(run_conv(h, s, pre, F.pre, DT_F32, DT_F32));
+    for (int l = 0; l < nl; ++l) {
+      ConvArgs in = a;
+      in.x = fh; in.x_ld = H; in.y = fa; in.y_ld = 2 * H; in.pad = (c.flow_wn_kernel - 1) / 2;
+      in.bbias = gc + (size_t)l * 2 * H; in.bbias_ld = gl;
+      PG_TRY(run_conv(h, s, in, F.in_layers[l], DT_F32, DT_F32));
+      PG_LAUNCH(h, launch_gate(fa, acts, (int64_t)B * T, H, s));
+      // skip (+)= res_skip[:, H:] (or the whole output on the last layer)
+      ConvArgs sk = a;
+      sk.x = acts; sk.x_ld = H; sk.y = skip; sk.y_ld = H; sk.accumulate = l > 0;
+      PG_TRY(run_conv(h, s, sk, F.skip[l], DT_F32, DT_F32));
+      if (l < nl - 1) {   // h = (h + res_skip[:, :H]) * mask
+        ConvArgs rs = a;
+        rs.x = acts; rs.x_ld = H; rs.y = fh; rs.y_ld = H; rs.res = fh; rs.res_ld = H;
+        rs.out_mask = 1;
+        PG_TRY(run_conv(h, s, rs, F.res[l], DT_F32, DT_F32));
+      }
+    }
+    // x1 = (x1 - post(skip * mask) * mask) * mask
+    ConvArgs po = a;
+    po.x = skip; po.x_ld = H; po.in_mask = 1;
+    po.y = z; po.y_ld = C; po.y_coff = x1_off;
+    po.res = z; po.res_ld = C; po.res_coff = x1_off; po.res_scale = -1.f; po.out_scale = -1.f;
+    po.out_mask = 1;
+    PG_TRY(run_conv(h, s, po, F.post, DT_F32, DT_F32));
+    PG_TRY(record_tap(h, s, "flow." + std::to_string(f), z, DT_F32, B, T, C));
+  }
+  return PG_OK;
+}
+
+// ---- GeneratorNSF.forward (nsf.py:120-144) ---------------------------------
+int run_generator(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const float* z,
+                  const float* source, float* wave) {
+  const pg_config& c = h->cfg;
+  const int* lens = at<int>(h, w.lens);
+  const int C0 = c.upsample_initial_channel;
+  float* dcond = at<float>(h, w.dcond);
+  PG_LAUNCH(h, launch_cond_gemv(h->emb_g, at<int>(h, w.sid), h->dec_cond_w, h->dec_cond_b, dcond, B,
+                                c.gin_channels, C0, s));
+  __half* buf[5];
+  for (int i = 0; i < 5; ++i) buf[i] = at<__half>(h, w.stage[i]);
+  // conv_pre(z * mask) + cond(g)
+  {
+    ConvArgs a;
+    a.B = B; a.L_in = T; a.L_out = T; a.lens = lens; a.in_mask = 1;
+    a.x = z; a.x_ld = c.inter_channels; a.pad = 3;
+    a.bbias = dcond; a.bbias_ld = C0;
+    a.y = buf[0]; a.y_ld = C0;
+    PG_TRY(run_conv(h, s, a, h->conv_pre, DT_F32, DT_F16));
+  }
+  PG_TRY(record_tap(h, s, "dec.conv_pre", buf[0], DT_F16, B, T, C0));
+  int cur = 0;          // buffer holding the stage input
+  int64_t L = T;
+  const int64_t Lsrc = (int64_t)T * h->upp;
+  for (int i = 0; i < c.n_ups; ++i) {
+    const StageW& S = h->stages[i];
+    const int C = S.C;
+    // free buffers: everything except cur
+    int fr[4], nf = 0;
+    for (int k = 0; k < 5; ++k)
+      if (k != cur) fr[nf++] = k;
+    __half* xin = buf[fr[0]];
+    __half* xa = buf[fr[1]];
+    __half* xb = buf[fr[2]];
+    __half* tmp = buf[fr[3]];
+    __half* acc = buf[cur];   // the ups input is dead once xin is produced
+    // x = ups(lrelu(x, 0.1)) as a dense conv over input frames
+    {
+      ConvArgs a;
+      a.B = B; a.L_in = (int)L; a.L_out = (int)L;
+      a.x = buf[cur]; a.x_ld = S.up.Cin; a.in_slope = 0.1f; a.pad = S.up_pad;
+      a.y = xin; a.y_ld = S.up.Cout;
+      PG_TRY(run_conv(h, s, a, S.up, DT_F16, DT_F16));
+    }
+    L *= S.u;
+    // x = x + noise_convs[i](har_source)
+    PG_LAUNCH(h, launch_noise_inject(xin, source, S.noise_w, S.noise_b, B, (int)L, C, (int)Lsrc,
+                                     S.noise_k, S.noise_stride, S.noise_pad, s));
+    PG_TRY(record_tap(h, s, "dec.ups" + std::to_string(i), xin, DT_F16, B, L, C));
+    // x = mean_j ResBlock_j(x)   (residuals.py:45-53)
+    const int nk = c.n_resblock_kernels, nd = c.n_dilations;
+    for (int j = 0; j < nk; ++j) {
+      const int ksz = c.resblock_kernel_sizes[j];
+      const __half* xc = xin;
+      for (int d = 0; d < nd; ++d) {
+        const int dil = c.resblock_dilations[j][d];
+        const bool last = d == nd - 1;
+        ConvArgs a1;
+        a1.B = B; a1.L_in = (int)L; a1.L_out = (int)L;
+        a1.x = xc; a1.x_ld = C; a1.in_slope = 0.1f; a1.dil = dil; a1.pad = (ksz * dil - dil) / 2;
+        a1.act = ACT_LRELU; a1.out_slope = 0.1f;
+        a1.y = tmp; a1.y_ld = C;
+        PG_TRY(run_conv(h, s, a1, S.c1[j * nd + d], DT_F16, DT_F16));
+        ConvArgs a2;
+        a2.B = B; a2.L_in = (int)L; a2.L_out = (int)L;
+        a2.x = tmp; a2.x_ld = C; a2.pad = (ksz - 1) / 2;
+        a2.res = xc; a2.res_ld = C;
+        __half* dst = last ? acc : (xc == xa ? xb : xa);
+        a2.y = dst; a2.y_ld = C;
+        if (last) {
+          a2.out_scale = 1.f / nk;
+          a2.accumulate = j > 0;
+        }
+        PG_TRY(run_conv(h, s, a2, S.c2[j * nd + d], DT_F16, DT_F16));
+        xc = dst;
+      }
+    }
+    PG_TRY(record_tap(h, s, "dec.stage" + std::to_string(i), acc, DT_F16, B, L, C));
+    // acc lives in buf[cur]: the next stage reads it
+  }
+  const int Cl = h->stages.back().C;
+  PG_LAUNCH(h, launch_conv_post(buf[cur], h->conv_post_w, wave, B, (int)L, Cl, 7, 0.01f, s));
+  return PG_OK;
+}
+
+int check_ready(pg_handle h, int B, int T) {
+  if (!h) return fail(PG_ERR_INVALID, "null handle");
+  if (!h->finalized) return fail(PG_ERR_STATE, "pg_finalize has not been called");
+  if (B <= 0 || T <= 0) return fail(PG_ERR_INVALID, "B and T must be positive");
+  return PG_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char* pg_last_error(void) { return g_err.c_str(); }
+int pg_abi_version(void) { return PG_ABI_VERSION; }
+
+int pg_create(const pg_config* cfg, int device, pg_handle* out) {
+  if (!cfg || !out) return fail(PG_ERR_INVALID, "null argument");
+  if (cfg->n_ups < 1 || cfg->n_ups > PG_MAX_UPS || cfg->n_resblock_kernels < 1 ||
+      cfg->n_resblock_kernels > PG_MAX_RESBLOCK_KERNELS || cfg->n_dilations < 1 ||
+      cfg->n_dilations > PG_MAX_DILATIONS)
+    return fail(PG_ERR_INVALID, "config out of range");
+  if (cfg->hidden_channels % cfg->n_heads || cfg->hidden_channels / cfg->n_heads != 96)
+    return fail(PG_ERR_UNSUPPORTED, "attention head dim must be 96 (hidden 192, 2 heads)");
+  if (cfg->flow_n_flows % 2)
+    return fail(PG_ERR_UNSUPPORTED, "flow_n_flows must be even (channel flips are folded into weights)");
+  if (cfg->inter_channels % 8 || cfg->input_dim % 4)
+    return fail(PG_ERR_UNSUPPORTED, "channel counts must be multiples of 4");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PG_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(PG_ERR_INVALID, "bad device index");
+  cudaDeviceProp prop;
+  PG_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(PG_ERR_UNSUPPORTED, "this library is built for sm_100a (B200) only; found sm_" +
+                                        std::to_string(prop.major) + std::to_string(prop.minor));
+  pg_handle h = new pg_handle_s();
+  h->cfg = *cfg;
+  h->device = device;
+  h->upp = 1;
+  for (int i = 0; i < cfg->n_ups; ++i) h->upp *= cfg->upsample_rates[i];
+  *out = h;
+  return PG_OK;
+}
+
+int pg_load_tensor(pg_handle h, const char* name, const void* data, const int64_t* shape, int ndim,
+                   int dtype) {
+  if (!h || !name || !data || !shape || ndim < 0 || ndim > 8)
+    return fail(PG_ERR_INVALID, "bad argument to pg_load_tensor");
+  if (dtype != PG_F32) return fail(PG_ERR_UNSUPPORTED, "pg_load_tensor takes f32 host data");
+  if (h->finalized) return fail(PG_ERR_STATE, "handle already finalized");
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  const int64_t n = t.numel();
+  t.data.assign(reinterpret_cast<const float*>(data), reinterpret_cast<const float*>(data) + n);
+  h->host[name] = std::move(t);
+  return PG_OK;
+}
+
+int pg_finalize(pg_handle h) {
+  if (!h) return fail(PG_ERR_INVALID, "null handle");
+  if (h->finalized) return PG_OK;
+  Guard g(h->device);
+  const pg_config& c = h->cfg;
+  const int H = c.hidden_channels, F = c.filter_channels, C = c.inter_channels;
+  const int R = 2 * c.attn_window + 1, D = H / c.n_heads;
+  // --- TextEncoder ---
+  PG_TRY(pack_conv(h, "enc_p.emb_phone.weight", "enc_p.emb_phone.bias", H, c.input_dim, 1, 0, H,
+                   false, false, false, &h->emb_phone));
+  PG_TRY(upload_named(h, "enc_p.emb_pitch.weight", {256, H}, &h->emb_pitch));
+  PG_TRY(upload_named(h, "emb_g.weight", {c.spk_embed_dim, c.gin_channels}, &h->emb_g));
+  h->enc.resize(c.n_layers);
+  for (int i = 0; i < c.n_layers; ++i) {
+    EncLayerW& L = h->enc[i];
+    const std::string p = "enc_p.encoder.attn_layers." + std::to_string(i) + ".";
+    {   // fused q|k|v weight [1][H][3H]
+      std::vector<float> w((size_t)H * 3 * H), b(3 * H);
+      const char* nm[3] = {"conv_q", "conv_k", "conv_v"};
+      for (int q = 0; q < 3; ++q) {
+        const HostTensor* W = find(h, p + nm[q] + ".weight", {H, H, 1});
+        const HostTensor* Bv = find(h, p + nm[q] + ".bias", {H});
+        if (!W || !Bv) return PG_ERR_INVALID;
+        for (int co = 0; co < H; ++co) {
+          b[q * H + co] = Bv->data[co];
+          for (int ci = 0; ci < H; ++ci) w[(size_t)ci * 3 * H + q * H + co] = W->data[(size_t)co * H + ci];
+        }
+      }
+      PG_TRY(upload(h, w, &L.qkv.w));
+      PG_TRY(upload(h, b, &L.qkv.bias));
+      L.qkv.Cin = H; L.qkv.Cout = 3 * H; L.qkv.K = 1;
+    }
+    PG_TRY(pack_conv(h, p + "conv_o.weight", p + "conv_o.bias", H, H, 1, 0, H, false, false, false, &L.o));
+    PG_TRY(upload_named(h, p + "emb_rel_k", {1, R, D}, &L.rel_k));
+    PG_TRY(upload_named(h, p + "emb_rel_v", {1, R, D}, &L.rel_v));
+    const std::string n1 = "enc_p.encoder.norm_layers_1." + std::to_string(i) + ".";
+    const std::string n2 = "enc_p.encoder.norm_layers_2." + std::to_string(i) + ".";
+    PG_TRY(upload_named(h, n1 + "gamma", {H}, &L.g1));
+    PG_TRY(upload_named(h, n1 + "beta", {H}, &L.b1));
+    PG_TRY(upload_named(h, n2 + "gamma", {H}, &L.g2));
+    PG_TRY(upload_named(h, n2 + "beta", {H}, &L.b2));
+    const std::string f = "enc_p.encoder.ffn_layers." + std::to_string(i) + ".";
+    PG_TRY(pack_conv(h, f + "conv_1.weight", f + "conv_1.bias", F, H, c.kernel_size, 0, F, false,
+                     false, false, &L.ffn1));
+    PG_TRY(pack_conv(h, f + "conv_2.weight", f + "conv_2.bias", H, F, c.kernel_size, 0, H, false,
+                     false, false, &L.ffn2));
+  }
+  PG_TRY(pack_conv(h, "enc_p.proj.weight", "enc_p.proj.bias", 2 * C, H, 1, 0, 2 * C, false, false,
+                   false, &h->proj));
+  // --- flow: reversed iteration applies Flip before each coupling layer, so the
+  // layers visited 1st, 3rd, ... (f = n-1, n-3, ...) see channel-reversed data.
+  const int half = C / 2, nl = c.flow_wn_layers;
+  h->flows.resize(c.flow_n_flows);
+  for (int f = 0; f < c.flow_n_flows; ++f) {
+    FlowW& Fw = h->flows[f];
+    Fw.flipped = ((c.flow_n_flows - 1 - f) % 2) == 0;
+    const std::string p = "flow.flows." + std::to_string(2 * f) + ".";
+    PG_TRY(pack_conv(h, p + "pre.weight", p + "pre.bias", H, half, 1, 0, H, Fw.flipped, false, false,
+                     &Fw.pre));
+    PG_TRY(pack_conv(h, p + "post.weight", p + "post.bias", half, H, 1, 0, half, false, Fw.flipped,
+                     false, &Fw.post));
+    PG_TRY(upload_named(h, p + "enc.cond_layer.weight", {2 * H * nl, c.gin_channels, 1}, &Fw.cond_w));
+    PG_TRY(upload_named(h, p + "enc.cond_layer.bias", {2 * H * nl}, &Fw.cond_b));
+    Fw.in_layers.resize(nl);
+    Fw.skip.resize(nl);
+    Fw.res.resize(nl - 1);
+    for (int l = 0; l < nl; ++l) {
+      const std::string q = p + "enc.in_layers." + std::to_string(l) + ".";
+      PG_TRY(pack_conv(h, q + "weight", q + "bias", 2 * H, H, c.flow_wn_kernel, 0, 2 * H, false, false,
+                       false, &Fw.in_layers[l]));
+      const std::string r = p + "enc.res_skip_layers." + std::to_string(l) + ".";
+      if (l < nl - 1) {
+        PG_TRY(pack_conv(h, r + "weight", r + "bias", 2 * H, H, 1, 0, H, false, false, false, &Fw.res[l]));
+        PG_TRY(pack_conv(h, r + "weight", r + "bias", 2 * H, H, 1, H, H, false, false, false, &Fw.skip[l]));
+      } else {
+        PG_TRY(pack_conv(h, r + "weight", r + "bias", H, H, 1, 0, H, false, false, false, &Fw.skip[l]));
+      }
+    }
+  }
+  // --- decoder ---
+  {
+    const HostTensor* lw = find(h, "dec.m_source.l_linear.weight", {1, 1});
+    const HostTensor* lb = find(h, "dec.m_source.l_linear.bias", {1});
+    if (!lw || !lb) return PG_ERR_INVALID;
+    h->src_w = lw->data[0];
+    h->src_b = lb->data[0];
+  }
+  const int C0 = c.upsample_initial_channel;
+  PG_TRY(pack_conv(h, "dec.conv_pre.weight", "dec.conv_pre.bias", C0, C, 7, 0, C0, false, false, false,
+                   &h->conv_pre));
+  PG_TRY(upload_named(h, "dec.cond.weight", {C0, c.gin_channels, 1}, &h->dec_cond_w));
+  PG_TRY(upload_named(h, "dec.cond.bias", {C0}, &h->dec_cond_b));
+  h->stages.resize(c.n_ups);
+  int cin = C0;
+  for (int i = 0; i < c.n_ups; ++i) {
+    StageW& S = h->stages[i];
+    const int cout = cin / 2, u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+    if ((k - u) % 2) return fail(PG_ERR_UNSUPPORTED, "upsample kernel - rate must be even");
+    S.C = cout;
+    S.u = u;
+    const std::string up = "dec.ups." + std::to_string(i) + ".";
+    PG_TRY(pack_conv_transpose(h, up + "weight", up + "bias", cin, cout, k, u, &S));
+    int stride = 1;
+    for (int j = i + 1; j < c.n_ups; ++j) stride *= c.upsample_rates[j];
+    S.noise_stride = stride;
+    S.noise_k = stride > 1 ? 2 * stride : 1;
+    S.noise_pad = stride > 1 ? stride / 2 : 0;
+    {
+      const std::string nc = "dec.noise_convs." + std::to_string(i) + ".";
+      const HostTensor* W = find(h, nc + "weight", {cout, 1, S.noise_k});
+      if (!W) return PG_ERR_INVALID;
+      std::vector<float> wn((size_t)S.noise_k * cout);
+      for (int co = 0; co < cout; ++co)
+        for (int j = 0; j < S.noise_k; ++j) wn[(size_t)j * cout + co] = W->data[(size_t)co * S.noise_k + j];
+      PG_TRY(upload(h, wn, &S.noise_w));
+      PG_TRY(upload_named(h, nc + "bias", {cout}, &S.noise_b));
+    }
+    const int nk = c.n_resblock_kernels, nd = c.n_dilations;
+    S.c1.resize(nk * nd);
+    S.c2.resize(nk * nd);
+    for (int j = 0; j < nk; ++j)
+      for (int d = 0; d < nd; ++d) {
+        const std::string rb = "dec.resblocks." + std::to_string(i * nk + j) + ".";
+        const int ksz = c.resblock_kernel_sizes[j];
+        PG_TRY(pack_conv(h, rb + "convs1." + std::to_string(d) + ".weight",
+                         rb + "convs1." + std::to_string(d) + ".bias", cout, cout, ksz, 0, cout, false,
+                         false, true, &S.c1[j * nd + d]));
+        PG_TRY(pack_conv(h, rb + "convs2." + std::to_string(d) + ".weight",
+                         rb + "convs2." + std::to_string(d) + ".bias", cout, cout, ksz, 0, cout, false,
+                         false, true, &S.c2[j * nd + d]));
+      }
+    cin = cout;
+  }
+  {
+    const HostTensor* W = find(h, "dec.conv_post.weight", {1, cin, 7});
+    if (!W) return PG_ERR_INVALID;
+    std::vector<float> wp((size_t)7 * cin);
+    for (int ci = 0; ci < cin; ++ci)
+      for (int j = 0; j < 7; ++j) wp[(size_t)j * cin + ci] = W->data[(size_t)ci * 7 + j];
+    PG_TRY(upload(h, wp, &h->conv_post_w));
+  }
+  h->host.clear();
+  h->finalized = true;
+  return PG_OK;
+}
+
+size_t pg_workspace_bytes(pg_handle h, int B, int T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  return plan_ws(h->cfg, B, T).total;
+}
+
+static int prepare(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const int64_t* lengths,
+                   const int64_t* pitch, const int64_t* sid) {
+  PG_TRY(ensure_ws(h, w.total));
+  PG_LAUNCH(h, launch_prepare_ints(lengths, pitch, sid, at<int>(h, w.lens), at<int>(h, w.pitch),
+                                   at<int>(h, w.sid), B, T, h->cfg.spk_embed_dim, s));
+  return PG_OK;
+}
+
+int pg_infer(pg_handle h, void* stream, int B, int T, const float* phone, const int64_t* lengths,
+             const int64_t* pitch, const float* f0, const int64_t* sid, const float* eps_zp,
+             const float* eps_src, uint64_t seed, float* wave, float* aux) {
+  PG_TRY(check_ready(h, B, T));
+  if (!phone || !lengths || !pitch || !f0 || !sid || !wave)
+    return fail(PG_ERR_INVALID, "null tensor argument to pg_infer");
+  Guard g(h->device);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const pg_config& c = h->cfg;
+  const Ws w = plan_ws(c, B, T);
+  h->launches = 0;
+  PG_TRY(prepare(h, s, w, B, T, lengths, pitch, sid));
+  PG_TRY(run_text_encoder(h, s, w, B, T, phone));
+  const int C = c.inter_channels;
+  float* z = at<float>(h, w.z);
+  PG_LAUNCH(h, launch_reparam(at<float>(h, w.stats), eps_zp, seed, at<int>(h, w.lens),
+                              at<float>(h, w.m_p), at<float>(h, w.logs_p), at<float>(h, w.z_p), z, B,
+                              T, C, s));
+  PG_TRY(run_flow(h, s, w, B, T, z));
+  float* source = at<float>(h, w.source);
+  PG_LAUNCH(h, launch_source(f0, eps_src, seed, h->src_w, h->src_b, at<double>(h, w.phase), source,
+                             nullptr, B, T, h->upp, c.sr, s));
+  ++h->launches;   // launch_source issues two kernels
+  PG_TRY(record_tap(h, s, "source", source, DT_F32, B, (int64_t)T * h->upp, 1));
+  PG_TRY(run_generator(h, s, w, B, T, z, source, wave));
+  if (aux) {
+    const size_t n = (size_t)B * T * C * sizeof(float);
+    char* a = reinterpret_cast<char*>(aux);
+    PG_CUDA_CHECK(cudaMemcpyAsync(a, z, n, cudaMemcpyDeviceToDevice, s));
+    PG_CUDA_CHECK(cudaMemcpyAsync(a + n, at<float>(h, w.z_p), n, cudaMemcpyDeviceToDevice, s));
+    PG_CUDA_CHECK(cudaMemcpyAsync(a + 2 * n, at<float>(h, w.m_p), n, cudaMemcpyDeviceToDevice, s));
+    PG_CUDA_CHECK(cudaMemcpyAsync(a + 3 * n, at<float>(h, w.logs_p), n, cudaMemcpyDeviceToDevice, s));
+  }
+  return PG_OK;
+}
+
+int pg_infer_host(pg_handle h, int B, int T, const float* phone, const int64_t* lengths,
+                  const int64_t* pitch, const float* f0, const int64_t* sid, uint64_t seed,
+                  float* wave) {
+  PG_TRY(check_ready(h, B, T));
+  if (!phone || !lengths || !pitch || !f0 || !sid || !wave)
+    return fail(PG_ERR_INVALID, "null tensor argument to pg_infer_host");
+  Guard g(h->device);
+  const pg_config& c = h->cfg;
+  const size_t BT = (size_t)B * T;
+  const size_t n_phone = BT * c.input_dim * sizeof(float), n_len = B * sizeof(int64_t),
+               n_pitch = BT * sizeof(int64_t), n_f0 = BT * sizeof(float), n_sid = B * sizeof(int64_t),
+               n_wave = BT * h->upp * sizeof(float);
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  const size_t total = al(n_phone) + al(n_len) + al(n_pitch) + al(n_f0) + al(n_sid) + al(n_wave);
+  if (h->host_stage.bytes < total) {
+    if (h->host_stage.p) PG_CUDA_CHECK(cudaFree(h->host_stage.p));
+    h->host_stage.p = nullptr;
+    h->host_stage.bytes = 0;
+    PG_CUDA_CHECK(cudaMalloc(&h->host_stage.p, total));
+    h->host_stage.bytes = total;
+  }
+  char* base = reinterpret_cast<char*>(h->host_stage.p);
+  float* d_phone = reinterpret_cast<float*>(base);
+  int64_t* d_len = reinterpret_cast<int64_t*>(base + al(n_phone));
+  int64_t* d_pitch = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(d_len) + al(n_len));
+  float* d_f0 = reinterpret_cast<float*>(reinterpret_cast<char*>(d_pitch) + al(n_pitch));
+  int64_t* d_sid = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(d_f0) + al(n_f0));
+  float* d_wave = reinterpret_cast<float*>(reinterpret_cast<char*>(d_sid) + al(n_sid));
+  cudaStream_t s = 0;
+  PG_CUDA_CHECK(cudaMemcpyAsync(d_phone, phone, n_phone, cudaMemcpyHostToDevice, s));
+  PG_CUDA_CHECK(cudaMemcpyAsync(d_len, lengths, n_len, cudaMemcpyHostToDevice, s));
+  PG_CUDA_CHECK(cudaMemcpyAsync(d_pitch, pitch, n_pitch, cudaMemcpyHostToDevice, s));
+  PG_CUDA_CHECK(cudaMemcpyAsync(d_f0, f0, n_f0, cudaMemcpyHostToDevice, s));
+  PG_CUDA_CHECK(cudaMemcpyAsync(d_sid, sid, n_sid, cudaMemcpyHostToDevice, s));
+  PG_TRY(pg_infer(h, s, B, T, d_phone, d_len, d_pitch, d_f0, d_sid, nullptr, nullptr, seed, d_wave,
+                  nullptr));
+  PG_CUDA_CHECK(cudaMemcpyAsync(wave, d_wave, n_wave, cudaMemcpyDeviceToHost, s));
+  PG_CUDA_CHECK(cudaStreamSynchronize(s));
+  return PG_OK;
+}
+
+int pg_text_encoder(pg_handle h, void* stream, int B, int T, const float* phone,
+                    const int64_t* lengths, const int64_t* pitch, float* m_p, float* logs_p) {
+  PG_TRY(check_ready(h, B, T));
+  if (!phone || !lengths || !pitch || !m_p || !logs_p) return fail(PG_ERR_INVALID, "null argument");
+  Guard g(h->device);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const Ws w = plan_ws(h->cfg, B, T);
+  h->launches = 0;
+  PG_TRY(prepare(h, s, w, B, T, lengths, pitch, nullptr));
+  PG_TRY(run_text_encoder(h, s, w, B, T, phone));
+  // split stats with eps == 0: z_p/z are scratch
+  PG_CUDA_CHECK(cudaMemsetAsync(at<float>(h, w.fa), 0, sizeof(float) * (size_t)B * T * h->cfg.inter_channels, s));
+  PG_LAUNCH(h, launch_reparam(at<float>(h, w.stats), at<float>(h, w.fa), 0, at<int>(h, w.lens), m_p,
+                              logs_p, at<float>(h, w.z_p), at<float>(h, w.z), B, T,
+                              h->cfg.inter_channels, s));
+  return PG_OK;
+}
+
+int pg_flow_reverse(pg_handle h, void* stream, int B, int T, const float* z_p,
+                    const int64_t* lengths, const int64_t* sid, float* z) {
+  PG_TRY(check_ready(h, B, T));
+  if (!z_p || !lengths || !sid || !z) return fail(PG_ERR_INVALID, "null argument");
+  Guard g(h->device);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const Ws w = plan_ws(h->cfg, B, T);
+  h->launches = 0;
+  PG_TRY(prepare(h, s, w, B, T, lengths, nullptr, sid));
+  const size_t n = sizeof(float) * (size_t)B * T * h->cfg.inter_channels;
+  if (z != z_p) PG_CUDA_CHECK(cudaMemcpyAsync(z, z_p, n, cudaMemcpyDeviceToDevice, s));
+  PG_TRY(run_flow(h, s, w, B, T, z));
+  return PG_OK;
+}
+
+int pg_source(pg_handle h, void* stream, int B, int T, const float* f0, const float* eps_src,
+              uint64_t seed, float* source, float* sine) {
+  PG_TRY(check_ready(h, B, T));
+  if (!f0 || !source) return fail(PG_ERR_INVALID, "null argument");
+  Guard g(h->device);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const Ws w = plan_ws(h->cfg, B, T);
+  h->launches = 0;
+  PG_TRY(ensure_ws(h, w.total));
+  PG_LAUNCH(h, launch_source(f0, eps_src, seed, h->src_w, h->src_b, at<double>(h, w.phase), source,
+                             sine, B, T, h->upp, h->cfg.sr, s));
+  ++h->launches;
+  return PG_OK;
+}
+
+int pg_generator(pg_handle h, void* stream, int B, int T, const float* z, const float* source,
+                 const int64_t* sid, float* wave) {
+  PG_TRY(check_ready(h, B, T));
+  if (!z || !source || !sid || !wave) return fail(PG_ERR_INVALID, "null argument");
+  Guard g(h->device);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const Ws w = plan_ws(h->cfg, B, T);
+  h->launches = 0;
+  PG_TRY(ensure_ws(h, w.total));
+  // the generator ignores x_mask after its input: all rows valid
+  std::vector<int64_t> full(B, T);
+  int64_t* d_len = reinterpret_cast<int64_t*>(at<char>(h, w.qkv));
+  PG_CUDA_CHECK(cudaMemcpyAsync(d_len, full.data(), sizeof(int64_t) * B, cudaMemcpyHostToDevice, s));
+  PG_CUDA_CHECK(cudaStreamSynchronize(s));
+  PG_LAUNCH(h, launch_prepare_ints(d_len, nullptr, sid, at<int>(h, w.lens), at<int>(h, w.pitch),
+                                   at<int>(h, w.sid), B, T, h->cfg.spk_embed_dim, s));
+  PG_TRY(run_generator(h, s, w, B, T, z, source, wave));
+  return PG_OK;
+}
+
+int64_t pg_debug_fetch(pg_handle h, void* stream, const char* tap, float* dst, int64_t capacity,
+                       int64_t* shape_out) {
+  if (!h || !tap) return fail(PG_ERR_INVALID, "null argument");
+  Guard g(h->device);
+  auto it = h->taps.find(tap);
+  if (it == h->taps.end())
+    return fail(PG_ERR_INVALID, std::string("unknown tap (was the handle created with flag 2?): ") + tap);
+  const Tap& t = it->second;
+  const int64_t n = t.shape[0] * t.shape[1] * t.shape[2];
+  if (shape_out) {
+    shape_out[0] = t.shape[0];
+    shape_out[1] = t.shape[1];
+    shape_out[2] = t.shape[2];
+  }
+  if (!dst) return n;
+  if (capacity < n) return fail(PG_ERR_INVALID, "destination too small");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (t.dtype == DT_F16) {
+    cudaError_t e = launch_cast_f16_to_f32(reinterpret_cast<const __half*>(t.p), dst, n, s);
+    if (e != cudaSuccess) return fail(PG_ERR_CUDA, cudaGetErrorString(e));
+  } else {
+    PG_CUDA_CHECK(cudaMemcpyAsync(dst, t.p, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  return n;
+}
+
+int64_t pg_launch_count(pg_handle h) { return h ? h->launches : 0; }
+
+int pg_destroy(pg_handle h) {
+  if (!h) return PG_OK;
+  Guard g(h->device);
+  for (void* p : h->dev_allocs) cudaFree(p);
+  for (auto& kv : h->taps)
+    if (kv.second.p) cudaFree(kv.second.p);
+  if (h->ws.p) cudaFree(h->ws.p);
+  if (h->host_stage.p) cudaFree(h->host_stage.p);
+  delete h;
+  return PG_OK;
+}
+
+// Single conv layer on f16 activations: op-level parity tests + micro-benchmarks.
+int pg_op_conv1d_f16(int device, int impl, int B, int L, int Cin, int Cout, int K, int dil,
+                     const void* x_dev, const float* w_host, const float* bias_host, float in_slope,
+                     float out_slope, const void* res_dev, void* y_dev, int iters, float* ms_out) {
+  if (!x_dev || !w_host || !y_dev || B <= 0 || L <= 0) return fail(PG_ERR_INVALID, "bad argument");
+  Guard g(device);
+  std::vector<float> w((size_t)K * Cin * Cout);
+  std::vector<__half> w16(w.size());
+  for (int co = 0; co < Cout; ++co)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int k = 0; k < K; ++k) {
+        const float v = w_host[((size_t)co * Cin + ci) * K + k];
+        w[((size_t)k * Cin + ci) * Cout + co] = v;
+        w16[((size_t)k * Cout + co) * Cin + ci] = __float2half_rn(v);
+      }
+  float *d_w = nullptr, *d_b = nullptr;
+  __half* d_w16 = nullptr;
+  PG_CUDA_CHECK(cudaMalloc(&d_w, w.size() * sizeof(float)));
+  PG_CUDA_CHECK(cudaMalloc(&d_w16, w16.size() * sizeof(__half)));
+  PG_CUDA_CHECK(cudaMemcpy(d_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+  PG_CUDA_CHECK(cudaMemcpy(d_w16, w16.data(), w16.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  if (bias_host) {
+    PG_CUDA_CHECK(cudaMalloc(&d_b, Cout * sizeof(float)));
+    PG_CUDA_CHECK(cudaMemcpy(d_b, bias_host, Cout * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  ConvArgs a;
+  a.x = x_dev; a.x_ld = Cin; a.B = B; a.L_in = L; a.L_out = L;
+  a.Cin = Cin; a.Cout = Cout; a.K = K; a.dil = dil; a.pad = (K * dil - dil) / 2;
+  a.w = d_w; a.w16 = d_w16; a.bias = d_b;
+  a.in_slope = in_slope;
+  if (out_slope != 1.f) { a.act = ACT_LRELU; a.out_slope = out_slope; }
+  a.res = res_dev; a.res_ld = Cout;
+  a.y = y_dev; a.y_ld = Cout;
+  int rc = PG_OK;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  if (impl == 1 && !umma_conv_supported(a)) {
+    rc = fail(PG_ERR_UNSUPPORTED, "shape not supported by the tcgen05 conv");
+  } else {
+    cudaEventRecord(e0, 0);
+    cudaError_t e = cudaSuccess;
+    for (int it = 0; it < (iters > 0 ? iters : 1) && e == cudaSuccess; ++it)
+      e = impl == 1 ? launch_conv_umma(a, 0) : launch_conv_simt(a, DT_F16, DT_F16, 0);
+    cudaEventRecord(e1, 0);
+    cudaError_t e2 = cudaDeviceSynchronize();
+    if (e != cudaSuccess || e2 != cudaSuccess)
+      rc = fail(PG_ERR_CUDA, std::string("conv launch: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+    else if (ms_out)
+      cudaEventElapsedTime(ms_out, e0, e1);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_w);
+  cudaFree(d_w16);
+  if (d_b) cudaFree(d_b);
+  return rc;
+}
+
+}  // extern "C"

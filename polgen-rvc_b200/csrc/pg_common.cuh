@@ -1,0 +1,90 @@
+// Shared declarations of the polgen-rvc_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace pg {
+
+// thread-local error string behind pg_last_error()
+void set_error(const std::string& msg);
+
+#define PG_CUDA_CHECK(expr)                                                         \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      ::pg::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+      return PG_ERR_CUDA;                                                           \
+    }                                                                               \
+  } while (0)
+
+enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_TANH = 3 };
+
+// One conv / GEMM layer over time-major activations.
+//   in row (b, t + tap*dil - pad), channel x_coff + ci, row pitch x_ld elements
+//   y = acc_old*accumulate + out_scale * (sum + bias[co] + bbias[b][co] + res_scale*res)
+//   then activation, then row mask (t < lens[b]).
+struct ConvArgs {
+  const void* x = nullptr; int x_ld = 0; int x_coff = 0;
+  int B = 0, L_in = 0, L_out = 0;
+  int Cin = 0, Cout = 0, K = 1, dil = 1, pad = 0;
+  const float* w = nullptr;          // SIMT: [K][Cin][Cout] f32
+  const void* w16 = nullptr;         // UMMA: [K][Cout][Cin] f16 (K-major tiles)
+  const float* bias = nullptr;       // [Cout]
+  const float* bbias = nullptr; int bbias_ld = 0;   // [B][bbias_ld]
+  float in_slope = 1.f; int in_mask = 0;
+  const int* lens = nullptr;         // [B] valid rows (frames) for in_mask/out_mask
+  int act = ACT_NONE; float out_slope = 1.f; int out_mask = 0;
+  const void* res = nullptr; int res_ld = 0; int res_coff = 0; float res_scale = 1.f;
+  void* y = nullptr; int y_ld = 0; int y_coff = 0;
+  int accumulate = 0; float out_scale = 1.f;
+};
+
+enum DType : int { DT_F32 = 0, DT_F16 = 1 };
+
+// ---- launchers (each returns cudaGetLastError()) --------------------------
+cudaError_t launch_conv_simt(const ConvArgs& a, DType in_dt, DType out_dt, cudaStream_t s);
+
+// tcgen05 implicit-GEMM conv over f16 activations (pg_conv_umma.cu).
+bool umma_conv_supported(const ConvArgs& a);
+cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s);
+
+cudaError_t launch_prepare_ints(const int64_t* lengths, const int64_t* pitch, const int64_t* sid,
+                                int* lens32, int* pitch32, int* sid32, int B, int T, int n_spk,
+                                cudaStream_t s);
+// y[b][n] = bias[n] + sum_k w[n][k] * emb[sid[b]][k]
+cudaError_t launch_cond_gemv(const float* emb, const int* sid, const float* w, const float* bias,
+                             float* y, int B, int Kdim, int N, cudaStream_t s);
+// x = lrelu((x + emb_pitch[pitch]) * scale, 0.1) * mask
+cudaError_t launch_embed_finish(float* x, const float* emb_pitch, const int* pitch, const int* lens,
+                                int B, int T, int H, float scale, cudaStream_t s);
+// x = LayerNorm_c(x + y) * (final_mask ? mask : 1)
+cudaError_t launch_add_layernorm(float* x, const float* y, const float* gamma, const float* beta,
+                                 int rows, int H, cudaStream_t s);
+// relative-position windowed attention; qkv [B][T][3H] -> out [B][T][H]
+cudaError_t launch_rel_attention(const float* qkv, const float* rel_k, const float* rel_v,
+                                 const int* lens, float* out, int B, int T, int H, int n_heads,
+                                 int window, cudaStream_t s);
+// z_p = (m + exp(logs) * eps * 0.66666) * mask ; stats [B][T][2C] -> m, logs, z_p, z(copy)
+cudaError_t launch_reparam(const float* stats, const float* eps, uint64_t seed, const int* lens,
+                           float* m_p, float* logs_p, float* z_p, float* z, int B, int T, int C,
+                           cudaStream_t s);
+// acts = tanh(a[:, :H]) * sigmoid(a[:, H:])
+cudaError_t launch_gate(const float* a, float* acts, int64_t rows, int H, cudaStream_t s);
+
+// harmonic source (pg_source.cu)
+cudaError_t launch_source(const float* f0, const float* eps, uint64_t seed, float lin_w, float lin_b,
+                          double* frame_phase, float* source, float* sine, int B, int T, int upp,
+                          int sr, cudaStream_t s);
+// x[b][t][c] += bn[c] + sum_j wn[c][j] * src[b][t*stride + j - pad]
+cudaError_t launch_noise_inject(__half* x, const float* src, const float* wn, const float* bn,
+                                int B, int L, int C, int Lsrc, int k, int stride, int pad,
+                                cudaStream_t s);
+// wave = tanh(conv_post(lrelu(x, 0.01)))
+cudaError_t launch_conv_post(const __half* x, const float* w /*[K][C]*/, float* wave, int B, int L,
+                             int C, int K, float in_slope, cudaStream_t s);
+cudaError_t launch_cast_f16_to_f32(const __half* x, float* y, int64_t n, cudaStream_t s);
+
+}  // namespace pg

@@ -1,0 +1,456 @@
+"""Drop-in host class for the reference ``Synthesizer``.
+
+Mirrors ``rvc/lib/algorithm/synthesizers.py:13-188`` at the module-object
+boundary the callers use:
+
+* ``Synthesizer(*cpt["config"], use_f0=..., input_dim=..., is_half=...)``
+  (``rvc/infer/infer.py:92-97``)
+* ``del net_g.enc_q``; ``load_state_dict(cpt["weight"], strict=False)``;
+  ``.eval().to(device)``; ``.half()`` / ``.float()`` (``infer.py:99-102``)
+* ``net_g.infer(feats, p_len, pitch, pitchf, sid)`` ->
+  ``(o, x_mask, (z, z_p, m_p, logs_p))`` (``rvc/infer/pipeline.py:275``)
+
+The torch modules below only HOLD parameters under the reference's state-dict
+names (legacy ``weight_g/weight_v`` checkpoints load through torch's
+weight-norm compat hook); none of their ``forward`` methods is ever called.
+All compute goes through the C ABI (``include/polgen_rvc.h``) into the
+hand-written sm_100a kernels.  There is no CPU path: ``infer`` on a non-CUDA
+tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+from torch.nn.utils.parametrizations import weight_norm
+
+from . import _lib
+from .configs import SynthConfig, config_from_ctor
+
+
+# --------------------------------------------------------------------------
+# weight-norm fold (done once at load; the reference recomputes it every
+# forward because remove_weight_norm is never called -- SURVEY.md K12)
+# --------------------------------------------------------------------------
+def fold_state_dict(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Return plain fp32 ``<module>.weight`` tensors: w = g * v / ||v|| with the
+    norm over every dim but 0 (Cout for Conv1d, Cin for ConvTranspose1d)."""
+    g_sfx = (".weight_g", ".parametrizations.weight.original0")
+    v_sfx = (".weight_v", ".parametrizations.weight.original1")
+    out: Dict[str, torch.Tensor] = {}
+    for key, val in sd.items():
+        if key.endswith(g_sfx):
+            continue
+        hit = next((i for i, s in enumerate(v_sfx) if key.endswith(s)), None)
+        if hit is None:
+            out[key] = val.detach().to("cpu", torch.float32).contiguous()
+            continue
+        base = key[: -len(v_sfx[hit])]
+        v = val.detach().to("cpu", torch.float32)
+        g = sd[base + g_sfx[hit]].detach().to("cpu", torch.float32)
+        flat = v.reshape(v.shape[0], -1)
+        scale = g.reshape(-1) / flat.norm(dim=1)
+        out[base + ".weight"] = (flat * scale[:, None]).reshape(v.shape).contiguous()
+    return out
+
+
+# --------------------------------------------------------------------------
+# Engine: one C-ABI handle on one GPU
+# --------------------------------------------------------------------------
+class Engine:
+    """Owns a ``pg_handle``.  ``weights`` is a folded fp32 CPU state dict."""
+
+    def __init__(self, cfg: SynthConfig, weights: Dict[str, torch.Tensor], device: int = 0,
+                 flags: int = 0):
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = int(device)
+        self._h = C.c_void_p()
+        pc = _lib.make_config(cfg, flags)
+        _lib.check(self.lib.pg_create(C.byref(pc), self.device, C.byref(self._h)), "pg_create")
+        try:
+            for name, t in weights.items():
+                if name.startswith("enc_q."):
+                    continue
+                t = t.detach().to("cpu", torch.float32).contiguous()
+                shape = (C.c_int64 * max(1, t.dim()))(*t.shape)
+                _lib.check(self.lib.pg_load_tensor(self._h, name.encode(), C.c_void_p(t.data_ptr()),
+                                                   shape, t.dim(), _lib.PG_F32), f"pg_load_tensor({name})")
+            _lib.check(self.lib.pg_finalize(self._h), "pg_finalize")
+        except Exception:
+            self.close()
+            raise
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.pg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        return C.c_void_p(0 if t is None else t.data_ptr())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self):
+        return torch.device("cuda", self.device)
+
+    def workspace_bytes(self, B: int, T: int) -> int:
+        return int(self.lib.pg_workspace_bytes(self._h, B, T))
+
+    def launch_count(self) -> int:
+        return int(self.lib.pg_launch_count(self._h))
+
+    def infer(self, phone, lengths, pitch, f0, sid, eps_zp=None, eps_src=None, seed: int = 0,
+              want_aux: bool = True):
+        """Time-major tensors on this engine's GPU.  Returns (wave [B][L], aux [4][B][T][C] | None)."""
+        B, T, _ = phone.shape
+        dev = self._dev()
+        wave = torch.empty(B, T * self.cfg.upp, device=dev, dtype=torch.float32)
+        aux = torch.empty(4, B, T, self.cfg.inter_channels, device=dev, dtype=torch.float32) if want_aux else None
+        _lib.check(self.lib.pg_infer(self._h, self._stream(), B, T, self._ptr(phone), self._ptr(lengths),
+                                     self._ptr(pitch), self._ptr(f0), self._ptr(sid), self._ptr(eps_zp),
+                                     self._ptr(eps_src), C.c_uint64(seed & (2 ** 64 - 1)), self._ptr(wave),
+                                     self._ptr(aux)), "pg_infer")
+        return wave, aux
+
+    def infer_host(self, phone, lengths, pitch, f0, sid, wave_out, seed: int = 0):
+        """Host (pinned) tensors in, host waveform out; H2D/D2H inside the call."""
+        B, T, _ = phone.shape
+        _lib.check(self.lib.pg_infer_host(self._h, B, T, self._ptr(phone), self._ptr(lengths),
+                                          self._ptr(pitch), self._ptr(f0), self._ptr(sid),
+                                          C.c_uint64(seed & (2 ** 64 - 1)), self._ptr(wave_out)),
+                   "pg_infer_host")
+        return wave_out
+
+    def text_encoder(self, phone, lengths, pitch):
+        B, T, _ = phone.shape
+        m_p = torch.empty(B, T, self.cfg.inter_channels, device=self._dev(), dtype=torch.float32)
+        logs_p = torch.empty_like(m_p)
+        _lib.check(self.lib.pg_text_encoder(self._h, self._stream(), B, T, self._ptr(phone),
+                                            self._ptr(lengths), self._ptr(pitch), self._ptr(m_p),
+                                            self._ptr(logs_p)), "pg_text_encoder")
+        return m_p, logs_p
+
+    def flow_reverse(self, z_p, lengths, sid):
+        B, T, _ = z_p.shape
+        z = torch.empty_like(z_p)
+        _lib.check(self.lib.pg_flow_reverse(self._h, self._stream(), B, T, self._ptr(z_p),
+                                            self._ptr(lengths), self._ptr(sid), self._ptr(z)),
+                   "pg_flow_reverse")
+        return z
+
+    def source(self, f0, eps_src=None, seed: int = 0, want_sine: bool = False):
+        B, T = f0.shape
+        src = torch.empty(B, T * self.cfg.upp, device=self._dev(), dtype=torch.float32)
+        sine = torch.empty_like(src) if want_sine else None
+        _lib.check(self.lib.pg_source(self._h, self._stream(), B, T, self._ptr(f0), self._ptr(eps_src),
+                                      C.c_uint64(seed & (2 ** 64 - 1)), self._ptr(src), self._ptr(sine)),
+                   "pg_source")
+        return src, sine
+
+    def generator(self, z, source, sid):
+        B, T, _ = z.shape
+        wave = torch.empty(B, T * self.cfg.upp, device=self._dev(), dtype=torch.float32)
+        _lib.check(self.lib.pg_generator(self._h, self._stream(), B, T, self._ptr(z), self._ptr(source),
+                                         self._ptr(sid), self._ptr(wave)), "pg_generator")
+        return wave
+
+    def fetch_tap(self, name: str) -> torch.Tensor:
+        shape = (C.c_int64 * 3)()
+        n = self.lib.pg_debug_fetch(self._h, self._stream(), name.encode(), None, 0, shape)
+        if n < 0:
+            _lib.check(int(n), f"pg_debug_fetch({name})")
+        out = torch.empty(tuple(int(s) for s in shape), device=self._dev(), dtype=torch.float32)
+        n = self.lib.pg_debug_fetch(self._h, self._stream(), name.encode(), self._ptr(out), out.numel(), shape)
+        if n < 0:
+            _lib.check(int(n), f"pg_debug_fetch({name})")
+        return out
+
+
+# --------------------------------------------------------------------------
+# parameter containers (names == the reference's state-dict keys)
+# --------------------------------------------------------------------------
+def _normal_(m: nn.Module, std: float = 0.01):
+    # commons.py:7-10 init_weights
+    m.weight.data.normal_(0.0, std)
+
+
+class _Holder(nn.Module):
+    def forward(self, *a, **k):   # pragma: no cover
+        raise RuntimeError("parameter container: compute runs in the CUDA library")
+
+
+def _attn(H: int, heads: int, window: int) -> nn.Module:
+    m = _Holder()
+    for n in "qkvo":
+        setattr(m, f"conv_{n}", nn.Conv1d(H, H, 1))
+    d = H // heads
+    m.emb_rel_k = nn.Parameter(torch.randn(1, 2 * window + 1, d) * d ** -0.5)
+    m.emb_rel_v = nn.Parameter(torch.randn(1, 2 * window + 1, d) * d ** -0.5)
+    for n in "qkv":
+        nn.init.xavier_uniform_(getattr(m, f"conv_{n}").weight)
+    return m
+
+
+def _ln(H: int) -> nn.Module:
+    m = _Holder()
+    m.gamma = nn.Parameter(torch.ones(H))
+    m.beta = nn.Parameter(torch.zeros(H))
+    return m
+
+
+def _text_encoder(cfg: SynthConfig) -> nn.Module:
+    H, F = cfg.hidden_channels, cfg.filter_channels
+    enc = _Holder()
+    enc.attn_layers = nn.ModuleList(_attn(H, cfg.n_heads, cfg.attn_window) for _ in range(cfg.n_layers))
+    enc.norm_layers_1 = nn.ModuleList(_ln(H) for _ in range(cfg.n_layers))
+    ffn = []
+    for _ in range(cfg.n_layers):
+        f = _Holder()
+        f.conv_1 = nn.Conv1d(H, F, cfg.kernel_size)
+        f.conv_2 = nn.Conv1d(F, H, cfg.kernel_size)
+        ffn.append(f)
+    enc.ffn_layers = nn.ModuleList(ffn)
+    enc.norm_layers_2 = nn.ModuleList(_ln(H) for _ in range(cfg.n_layers))
+    te = _Holder()
+    te.emb_phone = nn.Linear(cfg.input_dim, H)
+    te.emb_pitch = nn.Embedding(256, H)
+    te.encoder = enc
+    te.proj = nn.Conv1d(H, 2 * cfg.inter_channels, 1)
+    return te
+
+
+def _flow(cfg: SynthConfig) -> nn.Module:
+    H, half = cfg.hidden_channels, cfg.inter_channels // 2
+    nl, kw = cfg.flow_wn_layers, cfg.flow_wn_kernel
+    mods = []
+    for _ in range(cfg.flow_n_flows):
+        wn = _Holder()
+        # registration order follows modules.py:28-56 so state_dict() key order matches too
+        wn.in_layers = nn.ModuleList()
+        wn.res_skip_layers = nn.ModuleList()
+        wn.cond_layer = weight_norm(nn.Conv1d(cfg.gin_channels, 2 * H * nl, 1), name="weight")
+        for l in range(nl):
+            wn.in_layers.append(weight_norm(nn.Conv1d(H, 2 * H, kw, padding=(kw - 1) // 2), name="weight"))
+            wn.res_skip_layers.append(
+                weight_norm(nn.Conv1d(H, H if l == nl - 1 else 2 * H, 1), name="weight"))
+        rcl = _Holder()
+        rcl.pre = nn.Conv1d(half, H, 1)
+        rcl.enc = wn
+        rcl.post = nn.Conv1d(H, half, 1)
+        rcl.post.weight.data.zero_()     # residuals.py:207-208
+        rcl.post.bias.data.zero_()
+        mods += [rcl, _Holder()]          # coupling layer, Flip (no parameters)
+    f = _Holder()
+    f.flows = nn.ModuleList(mods)
+    return f
+
+
+def _decoder(cfg: SynthConfig) -> nn.Module:
+    dec = _Holder()
+    dec.m_source = _Holder()
+    dec.m_source.l_linear = nn.Linear(1, 1)
+    c0 = cfg.upsample_initial_channel
+    dec.conv_pre = nn.Conv1d(cfg.inter_channels, c0, 7, 1, padding=3)
+    ups, noise, blocks = [], [], []
+    cin = c0
+    strides = cfg.noise_strides()
+    for i, (u, k) in enumerate(zip(cfg.upsample_rates, cfg.upsample_kernel_sizes)):
+        cout = cin // 2
+        up = nn.ConvTranspose1d(cin, cout, k, u, padding=(k - u) // 2)
+        _normal_(up)
+        ups.append(weight_norm(up))
+        s = strides[i]
+        noise.append(nn.Conv1d(1, cout, kernel_size=(2 * s if s > 1 else 1), stride=s,
+                               padding=(s // 2 if s > 1 else 0)))
+        for ksz, dils in zip(cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes):
+            rb = _Holder()
+            c1, c2 = [], []
+            for d in dils:
+                a = nn.Conv1d(cout, cout, ksz, 1, dilation=d, padding=(ksz * d - d) // 2)
+                b = nn.Conv1d(cout, cout, ksz, 1, dilation=1, padding=(ksz - 1) // 2)
+                _normal_(a)
+                _normal_(b)
+                c1.append(weight_norm(a))
+                c2.append(weight_norm(b))
+            rb.convs1 = nn.ModuleList(c1)
+            rb.convs2 = nn.ModuleList(c2)
+            blocks.append(rb)
+        cin = cout
+    dec.ups = nn.ModuleList(ups)
+    dec.noise_convs = nn.ModuleList(noise)
+    dec.resblocks = nn.ModuleList(blocks)
+    dec.conv_post = nn.Conv1d(cin, 1, 7, 1, padding=3, bias=False)
+    dec.cond = nn.Conv1d(cfg.gin_channels, c0, 1)
+    dec.upp = cfg.upp
+    return dec
+
+
+class Synthesizer(nn.Module):
+    """B200-native drop-in for ``rvc.lib.algorithm.synthesizers.Synthesizer``."""
+
+    def __init__(self, spec_channels, segment_size, inter_channels, hidden_channels, filter_channels,
+                 n_heads, n_layers, kernel_size, p_dropout, resblock, resblock_kernel_sizes,
+                 resblock_dilation_sizes, upsample_rates, upsample_initial_channel,
+                 upsample_kernel_sizes, spk_embed_dim, gin_channels, sr, use_f0, input_dim=768,
+                 **kwargs):
+        super().__init__()
+        if not use_f0:
+            # the reference's non-F0 Generator has no forward (generators.py:57) and
+            # pipeline.py:282 passes sid in the pitch slot: nothing to be compatible with
+            raise NotImplementedError("only the F0 (NSF) synthesizer is supported")
+        if "is_half" not in kwargs:
+            raise KeyError("is_half")   # synthesizers.py:81 reads kwargs["is_half"]
+        if str(resblock) != "1":
+            raise NotImplementedError("only resblock='1' (ResBlock1) is supported")
+        self.is_half = bool(kwargs["is_half"])
+        args = [spec_channels, segment_size, inter_channels, hidden_channels, filter_channels, n_heads,
+                n_layers, kernel_size, p_dropout, resblock, resblock_kernel_sizes,
+                resblock_dilation_sizes, upsample_rates, upsample_initial_channel,
+                upsample_kernel_sizes, spk_embed_dim, gin_channels, sr]
+        self.cfg = config_from_ctor(args, input_dim=input_dim)
+        # the attributes the reference exposes
+        self.spec_channels = spec_channels
+        self.inter_channels = inter_channels
+        self.hidden_channels = hidden_channels
+        self.filter_channels = filter_channels
+        self.n_heads = n_heads
+        self.n_layers = n_layers
+        self.kernel_size = kernel_size
+        self.p_dropout = float(p_dropout)
+        self.resblock = resblock
+        self.resblock_kernel_sizes = resblock_kernel_sizes
+        self.resblock_dilation_sizes = resblock_dilation_sizes
+        self.upsample_rates = upsample_rates
+        self.upsample_initial_channel = upsample_initial_channel
+        self.upsample_kernel_sizes = upsample_kernel_sizes
+        self.segment_size = segment_size
+        self.gin_channels = gin_channels
+        self.spk_embed_dim = spk_embed_dim
+        self.use_f0 = use_f0
+
+        self.enc_p = _text_encoder(self.cfg)
+        self.dec = _decoder(self.cfg)
+        self.enc_q = _Holder()            # training-only posterior encoder; callers `del` it (infer.py:99)
+        self.flow = _flow(self.cfg)
+        self.emb_g = nn.Embedding(self.spk_embed_dim, gin_channels)
+        self._engine: Optional[Engine] = None
+        self._engine_flags = 0
+
+    # -- weight lifecycle: any change to the parameters drops the device copy --
+    def _invalidate(self):
+        eng = self.__dict__.get("_engine")
+        if eng is not None:
+            eng.close()
+        self.__dict__["_engine"] = None
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        self._invalidate()
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
+
+    def _apply(self, fn, recurse=True):
+        self._invalidate()
+        return super()._apply(fn, recurse)
+
+    def remove_weight_norm(self):
+        """The reference's version raises on the inference path; here the fold
+        happens when the weights are uploaded, so this is a no-op."""
+        return self
+
+    def _device_index(self) -> int:
+        p = self.emb_g.weight
+        if p.device.type != "cuda":
+            raise RuntimeError("polgen-rvc_b200 Synthesizer runs on CUDA (sm_100a) only: move the module "
+                               "with .to('cuda') -- there is no CPU path")
+        return p.device.index if p.device.index is not None else torch.cuda.current_device()
+
+    def engine(self) -> Engine:
+        if self._engine is None:
+            dev = self._device_index()
+            self.__dict__["_engine"] = Engine(self.cfg, fold_state_dict(self.state_dict()), dev,
+                                              self._engine_flags)
+        return self._engine
+
+    @torch.jit.ignore
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("training forward is out of scope (synthesizers.py:136-160)")
+
+    @torch.no_grad()
+    def infer(self, phone: torch.Tensor, phone_lengths: torch.Tensor, pitch: Optional[torch.Tensor] = None,
+              nsff0: Optional[torch.Tensor] = None, sid: torch.Tensor = None,
+              rate: Optional[torch.Tensor] = None, *, eps_zp: Optional[torch.Tensor] = None,
+              eps_src: Optional[torch.Tensor] = None):
+        """``synthesizers.py:162-188``.  ``eps_zp`` (B, C, T) / ``eps_src`` (B, T*upp, 1) replace the two
+        in-path ``randn_like`` draws (parity tests); otherwise noise is drawn on device from Philox
+        seeded by torch's CPU generator."""
+        if pitch is None or nsff0 is None or sid is None:
+            raise ValueError("pitch, nsff0 and sid are required (F0 synthesizer)")
+        if not phone.is_cuda:
+            raise RuntimeError("polgen-rvc_b200 has no CPU path: pass CUDA tensors")
+        eng = self.engine()
+        out_dtype = phone.dtype
+        dev = phone.device
+        B, T, _ = phone.shape
+        phone32 = phone.to(torch.float32).contiguous()
+        lengths = phone_lengths.to(dev, torch.int64).contiguous()
+        pitch64 = pitch.to(dev, torch.int64).contiguous()
+        f0 = nsff0.to(dev, torch.float32).contiguous()
+        sid64 = sid.to(dev, torch.int64).reshape(-1).contiguous()
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        C_ = self.cfg.inter_channels
+        if rate is None:
+            ez = None if eps_zp is None else eps_zp.to(dev, torch.float32).transpose(1, 2).contiguous()
+            es = None if eps_src is None else eps_src.to(dev, torch.float32).reshape(B, -1).contiguous()
+            wave, aux = eng.infer(phone32, lengths, pitch64, f0, sid64, ez, es, seed)
+            z, z_p, m_p, logs_p = (aux[i].transpose(1, 2) for i in range(4))
+            Tm = T
+        else:
+            # synthesizers.py:175-181: drop the head of the latent before the flow
+            assert isinstance(rate, torch.Tensor)
+            m_t, logs_t = eng.text_encoder(phone32, lengths, pitch64)
+            mask_t = (torch.arange(T, device=dev)[None, :] < lengths[:, None]).to(torch.float32)[:, :, None]
+            e = torch.randn_like(m_t) if eps_zp is None else eps_zp.to(dev, torch.float32).transpose(1, 2)
+            zp_t = (m_t + torch.exp(logs_t) * e * 0.66666) * mask_t
+            head = int(T * (1.0 - rate.item()))
+            zp_t = zp_t[:, head:].contiguous()
+            f0 = f0[:, head:].contiguous()
+            Tm = T - head
+            # the flow/decoder mask is the sliced x_mask: rows keep length - head valid frames
+            len2 = (lengths - head).clamp(min=0)
+            z_t = eng.flow_reverse(zp_t, len2, sid64)
+            es = None if eps_src is None else eps_src.to(dev, torch.float32).reshape(B, -1).contiguous()
+            src, _ = eng.source(f0, es, seed)
+            m2 = (torch.arange(Tm, device=dev)[None, :] < len2[:, None]).to(torch.float32)[:, :, None]
+            wave = eng.generator((z_t * m2).contiguous(), src, sid64)
+            z, z_p = z_t.transpose(1, 2), zp_t.transpose(1, 2)
+            m_p, logs_p = m_t.transpose(1, 2), logs_t.transpose(1, 2)
+            lengths = len2
+        x_mask = (torch.arange(Tm, device=dev)[None, :] < lengths[:, None]).to(out_dtype)[:, None, :]
+        o = wave[:, None, :].to(out_dtype)
+        return o, x_mask, (z.to(out_dtype), z_p.to(out_dtype), m_p.to(out_dtype), logs_p.to(out_dtype))
+
+
+# upstream-RVC class names (BASELINE.json north_star): thin aliases that pin input_dim
+class SynthesizerTrnMs768NSFsid(Synthesizer):
+    def __init__(self, *args, **kwargs):
+        kwargs.setdefault("use_f0", 1)
+        kwargs["input_dim"] = 768
+        super().__init__(*args, **kwargs)
+
+
+class SynthesizerTrnMs256NSFsid(Synthesizer):
+    def __init__(self, *args, **kwargs):
+        kwargs.setdefault("use_f0", 1)
+        kwargs["input_dim"] = 256
+        super().__init__(*args, **kwargs)
