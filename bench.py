@@ -1,0 +1,294 @@
+"""Benchmark of the RVC synthesizer decode hot path (Synthesizer.infer).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config v2-48k]
+
+Metric (BASELINE.json): audio-seconds synthesized per second at the model's native rate.
+
+Workload (BASELINE.json configs[1]): RVC v2 48 kHz decode of one 60 s clip, cut by the
+pipeline's silence split (x_pad, x_query, x_center, x_max = 1, 6, 38, 41 s --
+rvc/infer/infer.py:41-45, rvc/infer/pipeline.py:330-348) into overlapping segments; one "step"
+decodes every segment of the clip (B = 1 per segment, as pipeline.py:381-447 does).  Synthetic
+features (phone ~ N(0,1), log-swept F0 with an unvoiced gap) and random-init weights of the named
+architecture.  With --gpus N every rank decodes its own clip per step (segments are independent:
+weak scaling, no collective in the decode); value = audio-seconds of all ranks / max-over-ranks
+device time.
+
+--impl reference times the reference algorithm's CPU path (the oracle port of
+Synthesizer.infer: the same torch fp32 ATen conv kernels the reference dispatches to) on the
+box's host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "audio-seconds synthesized/sec @48 kHz (1/2/4/8 B200) vs host-CPU reference"
+UNIT = "audio-s/s"
+CLIP_SECONDS = 60
+
+
+def clip_segments(cfg, seed=0):
+    """60 s synthetic clip -> the frame counts of its silence-split segments (incl. x_pad overlap)."""
+    import numpy as np
+    from polgen_rvc_b200 import segments as seg
+    rng = np.random.default_rng(seed)
+    n = seg.SAMPLE_RATE * CLIP_SECONDS
+    t = np.arange(n) / seg.SAMPLE_RATE
+    env = 0.15 + np.abs(np.sin(2 * np.pi * t / 7.3)) * (0.5 + 0.5 * np.sin(2 * np.pi * t / 1.7) ** 2)
+    audio = rng.standard_normal(n) * env
+    plan = seg.SegmentPlan()
+    cuts = seg.split_points(audio, plan)
+    return [c for _, c in seg.segment_frames(n, cuts, plan)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 - 0.05 <= ts <= t1 + 0.15 and len(r) >= 8] or \
+               [r for _, r in self.rows if len(r) >= 8]
+        if not rows:
+            return None
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return float("nan")
+        sm = [num(r[1]) for r in rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": num(rows[0][2]),
+                "power_w_max": max(num(r[3]) for r in rows), "samples": len(rows), "reasons": reasons}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1405.0), d.get("hbm_gbs", 6457.4), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_rate(cfg, frames, steps, warmup, seed=0):
+    """Oracle port of Synthesizer.infer on the host cores: audio-s/s on one T=frames segment."""
+    import torch
+    import polgen_rvc_b200 as pg
+    from oracle import rvc_oracle as orc
+    sd = orc.fold_weight_norm(pg.synth_weights(cfg, seed=seed))
+    phone, lengths, pitch, f0, sid = pg.synth_inputs(cfg, 1, frames, seed=seed)
+    eps_zp, eps_src = pg.synth_noise(cfg, 1, frames, seed=seed)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.infer(sd, cfg, phone, lengths, pitch, f0, sid, eps_zp, eps_src, folded=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return frames / 100.0 / (sum(times) / len(times)), sum(times) / len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: rank 0 alone times the CPU path; other ranks exit 0."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    import polgen_rvc_b200 as pg
+    cfg = pg.CONFIGS[args.config]
+    frames = 500     # bounded sample: one 5 s segment of the same config per step
+    rate, sec, threads = cpu_reference_rate(cfg, frames, args.steps, args.warmup)
+    sample = f"one {frames / 100:.0f} s segment (T={frames}, B=1) of {args.config} per step, torch fp32 CPU"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"RVC {args.config} decode, 60 s clip split into silence segments (bounded CPU sample: {sample})"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "host": {"cpu_count": os.cpu_count(), "torch_threads": threads, "torch": torch.__version__},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import polgen_rvc_b200 as pg
+    from polgen_rvc_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = pg.CONFIGS[args.config]
+    seg_frames = clip_segments(cfg, seed=rank)
+    sd = pg.synth_weights(cfg, seed=0)
+    eng = pg.Engine(cfg, pg.fold_state_dict(sd), local, _lib.PG_FLAG_PROFILE)
+    segs_dev, segs_host, waves_host = [], [], []
+    for i, T in enumerate(seg_frames):
+        inp = pg.synth_inputs(cfg, 1, T, seed=100 * rank + i)
+        segs_host.append([t.pin_memory() for t in inp])
+        segs_dev.append([t.to(dev) for t in inp])
+        waves_host.append(torch.empty(1, T * cfg.upp, dtype=torch.float32).pin_memory())
+    audio_s = sum(seg_frames) / 100.0
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_device():
+        for s in segs_dev:
+            eng.infer(*s, None, None, 0, want_aux=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    eng.profile_read()
+
+    # ---- timed region: K steps, device time per step via CUDA events, L2 flushed between steps
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    t_wall0 = time.time()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_device()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_wall1 = time.time()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    prof = eng.profile_read()
+    clocks = sampler.stop(t_wall0, t_wall1)
+
+    # launches per step: pg_launch_count reports the last call, so run the segments once more
+    per_step_launches = 0
+    for s in segs_dev:
+        eng.infer(*s, None, None, 0, want_aux=False)
+        per_step_launches += eng.launch_count()
+    torch.cuda.synchronize()
+    eng.profile_read()
+
+    # ---- e2e: the C-ABI call with HOST (pinned) buffers, H2D + D2H inside the timed region
+    for s, w in zip(segs_host, waves_host):
+        eng.infer_host(*s, w, 0)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        for s, w in zip(segs_host, waves_host):
+            eng.infer_host(*s, w, 0)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    h2d = sum(sum(t.numel() * t.element_size() for t in s) for s in segs_host)
+    d2h = sum(w.numel() * 4 for w in waves_host)
+
+    t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    total_audio = audio_s * world * args.steps
+
+    if rank == 0:
+        tf_peak, hbm_peak, peak_src = peaks()
+        umma_ms, umma_fl, umma_n = prof["conv_umma"]
+        achieved = umma_fl / (umma_ms * 1e-3) / 1e12 if umma_ms > 0 else 0.0
+        roofline = {
+            "bound": "tensor", "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM ResBlock conv)",
+            "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+            "peak_source": peak_src, "traffic": None,
+            "launches": umma_n, "avg_launch_ms": umma_ms / max(umma_n, 1),
+            "algorithmic_flops_per_launch": umma_fl / max(umma_n, 1),
+            "share_of_step": umma_ms / dev_ms if dev_ms > 0 else None,
+        }
+        line = {
+            "metric": METRIC, "value": total_audio / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": f"RVC {args.config} synthesizer decode, {CLIP_SECONDS} s clip split into silence "
+                                   f"segments of {seg_frames} frames (incl. 1 s pad each side), B=1 per segment, "
+                                   f"one clip per GPU per step",
+                       "audio_s_per_step_per_gpu": audio_s, "l2": "flushed between steps (256 MiB write)",
+                       "parallelism": f"segment-sharded x{world}, no collective"},
+            "roofline": roofline,
+            "e2e": {"value": total_audio / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": per_step_launches * args.steps,
+            "clocks": clocks,
+            "generator_tflops": cfg.generator_flops_per_frame() * 100 * total_audio / (dev_ms_max * 1e-3) / 1e12,
+        }
+        if world == 1 and not args.no_cpu:
+            frames = 500
+            rate, sec, threads = cpu_reference_rate(cfg, frames, 2, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"one {frames / 100:.0f} s segment (T={frames}, B=1) of {args.config}, "
+                                              f"oracle port of Synthesizer.infer, torch fp32, mean of 2 after 1 warm-up"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="v2-48k", choices=["v2-48k", "v2-40k", "v2-32k", "v1-40k"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -84,6 +84,7 @@ typedef struct pg_config {
 
 #define PG_FLAG_FORCE_SIMT 1   /* run every conv on the CUDA-core fp32 kernels (validation aid) */
 #define PG_FLAG_KEEP_TAPS 2    /* keep copies of intermediates for pg_debug_fetch */
+#define PG_FLAG_PROFILE 4      /* CUDA events around every conv launch (pg_profile_read) */
 
 typedef struct pg_handle_s* pg_handle;
 
@@ -160,6 +161,11 @@ int64_t pg_debug_fetch(pg_handle h, void* stream, const char* tap, float* dst_de
 
 /* Statistics of the last call: number of kernels this library launched. */
 int64_t pg_launch_count(pg_handle h);
+
+/* PG_FLAG_PROFILE: device time, algorithmic FLOPs (2*B*L*Cin*Cout*K) and launch count of the
+ * conv launches since the previous read, per kernel class: [0] tcgen05 implicit-GEMM conv,
+ * [1] CUDA-core conv.  Each array has 2 entries.  Synchronises on the recorded events. */
+int pg_profile_read(pg_handle h, double* ms_out, double* flops_out, int64_t* launches_out);
 
 /* Single-layer entry used by the op-level parity tests and micro-benchmarks:
  * y[b][t][co] = sum_{tap,ci} w[co][ci][tap] * lrelu(x[b][t + tap*dil - pad][ci], in_slope) + bias

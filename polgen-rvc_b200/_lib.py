@@ -17,6 +17,7 @@ PG_MAX_RESBLOCK_KERNELS = 4
 PG_MAX_DILATIONS = 4
 PG_FLAG_FORCE_SIMT = 1
 PG_FLAG_KEEP_TAPS = 2
+PG_FLAG_PROFILE = 4
 PG_F32 = 0
 
 
@@ -52,6 +53,7 @@ SYMBOLS = {
     "pg_generator": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "pg_debug_fetch": (C.c_int64, [_P, _P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "pg_launch_count": (C.c_int64, [_P]),
+    "pg_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pg_op_conv1d_f16": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _I,
                               C.POINTER(_F)]),
     "pg_destroy": (_I, [_P]),

@@ -103,6 +103,11 @@ struct pg_handle_s {
 
   // pinned/device staging for pg_infer_host
   DevBuf host_stage;
+
+  // PG_FLAG_PROFILE: CUDA events around every conv launch, per kernel class
+  struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; };
+  std::vector<ProfRec> prof;       // records of the calls since the last pg_profile_read
+  std::vector<cudaEvent_t> ev_pool;
 };
 
 namespace {
@@ -351,6 +356,17 @@ int record_tap(pg_handle h, cudaStream_t s, const std::string& name, const void*
     if (_rc != PG_OK) return _rc; \
   } while (0)
 
+cudaEvent_t take_event(pg_handle h) {
+  if (!h->ev_pool.empty()) {
+    cudaEvent_t e = h->ev_pool.back();
+    h->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
 int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_dt, DType out_dt) {
   a.w = w.w;
   a.w16 = w.w16;
@@ -359,10 +375,24 @@ int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_d
   a.Cout = w.Cout;
   a.K = w.K;
   const bool force_simt = (h->cfg.flags & PG_FLAG_FORCE_SIMT) != 0;
-  if (!force_simt && in_dt == DT_F16 && out_dt == DT_F16 && w.w16 && umma_conv_supported(a)) {
+  const bool umma = !force_simt && in_dt == DT_F16 && out_dt == DT_F16 && w.w16 && umma_conv_supported(a);
+  const bool prof = (h->cfg.flags & PG_FLAG_PROFILE) != 0;
+  pg_handle_s::ProfRec rec;
+  if (prof) {
+    rec.e0 = take_event(h);
+    rec.e1 = take_event(h);
+    rec.cls = umma ? 0 : 1;
+    rec.flops = 2.0 * a.B * a.L_out * (double)a.Cin * a.Cout * a.K;
+    cudaEventRecord(rec.e0, s);
+  }
+  if (umma) {
     PG_LAUNCH(h, launch_conv_umma(a, s));
   } else {
     PG_LAUNCH(h, launch_conv_simt(a, in_dt, out_dt, s));
+  }
+  if (prof) {
+    cudaEventRecord(rec.e1, s);
+    h->prof.push_back(rec);
   }
   return PG_OK;
 }
@@ -951,6 +981,28 @@ int64_t pg_debug_fetch(pg_handle h, void* stream, const char* tap, float* dst, i
 
 int64_t pg_launch_count(pg_handle h) { return h ? h->launches : 0; }
 
+int pg_profile_read(pg_handle h, double* ms_out, double* flops_out, int64_t* launches_out) {
+  if (!h || !ms_out || !flops_out || !launches_out) return fail(PG_ERR_INVALID, "null argument");
+  Guard g(h->device);
+  for (int c = 0; c < 2; ++c) {
+    ms_out[c] = 0.0;
+    flops_out[c] = 0.0;
+    launches_out[c] = 0;
+  }
+  for (auto& r : h->prof) {
+    PG_CUDA_CHECK(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    PG_CUDA_CHECK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ms_out[r.cls] += ms;
+    flops_out[r.cls] += r.flops;
+    launches_out[r.cls] += 1;
+    h->ev_pool.push_back(r.e0);
+    h->ev_pool.push_back(r.e1);
+  }
+  h->prof.clear();
+  return PG_OK;
+}
+
 int pg_destroy(pg_handle h) {
   if (!h) return PG_OK;
   Guard g(h->device);
@@ -959,6 +1011,11 @@ int pg_destroy(pg_handle h) {
     if (kv.second.p) cudaFree(kv.second.p);
   if (h->ws.p) cudaFree(h->ws.p);
   if (h->host_stage.p) cudaFree(h->host_stage.p);
+  for (auto& r : h->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
   delete h;
   return PG_OK;
 }

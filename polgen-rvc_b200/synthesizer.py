@@ -111,6 +111,12 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.pg_launch_count(self._h))
 
+    def profile_read(self):
+        """PG_FLAG_PROFILE: {class: (ms, flops, launches)} of the conv launches since the last read."""
+        ms, fl, n = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_int64 * 2)()
+        _lib.check(self.lib.pg_profile_read(self._h, ms, fl, n), "pg_profile_read")
+        return {"conv_umma": (ms[0], fl[0], int(n[0])), "conv_simt": (ms[1], fl[1], int(n[1]))}
+
     def infer(self, phone, lengths, pitch, f0, sid, eps_zp=None, eps_src=None, seed: int = 0,
               want_aux: bool = True):
         """Time-major tensors on this engine's GPU.  Returns (wave [B][L], aux [4][B][T][C] | None)."""

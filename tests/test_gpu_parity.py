@@ -1,0 +1,300 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the committed golden vectors of
+the live reference and against the CPU oracle on identical seeded inputs.
+
+Tolerances are BASELINE.json's: waveform SNR >= 40 dB and max-abs <= 1e-2 vs the fp32
+reference (the decoder runs f16 operands / fp32 accumulation), sine source <= 1e-5; the fp32
+TextEncoder / flow taps are held to <= 1e-3 max-abs.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_files, load_case, snr_db
+
+pytestmark = pytest.mark.gpu
+
+WAVE_SNR_DB = 40.0
+WAVE_MAXABS = 1e-2
+SINE_MAXABS = 1e-5
+LATENT_MAXABS = 1e-3
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device -- there is no CPU fallback to test")
+    return torch.device("cuda:0")
+
+
+def _engine(cfg, sd, flags=0):
+    import polgen_rvc_b200 as pg
+    return pg.Engine(cfg, pg.fold_state_dict(sd), 0, flags)
+
+
+def _run(eng, inputs, noise):
+    d = _dev()
+    phone, lengths, pitch, f0, sid = (t.to(d) for t in inputs)
+    B = phone.shape[0]
+    ez = es = None
+    if noise is not None:
+        ez = noise[0].transpose(1, 2).contiguous().to(d)
+        es = noise[1].reshape(B, -1).contiguous().to(d)
+    wave, aux = eng.infer(phone, lengths, pitch, f0, sid, ez, es, seed=123)
+    torch.cuda.synchronize()
+    return wave.cpu(), [aux[i].cpu().transpose(1, 2) for i in range(4)]
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=os.path.basename)
+def test_infer_matches_reference_golden(path):
+    cfg, sd, inputs, noise, g = load_case(path)
+    eng = _engine(cfg, sd)
+    wave, (z, z_p, m_p, logs_p) = _run(eng, inputs, noise)
+    want = torch.from_numpy(g["o"])[:, 0]
+    assert wave.shape == want.shape
+    assert snr_db(wave, want) >= WAVE_SNR_DB
+    assert (wave - want).abs().max().item() <= WAVE_MAXABS
+    for name, got in (("z", z), ("z_p", z_p), ("m_p", m_p), ("logs_p", logs_p)):
+        assert (got - torch.from_numpy(g[name])).abs().max().item() <= LATENT_MAXABS, name
+    assert eng.launch_count() > 100          # our kernels ran, not a library fallback
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=os.path.basename)
+def test_sine_source_within_1e5(path):
+    cfg, sd, inputs, noise, g = load_case(path)
+    eng = _engine(cfg, sd)
+    d = _dev()
+    f0 = inputs[3].to(d)
+    B = f0.shape[0]
+    zeros = torch.zeros(B, f0.shape[1] * cfg.upp, device=d)
+    src, sine = eng.source(f0, zeros, want_sine=True)
+    torch.cuda.synchronize()
+    want = torch.from_numpy(g["source_nonoise"]).reshape(B, -1)
+    assert (src.cpu() - want).abs().max().item() <= SINE_MAXABS
+    # with the captured noise the full source matches too
+    es = noise[1].reshape(B, -1).contiguous().to(d)
+    src2, _ = eng.source(f0, es)
+    assert (src2.cpu() - torch.from_numpy(g["source"]).reshape(B, -1)).abs().max().item() <= 2e-5
+
+
+def test_sine_source_long_clips_vs_oracle():
+    """10 s and 41 s segments (the pipeline's x_max): fp64 phase accumulation keeps <= 1e-5."""
+    import polgen_rvc_b200 as pg
+    from oracle import rvc_oracle as orc
+    cfg = pg.CONFIGS["v2-48k"]
+    sd = pg.synth_weights(cfg, seed=0)
+    eng = _engine(cfg, sd)
+    W = orc.fold_weight_norm(sd)
+    d = _dev()
+    for T in (1000, 4100):
+        _, _, _, f0, _ = pg.synth_inputs(cfg, 2, T, seed=4)
+        zeros = torch.zeros(2, T * cfg.upp, device=d)
+        src, sine = eng.source(f0.to(d), zeros, want_sine=True)
+        _, want_sine = orc.sine_source(W, cfg, f0, None, exact=False)
+        assert (sine.cpu() - want_sine[:, :, 0]).abs().max().item() <= SINE_MAXABS, T
+
+
+def test_module_entry_points_vs_oracle():
+    import polgen_rvc_b200 as pg
+    from oracle import rvc_oracle as orc
+    cfg = pg.CONFIGS["v2-40k"]
+    B, T = 2, 50
+    sd = pg.synth_weights(cfg, seed=21, post_std=0.05)
+    phone, lengths, pitch, f0, sid = pg.synth_inputs(cfg, B, T, seed=21)
+    sid = torch.tensor([3, 77])
+    eps_zp, eps_src = pg.synth_noise(cfg, B, T, seed=21)
+    W = orc.fold_weight_norm(sd)
+    eng = _engine(cfg, sd)
+    d = _dev()
+    m_p, logs_p = eng.text_encoder(phone.to(d), lengths.to(d), pitch.to(d))
+    om, ol, omask = orc.text_encoder(W, cfg, phone, pitch, lengths)
+    assert (m_p.cpu().transpose(1, 2) - om).abs().max().item() <= LATENT_MAXABS
+    assert (logs_p.cpu().transpose(1, 2) - ol).abs().max().item() <= LATENT_MAXABS
+    g = W["emb_g.weight"][sid][:, :, None]
+    z_p = (om + torch.exp(ol) * eps_zp * 0.66666) * omask
+    oz = orc.flow_reverse(W, cfg, z_p, omask, g)
+    z = eng.flow_reverse(z_p.transpose(1, 2).contiguous().to(d), lengths.to(d), sid.to(d))
+    assert (z.cpu().transpose(1, 2) - oz).abs().max().item() <= LATENT_MAXABS
+    osrc, _ = orc.sine_source(W, cfg, f0, eps_src)
+    src, _ = eng.source(f0.to(d), eps_src.reshape(B, -1).contiguous().to(d))
+    assert (src.cpu() - osrc[:, :, 0]).abs().max().item() <= 2e-5
+    ow = orc.generator(W, cfg, oz * omask, osrc, g)[:, 0]
+    wave = eng.generator((oz * omask).transpose(1, 2).contiguous().to(d), osrc[:, :, 0].contiguous().to(d),
+                         sid.to(d))
+    torch.cuda.synchronize()
+    assert snr_db(wave.cpu(), ow) >= WAVE_SNR_DB
+    assert (wave.cpu() - ow).abs().max().item() <= WAVE_MAXABS
+
+
+def test_ragged_lengths_and_speakers_vs_oracle():
+    """sequence_mask semantics (commons.py:89-93) in encoder + flow; the generator ignores the
+    mask after its input exactly as the reference does."""
+    import polgen_rvc_b200 as pg
+    from oracle import rvc_oracle as orc
+    cfg = pg.CONFIGS["v2-32k"]
+    B, T = 3, 40
+    sd = pg.synth_weights(cfg, seed=12, post_std=0.05)
+    phone, lengths, pitch, f0, sid = pg.synth_inputs(cfg, B, T, seed=12)
+    lengths = torch.tensor([40, 23, 1])
+    sid = torch.tensor([0, 50, 108])
+    noise = pg.synth_noise(cfg, B, T, seed=12)
+    o, mask, (z, z_p, m_p, logs_p) = orc.infer(sd, cfg, phone, lengths, pitch, f0, sid, *noise)
+    eng = _engine(cfg, sd)
+    wave, (gz, gzp, gm, gl) = _run(eng, (phone, lengths, pitch, f0, sid), noise)
+    assert (gz - z).abs().max().item() <= LATENT_MAXABS
+    assert (gzp - z_p).abs().max().item() <= LATENT_MAXABS
+    assert (gm - m_p).abs().max().item() <= LATENT_MAXABS
+    assert float(gz[1, :, 23:].abs().max()) == 0.0 and float(gz[2, :, 1:].abs().max()) == 0.0
+    assert snr_db(wave, o[:, 0]) >= WAVE_SNR_DB
+    assert (wave - o[:, 0]).abs().max().item() <= WAVE_MAXABS
+
+
+def test_trained_scale_weights_still_within_tolerance():
+    """Weights at kaiming scale in the ResBlocks (a trained-like regime where the residual branch
+    is not small) -- the f16 tensor-core path must still clear 40 dB."""
+    import polgen_rvc_b200 as pg
+    from oracle import rvc_oracle as orc
+    cfg = pg.CONFIGS["v2-48k"]
+    B, T = 1, 40
+    sd = pg.synth_weights(cfg, seed=31)
+    gen = torch.Generator().manual_seed(99)
+    for k in list(sd):
+        if k.startswith("dec.resblocks.") and k.endswith("weight_v"):
+            fan_in = sd[k].shape[1] * sd[k].shape[2]
+            sd[k] = torch.randn(sd[k].shape, generator=gen) * (0.5 / fan_in ** 0.5)
+            sd[k.replace("weight_v", "weight_g")] = sd[k].reshape(sd[k].shape[0], -1).norm(dim=1).reshape(-1, 1, 1)
+    inputs = pg.synth_inputs(cfg, B, T, seed=31)
+    noise = pg.synth_noise(cfg, B, T, seed=31)
+    o, *_ = orc.infer(sd, cfg, *inputs, *noise)
+    wave, _ = _run(_engine(cfg, sd), inputs, noise)
+    assert snr_db(wave, o[:, 0]) >= WAVE_SNR_DB
+    assert (wave - o[:, 0]).abs().max().item() <= WAVE_MAXABS
+
+
+def test_tcgen05_path_matches_cuda_core_path():
+    import polgen_rvc_b200 as pg
+    from polgen_rvc_b200 import _lib
+    cfg = pg.CONFIGS["v2-48k"]
+    sd = pg.synth_weights(cfg, seed=2)
+    inputs = pg.synth_inputs(cfg, 2, 64, seed=2)
+    noise = pg.synth_noise(cfg, 2, 64, seed=2)
+    a, _ = _run(_engine(cfg, sd, 0), inputs, noise)
+    b, _ = _run(_engine(cfg, sd, _lib.PG_FLAG_FORCE_SIMT), inputs, noise)
+    assert snr_db(a, b) >= 55.0
+
+
+@pytest.mark.parametrize("shape", [(128, 3, 1, 1000, 1), (128, 11, 5, 777, 2), (64, 7, 3, 1500, 1),
+                                   (32, 11, 5, 130, 3), (32, 3, 1, 5000, 1), (256, 7, 1, 300, 2),
+                                   (256, 11, 5, 129, 1), (64, 3, 1, 1, 1)])
+def test_conv_op_tcgen05_bit_level(shape):
+    """One conv layer through the tcgen05 kernel vs fp32 torch conv on the same f16 inputs
+    (ragged L, batch > 1, every channel width of the generator)."""
+    from polgen_rvc_b200 import _lib
+    lib = _lib.load()
+    Cc, K, dil, L, B = shape
+    d = _dev()
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(B, L, Cc, generator=g).half()
+    w = (torch.randn(Cc, Cc, K, generator=g) / (Cc * K) ** 0.5).half().float()
+    bias = torch.randn(Cc, generator=g) * 0.1
+    res = torch.randn(B, L, Cc, generator=g).half()
+    xd, rd = x.to(d), res.to(d)
+    ref = torch.nn.functional.conv1d(
+        torch.nn.functional.leaky_relu(xd.float(), 0.1).half().float().transpose(1, 2), w.to(d), bias.to(d),
+        dilation=dil, padding=(K * dil - dil) // 2).transpose(1, 2) + rd.float()
+    outs = {}
+    for impl in (0, 1):
+        y = torch.full((B, L, Cc), 7.0, device=d, dtype=torch.half)
+        rc = lib.pg_op_conv1d_f16(0, impl, B, L, Cc, Cc, K, dil, C.c_void_p(xd.data_ptr()),
+                                  C.c_void_p(w.data_ptr()), C.c_void_p(bias.data_ptr()), C.c_float(0.1),
+                                  C.c_float(1.0), C.c_void_p(rd.data_ptr()), C.c_void_p(y.data_ptr()), 1, None)
+        assert rc == 0, lib.pg_last_error()
+        torch.cuda.synchronize()
+        outs[impl] = y.float()
+    tol = 2e-3 * max(1.0, ref.abs().max().item())     # one f16 ulp of the output range
+    assert (outs[1] - ref).abs().max().item() <= tol
+    assert (outs[0] - ref).abs().max().item() <= tol
+
+
+def test_full_size_properties_v2_48k():
+    """BASELINE size (10 s rows, 48 kHz): determinism, batch invariance, bounded output, and the
+    Philox noise path -- properties that need no oracle run."""
+    import polgen_rvc_b200 as pg
+    cfg = pg.CONFIGS["v2-48k"]
+    sd = pg.synth_weights(cfg, seed=0)
+    eng = _engine(cfg, sd)
+    d = _dev()
+    T = 1000
+    phone, lengths, pitch, f0, sid = pg.synth_inputs(cfg, 1, T, seed=0)
+    eps_zp, eps_src = pg.synth_noise(cfg, 1, T, seed=0)
+    one = [t.to(d) for t in (phone, lengths, pitch, f0, sid)]
+    ez, es = eps_zp.transpose(1, 2).contiguous().to(d), eps_src.reshape(1, -1).contiguous().to(d)
+    w1, _ = eng.infer(*one, ez, es, 0)
+    w1b, _ = eng.infer(*one, ez, es, 0)
+    assert torch.equal(w1, w1b)                                   # deterministic
+    two = [torch.cat([t, t]) for t in one]
+    w2, _ = eng.infer(*two, torch.cat([ez, ez]), torch.cat([es, es]), 0)
+    assert torch.equal(w2[0], w2[1]) and torch.equal(w2[0], w1[0])  # batch rows are independent
+    assert w1.shape == (1, T * cfg.upp) and bool(torch.isfinite(w1).all())
+    assert float(w1.abs().max()) < 1.0                            # tanh output
+    wa, _ = eng.infer(*one, None, None, 1)
+    wb, _ = eng.infer(*one, None, None, 2)
+    wa2, _ = eng.infer(*one, None, None, 1)
+    assert torch.equal(wa, wa2) and not torch.equal(wa, wb)       # Philox: seed-reproducible
+    assert snr_db(wa, w1) > 5.0                                    # same signal, different noise draw
+
+
+def test_parity_medium_clip_v2_48k_vs_oracle():
+    """3 s at 48 kHz (T=300): large enough to cross many tiles of every stage."""
+    import polgen_rvc_b200 as pg
+    from oracle import rvc_oracle as orc
+    cfg = pg.CONFIGS["v2-48k"]
+    sd = pg.synth_weights(cfg, seed=5)
+    inputs = pg.synth_inputs(cfg, 1, 300, seed=5)
+    noise = pg.synth_noise(cfg, 1, 300, seed=5)
+    o, *_ = orc.infer(sd, cfg, *inputs, *noise)
+    wave, _ = _run(_engine(cfg, sd), inputs, noise)
+    assert snr_db(wave, o[:, 0]) >= WAVE_SNR_DB
+    assert (wave - o[:, 0]).abs().max().item() <= WAVE_MAXABS
+
+
+def test_dropin_synthesizer_surface():
+    """The reference call sequence of rvc/infer/infer.py:92-102 and pipeline.py:275 on the drop-in."""
+    import polgen_rvc_b200 as pg
+    from oracle import rvc_oracle as orc
+    cfg = pg.CONFIGS["v1-40k"]
+    sd = pg.synth_weights(cfg, seed=8)
+    net = pg.Synthesizer(*cfg.ctor_args(), use_f0=1, input_dim=cfg.input_dim, is_half=False)
+    del net.enc_q
+    print(net.load_state_dict(sd, strict=False))
+    net.eval().to(_dev())
+    net = net.float()
+    B, T = 1, 30
+    phone, lengths, pitch, f0, sid = pg.synth_inputs(cfg, B, T, seed=8)
+    eps_zp, eps_src = pg.synth_noise(cfg, B, T, seed=8)
+    d = _dev()
+    with torch.no_grad():
+        o, x_mask, (z, z_p, m_p, logs_p) = net.infer(phone.to(d), lengths.to(d), pitch.to(d), f0.to(d),
+                                                      sid.to(d), eps_zp=eps_zp, eps_src=eps_src)
+        audio1 = net.infer(phone.to(d), lengths.to(d), pitch.to(d), f0.to(d), sid.to(d))[0][0, 0]
+    want_o, want_mask, (wz, wzp, wm, wl) = orc.infer(sd, cfg, phone, lengths, pitch, f0, sid, eps_zp, eps_src)
+    assert o.shape == want_o.shape and x_mask.shape == want_mask.shape
+    assert z.shape == wz.shape and m_p.shape == wm.shape
+    assert snr_db(o.cpu(), want_o) >= WAVE_SNR_DB
+    assert (z.cpu() - wz).abs().max().item() <= LATENT_MAXABS
+    assert audio1.shape == (T * cfg.upp,) and bool(torch.isfinite(audio1).all())
+    # is_half deployment: .half() module, half features in, half waveform out
+    net16 = net.half()
+    o16 = net16.infer(phone.to(d).half(), lengths.to(d), pitch.to(d), f0.to(d), sid.to(d),
+                      eps_zp=eps_zp, eps_src=eps_src)[0]
+    assert o16.dtype == torch.float16
+    assert snr_db(o16.float().cpu(), want_o) >= 35.0    # inputs/weights rounded to f16 first
+    # rate branch (synthesizers.py:175-181)
+    net32 = net16.float()
+    rate = torch.tensor(0.5)
+    o_r, m_r, (z_r, zp_r, _, _) = net32.infer(phone.to(d), lengths.to(d), pitch.to(d), f0.to(d), sid.to(d), rate,
+                                              eps_zp=eps_zp)
+    head = int(T * (1.0 - 0.5))
+    assert o_r.shape == (B, 1, (T - head) * cfg.upp) and m_r.shape == (B, 1, T - head)
+    assert z_r.shape == (B, cfg.inter_channels, T - head)

@@ -1,0 +1,57 @@
+"""world_size-2 gloo run of the segment-sharded decode driver on CPU: every rank decodes its
+share with a stand-in decode function and rank 0 receives all waveforms in order.  (The decode
+itself has no collective -- SURVEY.md 8(e); this covers the N>1 host logic.)"""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from polgen_rvc_b200 import segments as seg
+    lengths = [400, 240, 100, 100, 370, 55, 240]
+    calls = []
+
+    def decode(indices):
+        calls.append(list(indices))
+        return {i: np.full(lengths[i] * 3, float(i), dtype=np.float32) + rank * 0.0 for i in indices}
+
+    res = seg.decode_sharded(decode, lengths, rank, world)
+    mine = seg.plan_shards(lengths, world)[rank]
+    assert calls == [mine]
+    t = torch.tensor([float(sum(lengths[i] for i in mine))])
+    dist.all_reduce(t)
+    assert int(t.item()) == sum(lengths)
+    if rank == 0:
+        assert res is not None and len(res) == len(lengths)
+        for i, w in enumerate(res):
+            assert w.shape[0] == lengths[i] * 3 and float(w[0]) == float(i)
+        open(out_path, "w").write("ok")
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_decode_sharded_two_ranks(tmp_path):
+    out = str(tmp_path / "ok.txt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
