@@ -38,6 +38,7 @@ struct ConvW {
   float* w = nullptr;      // [K][Cin][Cout] f32   (CUDA-core path)
   __half* w16 = nullptr;   // [K][Cout][Cin] f16   (tcgen05 path)
   float* bias = nullptr;   // [Cout]
+  uint32_t* tapmask = nullptr;   // per Cout tile, taps with non-zero weights (polyphase upsampler)
   int Cin = 0, Cout = 0, K = 1;
 };
 
@@ -156,6 +157,23 @@ const HostTensor* find(pg_handle h, const std::string& name, std::initializer_li
   return &it->second;
 }
 
+// w [K][Cin][Cout] f32 -> device f32 copy + f16 [K][Cout][Cin] copy for the tcgen05 path
+int upload_conv(pg_handle h, const std::vector<float>& w, int K, int Cin, int Cout, ConvW* out) {
+  std::vector<__half> w16(w.size());
+  for (int k = 0; k < K; ++k)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int co = 0; co < Cout; ++co)
+        w16[((size_t)k * Cout + co) * Cin + ci] = __float2half_rn(w[((size_t)k * Cin + ci) * Cout + co]);
+  int rc = upload(h, w, &out->w);
+  if (rc) return rc;
+  rc = upload(h, w16, &out->w16);
+  if (rc) return rc;
+  out->Cin = Cin;
+  out->Cout = Cout;
+  out->K = K;
+  return PG_OK;
+}
+
 // Conv1d weight W[Cout][Cin][K] (rows co_begin..co_begin+co_count) ->
 //   w   [K][Cin][co_count] f32,  w16 [K][co_count][Cin] f16,  bias [co_count]
 int pack_conv(pg_handle h, const std::string& wname, const std::string& bname, int Cout, int Cin,
@@ -163,25 +181,17 @@ int pack_conv(pg_handle h, const std::string& wname, const std::string& bname, i
   const HostTensor* W = find(h, wname, {Cout, Cin, K});
   if (!W) return PG_ERR_INVALID;
   std::vector<float> w((size_t)K * Cin * co_count);
-  std::vector<__half> w16;
-  if (want16) w16.resize(w.size());
   for (int co = 0; co < co_count; ++co) {
     const int src_co = co_begin + (flip_co ? co_count - 1 - co : co);
     for (int ci = 0; ci < Cin; ++ci) {
       const int src_ci = flip_ci ? Cin - 1 - ci : ci;
-      for (int k = 0; k < K; ++k) {
-        const float v = W->data[((size_t)src_co * Cin + src_ci) * K + k];
-        w[((size_t)k * Cin + ci) * co_count + co] = v;
-        if (want16) w16[((size_t)k * co_count + co) * Cin + ci] = __float2half_rn(v);
-      }
+      for (int k = 0; k < K; ++k)
+        w[((size_t)k * Cin + ci) * co_count + co] = W->data[((size_t)src_co * Cin + src_ci) * K + k];
     }
   }
-  int rc = upload(h, w, &out->w);
+  (void)want16;
+  int rc = upload_conv(h, w, K, Cin, co_count, out);
   if (rc) return rc;
-  if (want16) {
-    rc = upload(h, w16, &out->w16);
-    if (rc) return rc;
-  }
   if (!bname.empty()) {
     const HostTensor* Bv = find(h, bname, {Cout});
     if (!Bv) return PG_ERR_INVALID;
@@ -238,13 +248,22 @@ int pack_conv_transpose(pg_handle h, const std::string& wname, const std::string
   std::vector<float> b(N);
   for (int r = 0; r < u; ++r)
     for (int co = 0; co < Cout; ++co) b[r * Cout + co] = Bv->data[co];
-  int rc = upload(h, w, &st->up.w);
+  int rc = upload_conv(h, w, taps, Cin, N, &st->up);
   if (rc) return rc;
   rc = upload(h, b, &st->up.bias);
   if (rc) return rc;
-  st->up.Cin = Cin;
-  st->up.Cout = N;
-  st->up.K = taps;
+  const int nt = umma_pick_nt(N);
+  if (nt > 0 && taps <= 32) {
+    std::vector<uint32_t> mask(N / nt, 0u);
+    for (int tap = 0; tap < taps; ++tap)
+      for (int n = 0; n < N; ++n) {
+        bool nz = false;
+        for (int ci = 0; ci < Cin && !nz; ++ci) nz = w[((size_t)tap * Cin + ci) * N + n] != 0.f;
+        if (nz) mask[n / nt] |= 1u << tap;
+      }
+    rc = upload(h, mask, &st->up.tapmask);
+    if (rc) return rc;
+  }
   st->up_pad = -dmin;
   return PG_OK;
 }
@@ -375,7 +394,8 @@ int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_d
   a.Cout = w.Cout;
   a.K = w.K;
   const bool force_simt = (h->cfg.flags & PG_FLAG_FORCE_SIMT) != 0;
-  const bool umma = !force_simt && in_dt == DT_F16 && out_dt == DT_F16 && w.w16 && umma_conv_supported(a);
+  a.tapmask = w.tapmask;
+  const bool umma = !force_simt && w.w16 && umma_conv_supported(a);
   const bool prof = (h->cfg.flags & PG_FLAG_PROFILE) != 0;
   pg_handle_s::ProfRec rec;
   if (prof) {
@@ -386,7 +406,7 @@ int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_d
     cudaEventRecord(rec.e0, s);
   }
   if (umma) {
-    PG_LAUNCH(h, launch_conv_umma(a, s));
+    PG_LAUNCH(h, launch_conv_umma(a, in_dt, out_dt, s));
   } else {
     PG_LAUNCH(h, launch_conv_simt(a, in_dt, out_dt, s));
   }
@@ -677,9 +697,8 @@ int pg_finalize(pg_handle h) {
           for (int ci = 0; ci < H; ++ci) w[(size_t)ci * 3 * H + q * H + co] = W->data[(size_t)co * H + ci];
         }
       }
-      PG_TRY(upload(h, w, &L.qkv.w));
+      PG_TRY(upload_conv(h, w, 1, H, 3 * H, &L.qkv));
       PG_TRY(upload(h, b, &L.qkv.bias));
-      L.qkv.Cin = H; L.qkv.Cout = 3 * H; L.qkv.K = 1;
     }
     PG_TRY(pack_conv(h, p + "conv_o.weight", p + "conv_o.bias", H, H, 1, 0, H, false, false, false, &L.o));
     PG_TRY(upload_named(h, p + "emb_rel_k", {1, R, D}, &L.rel_k));
@@ -1063,7 +1082,7 @@ int pg_op_conv1d_f16(int device, int impl, int B, int L, int Cin, int Cout, int 
     cudaEventRecord(e0, 0);
     cudaError_t e = cudaSuccess;
     for (int it = 0; it < (iters > 0 ? iters : 1) && e == cudaSuccess; ++it)
-      e = impl == 1 ? launch_conv_umma(a, 0) : launch_conv_simt(a, DT_F16, DT_F16, 0);
+      e = impl == 1 ? launch_conv_umma(a, DT_F16, DT_F16, 0) : launch_conv_simt(a, DT_F16, DT_F16, 0);
     cudaEventRecord(e1, 0);
     cudaError_t e2 = cudaDeviceSynchronize();
     if (e != cudaSuccess || e2 != cudaSuccess)

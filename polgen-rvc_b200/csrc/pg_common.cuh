@@ -40,6 +40,8 @@ struct ConvArgs {
   const void* res = nullptr; int res_ld = 0; int res_coff = 0; float res_scale = 1.f;
   void* y = nullptr; int y_ld = 0; int y_coff = 0;
   int accumulate = 0; float out_scale = 1.f;
+  // tcgen05 path only: per Cout-tile bitmask of taps with non-zero weights (polyphase upsampler)
+  const uint32_t* tapmask = nullptr;
 };
 
 enum DType : int { DT_F32 = 0, DT_F16 = 1 };
@@ -49,7 +51,8 @@ cudaError_t launch_conv_simt(const ConvArgs& a, DType in_dt, DType out_dt, cudaS
 
 // tcgen05 implicit-GEMM conv over f16 activations (pg_conv_umma.cu).
 bool umma_conv_supported(const ConvArgs& a);
-cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s);
+int umma_pick_nt(int cout);   // Cout tile the tcgen05 conv will use (0 = unsupported)
+cudaError_t launch_conv_umma(const ConvArgs& a, DType in_dt, DType out_dt, cudaStream_t s);
 
 cudaError_t launch_prepare_ints(const int64_t* lengths, const int64_t* pitch, const int64_t* sid,
                                 int* lens32, int* pitch32, int* sid32, int B, int T, int n_spk,

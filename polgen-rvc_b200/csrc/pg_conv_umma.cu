@@ -1,24 +1,31 @@
-// tcgen05 / TMEM implicit-GEMM Conv1d over time-major f16 activations (sm_100a).
+// tcgen05 / TMEM implicit-GEMM Conv1d over time-major activations (sm_100a).
 //
-// Computes one layer of the GeneratorNSF hot loop (reference
-// rvc/lib/algorithm/residuals.py:45-53, conv factory :15-25):
-//   y[b][t][co] = epi( sum_{tap,ci} W[tap][co][ci] * lrelu(x[b][t + tap*dil - pad][ci]) )
+// One kernel serves every dense conv / GEMM of the path: the ResBlock convs
+// (reference rvc/lib/algorithm/residuals.py:45-53), the polyphase form of the
+// ConvTranspose1d upsamplers (nsf.py:80-91), conv_pre (nsf.py:64-66), and the
+// 1x1 / k3 / k5 convs of the TextEncoder and the flow (encoders.py, attentions.py,
+// modules.py):
+//   y[b][t][co] = epi( sum_{tap,ci} W[tap][co][ci] * act_in(x[b][t + tap*dil - pad][ci]) )
 //
-// Mapping: D[M = 128 time rows, N = Cout] += A * B per tap and
-// per 16-channel K slice, accumulated in TMEM (fp32).
-//   A = activations.  The CTA stages the window of 128 + (K-1)*dil rows ONCE in
-//       shared memory as channel-chunk planes [Cin/8][rows][8 ch] (the UMMA
-//       no-swizzle K-major canonical layout with SBO = 128 B), applying the
-//       pre-activation leaky-ReLU on the way in.  Rows are 16 B apart inside a
-//       plane, so a tap/dilation shift is just `start_address += shift*16`:
-//       zero-copy implicit im2col, every tap re-reads the same window.
+// Mapping: D[M = 128 time rows, N = Cout tile] += A * B per tap and
+// per 16-channel K slice, f16 operands, fp32 accumulation in TMEM.
+//   A = activations.  The CTA stages the window of MT*128 + (K-1)*dil rows in
+//       shared memory as channel-chunk planes [Cin/8][rows][8 ch] -- the UMMA
+//       no-swizzle K-major canonical layout with SBO = 128 B -- converting to
+//       f16 and applying the input mask / pre-activation leaky-ReLU on the way
+//       in.  Rows are 16 B apart inside a plane, so a tap/dilation shift is just
+//       `start_address += shift*16`: zero-copy implicit im2col, every tap and
+//       every one of the MT row tiles re-reads the same window.  Wide inputs
+//       (Cin > 256) go through a double-buffered ring of 256-channel groups.
 //   B = weights, [tap][Cout][Cin] f16 in global, streamed by TMA (128B swizzle,
-//       64-channel chunks; 64B swizzle for Cin = 32) through an mbarrier ring.
+//       64-channel chunks; 64B swizzle, 32-channel chunks when Cin % 64 != 0)
+//       through an mbarrier ring; each stage feeds MT accumulators.
 // Roles: warps 0-3 stage A then run the epilogue (TMEM -> regs -> bias /
-// residual / scale / accumulate / leaky-ReLU -> f16 -> global), warp 4 is the
-// TMA producer, warp 5 owns TMEM and issues the MMAs (one elected lane).
+// per-batch bias / residual / scale / accumulate / activation / mask -> global),
+// warp 4 is the TMA producer, warp 5 owns TMEM and issues the MMAs.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -30,9 +37,9 @@ namespace pg {
 
 namespace {
 
-constexpr int BM = 128;              // output rows (time) per CTA
+constexpr int BM = 128;              // rows per accumulator tile
 constexpr int NTHREADS = 192;
-constexpr int MAX_WINDOW = BM + 10 * 5;   // K <= 11, dil <= 5
+constexpr int GROUP_PLANES = 32;     // 256 channels per A group
 
 // ------------------------------ PTX wrappers -------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -66,8 +73,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) {
-      printf("pg_conv_umma: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x,
-             blockIdx.y, threadIdx.x);
+      printf("pg_conv_umma: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x);
       __trap();
     }
   }
@@ -107,7 +114,7 @@ __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
                    smem_u32(bar))
                : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], kind::f16 (f16/bf16 operands, fp32 accumulate)
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (f16 operands, fp32 accumulate)
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                          uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -148,60 +155,98 @@ constexpr uint32_t LAYOUT_NONE = 0, LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 @4, a/b
 // format F16 (0) @7/@10, K-major both, N>>3 @17, M>>4 @24.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+inline uint32_t make_idesc(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 struct UmmaParams {
-  const __half* x; const __half* res; __half* y;
-  const float* bias;
-  int B, L;                 // L_in == L_out
-  int K, dil, pad;
-  float in_slope, out_slope, out_scale, res_scale;
+  const void* x; int x_ld, x_coff;
+  const void* res; int res_ld, res_coff; float res_scale;
+  void* y; int y_ld, y_coff;
+  const float* bias; const float* bbias; int bbias_ld;
+  const int* lens; int in_mask, out_mask;
+  const uint32_t* tapmask;     // [n_tiles] bit t set = tap t has non-zero weights (nullable)
+  int B, L;
+  int Cin, Cout, K, dil, pad;
+  int NT;                       // Cout tile (accumulator columns)
+  float in_slope, out_slope, out_scale;
   int act, accumulate;
-  int rows_alloc;           // window rows rounded up to 8
-  int plane_bytes;          // A plane pitch (16 B * (rows_alloc + 1))
-  int stages;
+  int plane_bytes;              // A plane pitch (16 B * (rows_alloc + 1))
+  int KC;                       // channels per weight stage: 64 (SW128) or 32 (SW64)
+  int PG, n_groups, a_bufs;     // planes per A group, groups, group buffers
+  int stages, stage_bytes;      // weight ring
+  int tmem_cols;
+  uint32_t idesc;
 };
 
-template <int CIN, int COUT>
+template <typename T> struct VecIO;
+template <> struct VecIO<__half> {
+  // 8 channels -> 8 floats
+  static __device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+    uint4 q;
+    __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = q;
+  }
+};
+template <> struct VecIO<float> {
+  static __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+
+template <int MT, typename TIn, typename TOut>
 __global__ void __launch_bounds__(NTHREADS)
 conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
-  constexpr int KC = CIN >= 64 ? 64 : CIN;          // channels per weight stage
-  constexpr int NCHUNK = CIN / KC;
-  constexpr int STAGE_BYTES = COUT * KC * 2;
-  constexpr uint32_t W_LAYOUT = KC == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
-  constexpr uint32_t W_SBO = 8 * KC * 2;
-  constexpr int TMEM_COLS = COUT < 32 ? 32 : COUT;
-  constexpr int PLANES = CIN / 8;
-  constexpr uint32_t IDESC = make_idesc(BM, COUT);
-
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [W ring | A planes | barriers]
+  // carve: [W ring | A group buffers | barriers]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_ring = smem;
-  uint8_t* a_planes = w_ring + (size_t)p.stages * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_planes + (size_t)PLANES * p.plane_bytes);
-  uint64_t* full = bars;                  // [stages]
-  uint64_t* empty = bars + p.stages;      // [stages]
-  uint64_t* a_ready = bars + 2 * p.stages;
-  uint64_t* d_ready = a_ready + 1;
+  uint8_t* a_bufs = w_ring + (size_t)p.stages * p.stage_bytes;
+  const uint32_t a_buf_bytes = (uint32_t)p.PG * p.plane_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_bufs + (size_t)p.a_bufs * a_buf_bytes);
+  uint64_t* full = bars;                    // [stages]
+  uint64_t* empty = full + p.stages;        // [stages]
+  uint64_t* a_full = empty + p.stages;      // [a_bufs]
+  uint64_t* a_empty = a_full + p.a_bufs;    // [a_bufs]
+  uint64_t* d_ready = a_empty + p.a_bufs;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_ready + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * BM;
+  const int t0 = blockIdx.x * (BM * MT);
+  const int ntile = blockIdx.z;
+  const uint32_t tapmask = p.tapmask ? p.tapmask[ntile] : 0xFFFFFFFFu;
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(a_ready, 128);
+    for (int s = 0; s < p.a_bufs; ++s) {
+      mbar_init(&a_full[s], 128);
+      mbar_init(&a_empty[s], 1);
+    }
     mbar_init(d_ready, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tcgen05_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 5) tcgen05_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   if (warp == 4 && lane == 0)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
   tcgen05_fence_before();
@@ -209,143 +254,169 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_iters = NCHUNK * p.K;
+  const int chunks_per_group = p.PG * 8 / p.KC;
+  const int n_chunks = p.Cin / p.KC;
 
   if (warp == 4) {
-    // ===== TMA producer: weights, (chunk, tap) order =====
+    // ===== TMA producer: weights in (chunk, tap) order =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < n_iters; ++it) {
-        const int chunk = it / p.K, tap = it % p.K;
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], STAGE_BYTES);
-        tma_load_2d(w_ring + (size_t)stage * STAGE_BYTES, &wmap, &full[stage], chunk * KC, tap * COUT);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        for (int tap = 0; tap < p.K; ++tap) {
+          if (!((tapmask >> tap) & 1u)) continue;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], (uint32_t)p.stage_bytes);
+          tma_load_2d(w_ring + (size_t)stage * p.stage_bytes, &wmap, &full[stage], chunk * p.KC,
+                      tap * p.Cout + ntile * p.NT);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 5) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      mbar_wait(a_ready, 0);
-      tcgen05_fence_after();
-      const uint32_t a_base = smem_u32(a_planes);
+      const uint32_t w_layout = p.KC == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
+      const uint32_t w_sbo = 8u * (uint32_t)p.KC * 2u;
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < n_iters; ++it) {
-        const int chunk = it / p.K, tap = it % p.K;
-        mbar_wait(&full[stage], phase);
+      uint32_t started = 0;
+      for (int g = 0; g < p.n_groups; ++g) {
+        const int ab = g % p.a_bufs;
+        mbar_wait(&a_full[ab], (uint32_t)(g / p.a_bufs) & 1u);
         tcgen05_fence_after();
-        const uint32_t w_base = smem_u32(w_ring + (size_t)stage * STAGE_BYTES);
-        const uint32_t row_shift = (uint32_t)(tap * p.dil) * 16u;
+        const uint32_t a_base = smem_u32(a_bufs + (size_t)ab * a_buf_bytes);
+        const int c_end = min(n_chunks, (g + 1) * chunks_per_group);
+        for (int chunk = g * chunks_per_group; chunk < c_end; ++chunk) {
+          const int chunk_in_group = chunk - g * chunks_per_group;
+          for (int tap = 0; tap < p.K; ++tap) {
+            if (!((tapmask >> tap) & 1u)) continue;
+            mbar_wait(&full[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t w_base = smem_u32(w_ring + (size_t)stage * p.stage_bytes);
+            const uint32_t row_shift = (uint32_t)(tap * p.dil) * 16u;
+            for (int k16 = 0; k16 < p.KC / 16; ++k16) {
+              const uint32_t plane = (uint32_t)(chunk_in_group * (p.KC / 8) + 2 * k16);
+              const uint64_t bdesc = make_desc(w_base + k16 * 32, 0u, w_sbo, w_layout);
 #pragma unroll
-        for (int k16 = 0; k16 < KC / 16; ++k16) {
-          const uint32_t plane = (uint32_t)(chunk * (KC / 8) + 2 * k16);
-          const uint64_t adesc = make_desc(a_base + plane * p.plane_bytes + row_shift,
-                                           (uint32_t)p.plane_bytes, 128u, LAYOUT_NONE);
-          const uint64_t bdesc = make_desc(w_base + k16 * 32, 0u, W_SBO, W_LAYOUT);
-          umma_f16(tmem_base, adesc, bdesc, IDESC, (it | k16) != 0);
+              for (int m = 0; m < MT; ++m) {
+                const uint64_t adesc = make_desc(a_base + plane * p.plane_bytes + row_shift + m * (BM * 16),
+                                                 (uint32_t)p.plane_bytes, 128u, LAYOUT_NONE);
+                umma_f16(tmem_base + (uint32_t)(m * p.NT), adesc, bdesc, p.idesc, started);
+              }
+              started = 1;
+            }
+            tcgen05_commit(&empty[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
         }
-        tcgen05_commit(&empty[stage]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        tcgen05_commit(&a_empty[ab]);
       }
       tcgen05_commit(d_ready);
     }
   } else {
-    // ===== warps 0-3: stage the activation window, then epilogue =====
+    // ===== warps 0-3: stage the activation window group by group, then epilogue =====
+    const int len = p.lens ? p.lens[b] : p.L;
     {
-      const int rows = BM + (p.K - 1) * p.dil;
-      const int nvec = rows * PLANES;
-      const __half* xb = p.x + (size_t)b * p.L * CIN;
+      const int rows = BM * MT + (p.K - 1) * p.dil;
+      const TIn* xb = reinterpret_cast<const TIn*>(p.x) + (size_t)b * p.L * p.x_ld + p.x_coff;
       const float slope = p.in_slope;
-      for (int v = tid; v < nvec; v += 128) {
-        const int r = v / PLANES, pl = v % PLANES;
-        const int t = t0 - p.pad + r;
-        uint4 q = make_uint4(0u, 0u, 0u, 0u);
-        if (t >= 0 && t < p.L) {
-          q = *reinterpret_cast<const uint4*>(xb + (size_t)t * CIN + pl * 8);
-          if (slope != 1.f) {
+      const int planes_total = p.Cin / 8;
+      for (int g = 0; g < p.n_groups; ++g) {
+        const int ab = g % p.a_bufs;
+        mbar_wait(&a_empty[ab], ((uint32_t)(g / p.a_bufs) & 1u) ^ 1u);
+        uint8_t* dst = a_bufs + (size_t)ab * a_buf_bytes;
+        const int pl0 = g * p.PG;
+        const int npl = min(p.PG, planes_total - pl0);
+        const int nvec = rows * npl;
+        for (int v = tid; v < nvec; v += 128) {
+          const int r = v / npl, pl = v - r * npl;
+          const int t = t0 - p.pad + r;
+          uint4 q = make_uint4(0u, 0u, 0u, 0u);
+          if (t >= 0 && t < p.L && (!p.in_mask || t < len)) {
+            float f[8];
+            VecIO<TIn>::load8(xb + (size_t)t * p.x_ld + (pl0 + pl) * 8, f);
+            if (slope != 1.f) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * slope;
+            }
             __half2* h = reinterpret_cast<__half2*>(&q);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float2 f = __half22float2(h[i]);
-              f.x = f.x > 0.f ? f.x : f.x * slope;
-              f.y = f.y > 0.f ? f.y : f.y * slope;
-              h[i] = __floats2half2_rn(f.x, f.y);
-            }
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
           }
+          *reinterpret_cast<uint4*>(dst + (size_t)pl * p.plane_bytes + (size_t)r * 16) = q;
         }
-        *reinterpret_cast<uint4*>(a_planes + (size_t)pl * p.plane_bytes + (size_t)r * 16) = q;
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&a_full[ab]);
       }
-      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(a_ready);
     }
     mbar_wait(d_ready, 0);
     tcgen05_fence_after();
-    const int row = t0 + warp * 32 + lane;
-    const bool row_ok = row < p.L;
-    const size_t goff = ((size_t)b * p.L + (row_ok ? row : 0)) * COUT;
+    const int n0 = ntile * p.NT;
+    const float* bbias = p.bbias ? p.bbias + (size_t)b * p.bbias_ld + n0 : nullptr;
+    const float* bias = p.bias ? p.bias + n0 : nullptr;
 #pragma unroll 1
-    for (int c0 = 0; c0 < COUT; c0 += 32) {
-      uint32_t acc[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
-      if (!row_ok) continue;
-      float v[32];
+    for (int m = 0; m < MT; ++m) {
+      const int row = t0 + m * BM + warp * 32 + lane;
+      const bool row_ok = row < p.L;
+      const size_t grow = (size_t)b * p.L + (row_ok ? row : 0);
+      TOut* yrow = reinterpret_cast<TOut*>(p.y) + grow * p.y_ld + p.y_coff + n0;
+      const TOut* rrow = p.res ? reinterpret_cast<const TOut*>(p.res) + grow * p.res_ld + p.res_coff + n0 : nullptr;
+      const bool zero_row = p.out_mask && row >= len;
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.NT; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * p.NT + c0), acc);
+        if (!row_ok) continue;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-      if (p.bias) {
+        for (int q8 = 0; q8 < 4; ++q8) {
+          float v[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + c0 + j);
-      }
-      if (p.res) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + goff + c0);
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[q8 * 8 + j]);
+          const int c = c0 + q8 * 8;
+          if (bias) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 rv = rp[q];
-          const __half2* h = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(h[i]);
-            v[q * 8 + 2 * i] += p.res_scale * f.x;
-            v[q * 8 + 2 * i + 1] += p.res_scale * f.y;
+            for (int j = 0; j < 8; ++j) v[j] += __ldg(bias + c + j);
           }
-        }
-      }
-      if (p.out_scale != 1.f) {
+          if (bbias) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
-      }
-      uint4* yp = reinterpret_cast<uint4*>(p.y + goff + c0);
-      if (p.accumulate) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 ov = yp[q];
-          const __half2* h = reinterpret_cast<const __half2*>(&ov);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(h[i]);
-            v[q * 8 + 2 * i] += f.x;
-            v[q * 8 + 2 * i + 1] += f.y;
+            for (int j = 0; j < 8; ++j) v[j] += __ldg(bbias + c + j);
           }
+          if (rrow) {
+            float r[8];
+            VecIO<TOut>::load8(rrow + c, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += p.res_scale * r[j];
+          }
+          if (p.out_scale != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= p.out_scale;
+          }
+          if (p.accumulate) {
+            float o[8];
+            VecIO<TOut>::load8(yrow + c, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += o[j];
+          }
+          if (p.act == ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.out_slope;
+          } else if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (zero_row) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+          }
+          VecIO<TOut>::store8(yrow + c, v);
         }
-      }
-      if (p.act == ACT_LRELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.out_slope;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 ov;
-        __half2* h = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[q * 8 + 2 * i], v[q * 8 + 2 * i + 1]);
-        yp[q] = ov;
       }
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) tcgen05_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 5) tcgen05_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------ host side ----------------------------------
@@ -363,18 +434,18 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 struct MapKey {
-  const void* ptr; int cin, cout, k;
+  const void* ptr; int cin, cout, k, kc, nt;
   bool operator<(const MapKey& o) const {
-    return std::tie(ptr, cin, cout, k) < std::tie(o.ptr, o.cin, o.cout, o.k);
+    return std::tie(ptr, cin, cout, k, kc, nt) < std::tie(o.ptr, o.cin, o.cout, o.k, o.kc, o.nt);
   }
 };
 std::map<MapKey, CUtensorMap> g_maps;
 std::mutex g_maps_mu;
 
-// weights [K][Cout][Cin] f16 viewed as a 2-D tensor {Cin, K*Cout}
-bool get_wmap(const void* w16, int cin, int cout, int k, CUtensorMap* out) {
+// weights [K][Cout][Cin] f16 viewed as a 2-D tensor {Cin, K*Cout}; box {KC, NT}
+bool get_wmap(const void* w16, int cin, int cout, int k, int kc, int nt, CUtensorMap* out) {
   std::lock_guard<std::mutex> lk(g_maps_mu);
-  MapKey key{w16, cin, cout, k};
+  MapKey key{w16, cin, cout, k, kc, nt};
   auto it = g_maps.find(key);
   if (it != g_maps.end()) {
     *out = it->second;
@@ -382,10 +453,9 @@ bool get_wmap(const void* w16, int cin, int cout, int k, CUtensorMap* out) {
   }
   auto enc = get_encode();
   if (!enc) return false;
-  const int kc = cin >= 64 ? 64 : cin;
   cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)k * cout};
   cuuint64_t strides[1] = {(cuuint64_t)cin * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)cout};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)nt};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w16), dims, strides, box,
@@ -398,68 +468,132 @@ bool get_wmap(const void* w16, int cin, int cout, int k, CUtensorMap* out) {
   return true;
 }
 
-template <int CIN, int COUT>
-cudaError_t launch_t(const ConvArgs& a, cudaStream_t s) {
+int pick_nt(int cout) {
+  for (int nt : {256, 192, 128, 96, 64, 32})
+    if (cout % nt == 0) return nt;
+  return 0;
+}
+
+struct Plan {
+  int MT, NT, KC, PG, n_groups, a_bufs, stages, stage_bytes, plane_bytes, tmem_cols;
+  size_t smem;
+};
+
+// Choose the row-tile multiplicity, A grouping and weight-ring depth.  Preference: fit two
+// CTAs per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's epilogue overlaps the
+// other's MMAs; more row tiles per CTA amortise the weight stream from L2.
+bool make_plan(const ConvArgs& a, Plan* out) {
+  const int NT = pick_nt(a.Cout);
+  if (!NT) return false;
+  const int KC = a.Cin % 64 == 0 ? 64 : 32;
+  const int planes = a.Cin / 8;
+  const int PG = planes < GROUP_PLANES ? planes : GROUP_PLANES;
+  if ((PG * 8) % KC) return false;
+  const int n_groups = (planes + PG - 1) / PG;
+  const int a_bufs = n_groups > 1 ? 2 : 1;
+  const int stage_bytes = NT * KC * 2;
+  const int n_tiles_rows = (a.L_out + BM - 1) / BM;
+  const size_t fixed = 1024 + 512;
+  static const int forced_mt = [] {
+    const char* e = getenv("PG_UMMA_MT");   // tuning aid
+    return e ? atoi(e) : 0;
+  }();
+  Plan best{};
+  bool have = false;
+  for (int pass = 0; pass < 2 && !have; ++pass) {
+    const size_t budget = pass == 0 ? 113 * 1024 : 227 * 1024;
+    const int tmem_budget = pass == 0 ? 256 : 512;
+    for (int MT : {4, 2, 1}) {
+      if (MT > 1 && (NT & (NT - 1))) continue;          // multi-tile only with power-of-two N
+      if (MT * NT > tmem_budget) continue;
+      if (forced_mt > 0 && MT != forced_mt && MT != 1) continue;
+      const long ctas = (long)((n_tiles_rows + MT - 1) / MT) * a.B * (a.Cout / NT);
+      if (MT > 1 && forced_mt <= 0 && ctas < 2 * 148) continue;   // do not starve the grid on short inputs
+      const int rows = BM * MT + (a.K - 1) * a.dil;
+      const int rows_alloc = (rows + 7) & ~7;
+      const int plane_bytes = 16 * (rows_alloc + 1);
+      const size_t a_bytes = (size_t)a_bufs * PG * plane_bytes;
+      if (a_bytes + 2 * (size_t)stage_bytes + fixed > budget) continue;
+      int stages = (int)((budget - fixed - a_bytes) / stage_bytes);
+      if (stages > 6) stages = 6;
+      int tm = 32;
+      while (tm < MT * NT) tm <<= 1;
+      best = Plan{MT, NT, KC, PG, n_groups, a_bufs, stages, stage_bytes, plane_bytes, tm,
+                  fixed + a_bytes + (size_t)stages * stage_bytes};
+      have = true;
+      break;
+    }
+  }
+  if (!have) return false;
+  *out = best;
+  return true;
+}
+
+template <int MT, typename TIn, typename TOut>
+cudaError_t launch_t(const ConvArgs& a, const Plan& pl, cudaStream_t s) {
   CUtensorMap wmap;
-  if (!get_wmap(a.w16, CIN, COUT, a.K, &wmap)) return cudaErrorNotSupported;
-  constexpr int KC = CIN >= 64 ? 64 : CIN;
-  constexpr int STAGE_BYTES = COUT * KC * 2;
+  if (!get_wmap(a.w16, a.Cin, a.Cout, a.K, pl.KC, pl.NT, &wmap)) return cudaErrorNotSupported;
   UmmaParams p;
-  p.x = reinterpret_cast<const __half*>(a.x);
-  p.res = reinterpret_cast<const __half*>(a.res);
-  p.y = reinterpret_cast<__half*>(a.y);
-  p.bias = a.bias;
-  p.B = a.B; p.L = a.L_out; p.K = a.K; p.dil = a.dil; p.pad = a.pad;
+  p.x = a.x; p.x_ld = a.x_ld; p.x_coff = a.x_coff;
+  p.res = a.res; p.res_ld = a.res_ld; p.res_coff = a.res_coff; p.res_scale = a.res_scale;
+  p.y = a.y; p.y_ld = a.y_ld; p.y_coff = a.y_coff;
+  p.bias = a.bias; p.bbias = a.bbias; p.bbias_ld = a.bbias_ld;
+  p.lens = a.lens; p.in_mask = a.in_mask; p.out_mask = a.out_mask;
+  p.tapmask = a.tapmask;
+  p.B = a.B; p.L = a.L_out; p.Cin = a.Cin; p.Cout = a.Cout; p.K = a.K; p.dil = a.dil; p.pad = a.pad;
+  p.NT = pl.NT;
   p.in_slope = a.in_slope; p.out_slope = a.out_slope; p.out_scale = a.out_scale;
-  p.res_scale = a.res_scale; p.act = a.act; p.accumulate = a.accumulate;
-  const int rows = BM + (a.K - 1) * a.dil;
-  p.rows_alloc = (rows + 7) & ~7;
-  p.plane_bytes = 16 * (p.rows_alloc + 1);
-  const size_t a_bytes = (size_t)(CIN / 8) * p.plane_bytes;
-  // as many weight stages as fit next to a second resident CTA, 2..6
-  int stages = (int)((110 * 1024 - (long)a_bytes - 2048) / STAGE_BYTES);
-  if (stages < 3) stages = (int)((225 * 1024 - (long)a_bytes - 2048) / STAGE_BYTES);
-  if (stages > 6) stages = 6;
-  if (stages > a.K * (CIN / KC)) stages = a.K * (CIN / KC);
-  if (stages < 1) return cudaErrorInvalidValue;
-  p.stages = stages;
-  const size_t smem = 1024 + (size_t)stages * STAGE_BYTES + a_bytes + 256;
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  p.act = a.act; p.accumulate = a.accumulate;
+  p.plane_bytes = pl.plane_bytes; p.KC = pl.KC; p.PG = pl.PG; p.n_groups = pl.n_groups;
+  p.a_bufs = pl.a_bufs; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes;
+  p.tmem_cols = pl.tmem_cols;
+  p.idesc = make_idesc(BM, pl.NT);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<CIN, COUT>,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<MT, TIn, TOut>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  dim3 grid((a.L_out + BM - 1) / BM, a.B);
-  conv_umma_kernel<CIN, COUT><<<grid, NTHREADS, smem, s>>>(wmap, p);
+  dim3 grid((a.L_out + BM * MT - 1) / (BM * MT), a.B, a.Cout / pl.NT);
+  conv_umma_kernel<MT, TIn, TOut><<<grid, NTHREADS, pl.smem, s>>>(wmap, p);
   return cudaGetLastError();
+}
+
+template <typename TIn, typename TOut>
+cudaError_t launch_mt(const ConvArgs& a, const Plan& pl, cudaStream_t s) {
+  switch (pl.MT) {
+    case 1: return launch_t<1, TIn, TOut>(a, pl, s);
+    case 2: return launch_t<2, TIn, TOut>(a, pl, s);
+    case 4: return launch_t<4, TIn, TOut>(a, pl, s);
+  }
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace
 
+int umma_pick_nt(int cout) { return pick_nt(cout); }
+
 bool umma_conv_supported(const ConvArgs& a) {
-  if (!a.w16 || a.Cin != a.Cout) return false;
-  if (a.Cin != 32 && a.Cin != 64 && a.Cin != 128 && a.Cin != 256) return false;
-  if (a.x_ld != a.Cin || a.x_coff != 0 || a.y_ld != a.Cout || a.y_coff != 0) return false;
-  if (a.res && (a.res_ld != a.Cout || a.res_coff != 0)) return false;
-  if (a.in_mask || a.out_mask || a.bbias) return false;
+  if (!a.w16) return false;
+  if (a.Cin % 32 || a.Cin < 32) return false;
+  if (a.x_ld % 8 || a.x_coff % 8 || a.y_ld % 8 || a.y_coff % 8) return false;
+  if (a.res && (a.res_ld % 8 || a.res_coff % 8)) return false;
   if (a.L_in != a.L_out) return false;
-  if (a.act != ACT_NONE && a.act != ACT_LRELU) return false;
-  if ((a.K - 1) * a.dil > MAX_WINDOW - BM || a.K < 1) return false;
-  return true;
+  if (a.act == ACT_TANH) return false;
+  if (a.K < 1 || a.K > 32) return false;
+  if ((a.in_mask || a.out_mask) && !a.lens) return false;
+  Plan pl;
+  return make_plan(a, &pl);
 }
 
-cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
-  if (!umma_conv_supported(a)) return cudaErrorInvalidValue;
-  switch (a.Cin) {
-    case 32: return launch_t<32, 32>(a, s);
-    case 64: return launch_t<64, 64>(a, s);
-    case 128: return launch_t<128, 128>(a, s);
-    case 256: return launch_t<256, 256>(a, s);
-  }
-  return cudaErrorInvalidValue;
+cudaError_t launch_conv_umma(const ConvArgs& a, DType in_dt, DType out_dt, cudaStream_t s) {
+  Plan pl;
+  if (!umma_conv_supported(a) || !make_plan(a, &pl)) return cudaErrorInvalidValue;
+  if (in_dt == DT_F16 && out_dt == DT_F16) return launch_mt<__half, __half>(a, pl, s);
+  if (in_dt == DT_F32 && out_dt == DT_F32) return launch_mt<float, float>(a, pl, s);
+  if (in_dt == DT_F32 && out_dt == DT_F16) return launch_mt<float, __half>(a, pl, s);
+  return launch_mt<__half, float>(a, pl, s);
 }
 
 }  // namespace pg

@@ -35,7 +35,7 @@ def snr_db(a, b):
     return float(10 * torch.log10((b ** 2).sum() / ((a - b) ** 2).sum().clamp_min(1e-300)))
 
 
-def taps(mode, name="v2-40k", T=24, B=1, seed=0):
+def taps(mode, name="v2-40k", T=24, B=1, seed=0):  # noqa: C901
     import torch
     import polgen_rvc_b200 as pg
     from polgen_rvc_b200 import _lib
@@ -80,17 +80,43 @@ def taps(mode, name="v2-40k", T=24, B=1, seed=0):
     emit(rec)
 
 
+def snrscan():
+    """wave SNR over configs / seeds / lengths, tcgen05 and CUDA-core paths."""
+    import torch
+    import polgen_rvc_b200 as pg
+    from polgen_rvc_b200 import _lib
+    from oracle import rvc_oracle as orc
+    d = torch.device("cuda:0")
+    for name, T, seed in [("v1-40k", 30, 8), ("v1-40k", 30, 9), ("v2-40k", 30, 8), ("v2-48k", 30, 8),
+                          ("v2-32k", 30, 8), ("v1-40k", 13, 3), ("v2-40k", 100, 4), ("v2-48k", 100, 5),
+                          ("v1-40k", 100, 6), ("v2-32k", 100, 7)]:
+        cfg = pg.CONFIGS[name]
+        sd = pg.synth_weights(cfg, seed=seed)
+        inp = pg.synth_inputs(cfg, 1, T, seed=seed)
+        eps_zp, eps_src = pg.synth_noise(cfg, 1, T, seed=seed)
+        o = orc.infer(sd, cfg, *inp, eps_zp, eps_src)[0][:, 0]
+        rec = {"stage": "snrscan", "config": name, "T": T, "seed": seed, "o_rms": float(o.pow(2).mean().sqrt())}
+        for mode, flags in (("umma", 0), ("simt", _lib.PG_FLAG_FORCE_SIMT)):
+            eng = pg.Engine(cfg, pg.fold_state_dict(sd), 0, flags)
+            wave, _ = eng.infer(*[t.to(d) for t in inp], eps_zp.transpose(1, 2).contiguous().to(d),
+                                eps_src.reshape(1, -1).contiguous().to(d), 0)
+            rec[mode] = {"snr_db": round(snr_db(wave.cpu(), o), 2), "maxabs": float((wave.cpu() - o).abs().max())}
+            eng.close()
+        emit(rec)
+
+
 def convop():
     import torch
     from polgen_rvc_b200 import _lib
     lib = _lib.load()
     d = torch.device("cuda:0")
     g = torch.Generator().manual_seed(0)
-    for (Cc, K, dil, L, B) in [(128, 3, 1, 1000, 1), (128, 7, 3, 1000, 2), (128, 11, 5, 4096, 1),
-                               (64, 3, 1, 777, 1), (64, 11, 5, 2048, 1), (32, 7, 1, 3000, 1),
-                               (32, 11, 3, 4096, 2), (256, 3, 1, 600, 1), (256, 11, 5, 1200, 1),
-                               (128, 7, 1, 120000, 1), (64, 7, 1, 240000, 1), (32, 7, 1, 480000, 1),
-                               (256, 7, 1, 12000, 1)]:
+    for (Cc, K, dil, L, B) in [(128, 7, 3, 1000, 2), (64, 11, 5, 2048, 1), (32, 11, 3, 4096, 2),
+                               (256, 3, 1, 600, 1),
+                               (128, 3, 1, 120000, 1), (128, 7, 1, 120000, 1), (128, 11, 5, 120000, 1),
+                               (64, 3, 1, 240000, 1), (64, 7, 1, 240000, 1), (64, 11, 5, 240000, 1),
+                               (32, 3, 1, 480000, 1), (32, 7, 1, 480000, 1), (32, 11, 5, 480000, 1),
+                               (256, 3, 1, 12000, 1), (256, 7, 1, 12000, 1), (256, 11, 5, 12000, 1)]:
         x = (torch.randn(B, L, Cc, generator=g) * 1.0).half()
         w = torch.randn(Cc, Cc, K, generator=g) * (1.0 / (Cc * K) ** 0.5)
         bias = torch.randn(Cc, generator=g) * 0.1
@@ -99,7 +125,7 @@ def convop():
         ref = torch.nn.functional.conv1d(
             torch.nn.functional.leaky_relu(xd.float(), 0.1).transpose(1, 2), w.half().float().to(d), bias.to(d),
             dilation=dil, padding=(K * dil - dil) // 2).transpose(1, 2) + rd.float()
-        rec = {"stage": "convop", "C": Cc, "K": K, "dil": dil, "L": L, "B": B}
+        rec = {"stage": "convop", "C": Cc, "K": K, "dil": dil, "L": L, "B": B, "mt": os.environ.get("PG_UMMA_MT", "auto")}
         for impl, nm in [(0, "simt"), (1, "umma")]:
             y = torch.zeros(B, L, Cc, device=d, dtype=torch.half)
             ms = C.c_float(0)
@@ -145,6 +171,38 @@ def timeit(name="v2-48k", T=1000, B=1, mode="umma"):
           "ws_MB": eng.workspace_bytes(B, T) / 2 ** 20})
 
 
+def run_jobs(jobs):
+    for j in jobs:
+        env = dict(os.environ)
+        if isinstance(j, tuple):
+            env.update(j[1])
+            j = j[0]
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__)] + j, timeout=420,
+                               capture_output=True, text=True, env=env)
+            sys.stdout.write(r.stdout)
+            if r.returncode != 0:
+                emit({"stage": "job_failed", "job": j, "rc": r.returncode, "stderr": r.stderr[-3000:],
+                      "stdout_tail": r.stdout[-1500:]})
+        except subprocess.TimeoutExpired:
+            emit({"stage": "job_timeout", "job": j})
+        print(f"# job {j} took {time.time() - t0:.1f}s", flush=True)
+
+
+def run_tune():
+    run_jobs([
+        ["taps", "umma", "v2-40k", "24", "1"],
+        ["taps", "umma", "v2-48k", "300", "1"],
+        (["convop"], {"PG_UMMA_MT": "1"}),
+        (["convop"], {"PG_UMMA_MT": "2"}),
+        (["convop"], {"PG_UMMA_MT": "4"}),
+        ["convop"],
+        ["time", "v2-48k", "1000", "1", "umma"],
+        ["time", "v2-48k", "4000", "1", "umma"],
+    ])
+
+
 def run_all():
     jobs = [
         ["taps", "simt", "v2-40k", "24", "1"],
@@ -157,18 +215,7 @@ def run_all():
         ["time", "v2-48k", "1000", "1", "umma"],
         ["time", "v2-48k", "4000", "1", "umma"],
     ]
-    for j in jobs:
-        t0 = time.time()
-        try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__)] + j, timeout=420,
-                               capture_output=True, text=True)
-            sys.stdout.write(r.stdout)
-            if r.returncode != 0:
-                emit({"stage": "job_failed", "job": j, "rc": r.returncode, "stderr": r.stderr[-3000:],
-                      "stdout_tail": r.stdout[-1500:]})
-        except subprocess.TimeoutExpired:
-            emit({"stage": "job_timeout", "job": j})
-        print(f"# job {j} took {time.time() - t0:.1f}s", flush=True)
+    run_jobs(jobs)
 
 
 if __name__ == "__main__":
@@ -176,9 +223,13 @@ if __name__ == "__main__":
     a = sys.argv[2:]
     if cmd == "all":
         run_all()
+    elif cmd == "tune":
+        run_tune()
     elif cmd == "taps":
         taps(a[0], a[1] if len(a) > 1 else "v2-40k", int(a[2]) if len(a) > 2 else 24,
-             int(a[3]) if len(a) > 3 else 1)
+             int(a[3]) if len(a) > 3 else 1, int(a[4]) if len(a) > 4 else 0)
+    elif cmd == "snrscan":
+        snrscan()
     elif cmd == "convop":
         convop()
     elif cmd == "time":
