@@ -85,6 +85,7 @@ typedef struct pg_config {
 #define PG_FLAG_FORCE_SIMT 1   /* run every conv on the CUDA-core fp32 kernels (validation aid) */
 #define PG_FLAG_KEEP_TAPS 2    /* keep copies of intermediates for pg_debug_fetch */
 #define PG_FLAG_PROFILE 4      /* CUDA events around every conv launch (pg_profile_read) */
+#define PG_FLAG_F16_LATENTS 8  /* TextEncoder / flow GEMMs with single-pass f16 tensor-core operands (default: fp32-accurate) */
 
 typedef struct pg_handle_s* pg_handle;
 

@@ -18,6 +18,7 @@ PG_MAX_DILATIONS = 4
 PG_FLAG_FORCE_SIMT = 1
 PG_FLAG_KEEP_TAPS = 2
 PG_FLAG_PROFILE = 4
+PG_FLAG_F16_LATENTS = 8
 PG_F32 = 0
 
 

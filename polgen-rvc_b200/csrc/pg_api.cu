@@ -321,7 +321,7 @@ Ws plan_ws(const pg_config& c, int B, int T) {
   w.source = p.take(sizeof(float) * B * L);
   w.phase = p.take(sizeof(double) * BT);
   w.stage_elems = max_elems;
-  for (int i = 0; i < 5; ++i) w.stage[i] = p.take(sizeof(__half) * max_elems + 4096);
+  for (int i = 0; i < 5; ++i) w.stage[i] = p.take(sizeof(float) * max_elems + 4096);
   w.total = p.total;
   return w;
 }
@@ -386,14 +386,19 @@ cudaEvent_t take_event(pg_handle h) {
   return e;
 }
 
-int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_dt, DType out_dt) {
+// `latent` marks the TextEncoder / flow GEMMs: their results are returned to the caller (m_p,
+// logs_p, z_p, z) and feed the whole decoder, so unless PG_FLAG_F16_LATENTS is set they stay on
+// the fp32 path (single-pass f16 operands cost ~5 dB of waveform SNR on short clips).
+int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_dt, DType out_dt,
+             bool latent = false) {
   a.w = w.w;
   a.w16 = w.w16;
   a.bias = w.bias;
   a.Cin = w.Cin;
   a.Cout = w.Cout;
   a.K = w.K;
-  const bool force_simt = (h->cfg.flags & PG_FLAG_FORCE_SIMT) != 0;
+  const bool force_simt = (h->cfg.flags & PG_FLAG_FORCE_SIMT) != 0 ||
+                          (latent && !(h->cfg.flags & PG_FLAG_F16_LATENTS));
   a.tapmask = w.tapmask;
   const bool umma = !force_simt && w.w16 && umma_conv_supported(a);
   const bool prof = (h->cfg.flags & PG_FLAG_PROFILE) != 0;
@@ -428,7 +433,7 @@ int run_text_encoder(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, con
     ConvArgs a;
     a.x = phone; a.x_ld = c.input_dim; a.B = B; a.L_in = T; a.L_out = T;
     a.y = x; a.y_ld = H;
-    PG_TRY(run_conv(h, s, a, h->emb_phone, DT_F32, DT_F32));
+    PG_TRY(run_conv(h, s, a, h->emb_phone, DT_F32, DT_F32, true));
     PG_LAUNCH(h, launch_embed_finish(x, h->emb_pitch, at<int>(h, w.pitch), lens, B, T, H,
                                      sqrtf((float)H), s));
   }
@@ -443,21 +448,21 @@ int run_text_encoder(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, con
     a.B = B; a.L_in = T; a.L_out = T; a.lens = lens;
     // q, k, v 1x1 convs fused into one GEMM (attentions.py:64-66)
     a.x = x; a.x_ld = H; a.y = qkv; a.y_ld = 3 * H;
-    PG_TRY(run_conv(h, s, a, L.qkv, DT_F32, DT_F32));
+    PG_TRY(run_conv(h, s, a, L.qkv, DT_F32, DT_F32, true));
     PG_LAUNCH(h, launch_rel_attention(qkv, L.rel_k, L.rel_v, lens, att, B, T, H, c.n_heads,
                                       c.attn_window, s));
     a.x = att; a.x_ld = H; a.y = y; a.y_ld = H;
-    PG_TRY(run_conv(h, s, a, L.o, DT_F32, DT_F32));
+    PG_TRY(run_conv(h, s, a, L.o, DT_F32, DT_F32, true));
     PG_LAUNCH(h, launch_add_layernorm(x, y, L.g1, L.b1, B * T, H, s));
     // FFN (attentions.py:195-203): conv(x*m) -> relu -> conv(.*m) -> *m, same padding
     ConvArgs f1 = a;
     f1.x = x; f1.x_ld = H; f1.y = ffn; f1.y_ld = F; f1.in_mask = 1; f1.pad = (ksz - 1) / 2;
     f1.act = ACT_RELU;
-    PG_TRY(run_conv(h, s, f1, L.ffn1, DT_F32, DT_F32));
+    PG_TRY(run_conv(h, s, f1, L.ffn1, DT_F32, DT_F32, true));
     ConvArgs f2 = a;
     f2.x = ffn; f2.x_ld = F; f2.y = y; f2.y_ld = H; f2.in_mask = 1; f2.pad = (ksz - 1) / 2;
     f2.out_mask = 1;
-    PG_TRY(run_conv(h, s, f2, L.ffn2, DT_F32, DT_F32));
+    PG_TRY(run_conv(h, s, f2, L.ffn2, DT_F32, DT_F32, true));
     PG_LAUNCH(h, launch_add_layernorm(x, y, L.g2, L.b2, B * T, H, s));
     PG_TRY(record_tap(h, s, "enc.layer" + std::to_string(i), x, DT_F32, B, T, H));
   }
@@ -465,7 +470,7 @@ int run_text_encoder(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, con
   ConvArgs a;
   a.B = B; a.L_in = T; a.L_out = T; a.lens = lens; a.in_mask = 1; a.out_mask = 1;
   a.x = x; a.x_ld = H; a.y = at<float>(h, w.stats); a.y_ld = 2 * c.inter_channels;
-  PG_TRY(run_conv(h, s, a, h->proj, DT_F32, DT_F32));
+  PG_TRY(run_conv(h, s, a, h->proj, DT_F32, DT_F32, true));
   return PG_OK;
 }
 
@@ -492,22 +497,22 @@ int run_flow(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, float* z) {
     // h = pre(x0) * mask
     ConvArgs pre = a;
     pre.x = z; pre.x_ld = C; pre.x_coff = x0_off; pre.y = fh; pre.y_ld = H; pre.out_mask = 1;
-    PG_TRY(run_conv(h, s, pre, F.pre, DT_F32, DT_F32));
+    PG_TRY(run_conv(h, s, pre, F.pre, DT_F32, DT_F32, true));
     for (int l = 0; l < nl; ++l) {
       ConvArgs in = a;
       in.x = fh; in.x_ld = H; in.y = fa; in.y_ld = 2 * H; in.pad = (c.flow_wn_kernel - 1) / 2;
       in.bbias = gc + (size_t)l * 2 * H; in.bbias_ld = gl;
-      PG_TRY(run_conv(h, s, in, F.in_layers[l], DT_F32, DT_F32));
+      PG_TRY(run_conv(h, s, in, F.in_layers[l], DT_F32, DT_F32, true));
       PG_LAUNCH(h, launch_gate(fa, acts, (int64_t)B * T, H, s));
       // skip (+)= res_skip[:, H:] (or the whole output on the last layer)
       ConvArgs sk = a;
       sk.x = acts; sk.x_ld = H; sk.y = skip; sk.y_ld = H; sk.accumulate = l > 0;
-      PG_TRY(run_conv(h, s, sk, F.skip[l], DT_F32, DT_F32));
+      PG_TRY(run_conv(h, s, sk, F.skip[l], DT_F32, DT_F32, true));
       if (l < nl - 1) {   // h = (h + res_skip[:, :H]) * mask
         ConvArgs rs = a;
         rs.x = acts; rs.x_ld = H; rs.y = fh; rs.y_ld = H; rs.res = fh; rs.res_ld = H;
         rs.out_mask = 1;
-        PG_TRY(run_conv(h, s, rs, F.res[l], DT_F32, DT_F32));
+        PG_TRY(run_conv(h, s, rs, F.res[l], DT_F32, DT_F32, true));
       }
     }
     // x1 = (x1 - post(skip * mask) * mask) * mask
@@ -516,7 +521,7 @@ int run_flow(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, float* z) {
     po.y = z; po.y_ld = C; po.y_coff = x1_off;
     po.res = z; po.res_ld = C; po.res_coff = x1_off; po.res_scale = -1.f; po.out_scale = -1.f;
     po.out_mask = 1;
-    PG_TRY(run_conv(h, s, po, F.post, DT_F32, DT_F32));
+    PG_TRY(run_conv(h, s, po, F.post, DT_F32, DT_F32, true));
     PG_TRY(record_tap(h, s, "flow." + std::to_string(f), z, DT_F32, B, T, C));
   }
   return PG_OK;
@@ -531,8 +536,11 @@ int run_generator(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const 
   float* dcond = at<float>(h, w.dcond);
   PG_LAUNCH(h, launch_cond_gemv(h->emb_g, at<int>(h, w.sid), h->dec_cond_w, h->dec_cond_b, dcond, B,
                                 c.gin_channels, C0, s));
-  __half* buf[5];
-  for (int i = 0; i < 5; ++i) buf[i] = at<__half>(h, w.stage[i]);
+  // Five rotating stage buffers.  The residual stream of the LAST stage is kept in fp32: its mean
+  // feeds conv_post directly, and with random-init conv_post weights the 224-term sum cancels by
+  // ~35 dB, so one f16 rounding (2^-11) of that stream is already the whole 40 dB error budget.
+  char* buf[5];
+  for (int i = 0; i < 5; ++i) buf[i] = at<char>(h, w.stage[i]);
   // conv_pre(z * mask) + cond(g)
   {
     ConvArgs a;
@@ -544,38 +552,40 @@ int run_generator(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const 
   }
   PG_TRY(record_tap(h, s, "dec.conv_pre", buf[0], DT_F16, B, T, C0));
   int cur = 0;          // buffer holding the stage input
+  DType cur_dt = DT_F16;
   int64_t L = T;
   const int64_t Lsrc = (int64_t)T * h->upp;
   for (int i = 0; i < c.n_ups; ++i) {
     const StageW& S = h->stages[i];
     const int C = S.C;
+    const DType sdt = i == c.n_ups - 1 ? DT_F32 : DT_F16;   // storage of this stage's residual stream
     // free buffers: everything except cur
     int fr[4], nf = 0;
     for (int k = 0; k < 5; ++k)
       if (k != cur) fr[nf++] = k;
-    __half* xin = buf[fr[0]];
-    __half* xa = buf[fr[1]];
-    __half* xb = buf[fr[2]];
-    __half* tmp = buf[fr[3]];
-    __half* acc = buf[cur];   // the ups input is dead once xin is produced
+    char* xin = buf[fr[0]];
+    char* xa = buf[fr[1]];
+    char* xb = buf[fr[2]];
+    char* tmp = buf[fr[3]];
+    char* acc = buf[cur];   // the ups input is dead once xin is produced
     // x = ups(lrelu(x, 0.1)) as a dense conv over input frames
     {
       ConvArgs a;
       a.B = B; a.L_in = (int)L; a.L_out = (int)L;
       a.x = buf[cur]; a.x_ld = S.up.Cin; a.in_slope = 0.1f; a.pad = S.up_pad;
       a.y = xin; a.y_ld = S.up.Cout;
-      PG_TRY(run_conv(h, s, a, S.up, DT_F16, DT_F16));
+      PG_TRY(run_conv(h, s, a, S.up, cur_dt, sdt));
     }
     L *= S.u;
     // x = x + noise_convs[i](har_source)
-    PG_LAUNCH(h, launch_noise_inject(xin, source, S.noise_w, S.noise_b, B, (int)L, C, (int)Lsrc,
+    PG_LAUNCH(h, launch_noise_inject(xin, sdt, source, S.noise_w, S.noise_b, B, (int)L, C, (int)Lsrc,
                                      S.noise_k, S.noise_stride, S.noise_pad, s));
-    PG_TRY(record_tap(h, s, "dec.ups" + std::to_string(i), xin, DT_F16, B, L, C));
+    PG_TRY(record_tap(h, s, "dec.ups" + std::to_string(i), xin, sdt, B, L, C));
     // x = mean_j ResBlock_j(x)   (residuals.py:45-53)
     const int nk = c.n_resblock_kernels, nd = c.n_dilations;
     for (int j = 0; j < nk; ++j) {
       const int ksz = c.resblock_kernel_sizes[j];
-      const __half* xc = xin;
+      const char* xc = xin;
       for (int d = 0; d < nd; ++d) {
         const int dil = c.resblock_dilations[j][d];
         const bool last = d == nd - 1;
@@ -584,26 +594,27 @@ int run_generator(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const 
         a1.x = xc; a1.x_ld = C; a1.in_slope = 0.1f; a1.dil = dil; a1.pad = (ksz * dil - dil) / 2;
         a1.act = ACT_LRELU; a1.out_slope = 0.1f;
         a1.y = tmp; a1.y_ld = C;
-        PG_TRY(run_conv(h, s, a1, S.c1[j * nd + d], DT_F16, DT_F16));
+        PG_TRY(run_conv(h, s, a1, S.c1[j * nd + d], sdt, DT_F16));
         ConvArgs a2;
         a2.B = B; a2.L_in = (int)L; a2.L_out = (int)L;
         a2.x = tmp; a2.x_ld = C; a2.pad = (ksz - 1) / 2;
         a2.res = xc; a2.res_ld = C;
-        __half* dst = last ? acc : (xc == xa ? xb : xa);
+        char* dst = last ? acc : (xc == xa ? xb : xa);
         a2.y = dst; a2.y_ld = C;
         if (last) {
           a2.out_scale = 1.f / nk;
           a2.accumulate = j > 0;
         }
-        PG_TRY(run_conv(h, s, a2, S.c2[j * nd + d], DT_F16, DT_F16));
+        PG_TRY(run_conv(h, s, a2, S.c2[j * nd + d], DT_F16, sdt));
         xc = dst;
       }
     }
-    PG_TRY(record_tap(h, s, "dec.stage" + std::to_string(i), acc, DT_F16, B, L, C));
+    PG_TRY(record_tap(h, s, "dec.stage" + std::to_string(i), acc, sdt, B, L, C));
+    cur_dt = sdt;
     // acc lives in buf[cur]: the next stage reads it
   }
   const int Cl = h->stages.back().C;
-  PG_LAUNCH(h, launch_conv_post(buf[cur], h->conv_post_w, wave, B, (int)L, Cl, 7, 0.01f, s));
+  PG_LAUNCH(h, launch_conv_post(buf[cur], cur_dt, h->conv_post_w, wave, B, (int)L, Cl, 7, 0.01f, s));
   return PG_OK;
 }
 

@@ -82,12 +82,12 @@ cudaError_t launch_source(const float* f0, const float* eps, uint64_t seed, floa
                           double* frame_phase, float* source, float* sine, int B, int T, int upp,
                           int sr, cudaStream_t s);
 // x[b][t][c] += bn[c] + sum_j wn[c][j] * src[b][t*stride + j - pad]
-cudaError_t launch_noise_inject(__half* x, const float* src, const float* wn, const float* bn,
+cudaError_t launch_noise_inject(void* x, DType dt, const float* src, const float* wn, const float* bn,
                                 int B, int L, int C, int Lsrc, int k, int stride, int pad,
                                 cudaStream_t s);
 // wave = tanh(conv_post(lrelu(x, 0.01)))
-cudaError_t launch_conv_post(const __half* x, const float* w /*[K][C]*/, float* wave, int B, int L,
-                             int C, int K, float in_slope, cudaStream_t s);
+cudaError_t launch_conv_post(const void* x, DType dt, const float* w /*[K][C]*/, float* wave, int B,
+                             int L, int C, int K, float in_slope, cudaStream_t s);
 cudaError_t launch_cast_f16_to_f32(const __half* x, float* y, int64_t n, cudaStream_t s);
 
 }  // namespace pg

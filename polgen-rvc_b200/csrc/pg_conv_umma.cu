@@ -25,6 +25,7 @@
 // warp 4 is the TMA producer, warp 5 owns TMEM and issues the MMAs.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <map>
@@ -38,8 +39,11 @@ namespace pg {
 namespace {
 
 constexpr int BM = 128;              // rows per accumulator tile
-constexpr int NTHREADS = 192;
-constexpr int GROUP_PLANES = 32;     // 256 channels per A group
+constexpr int EPI_WARPS = 8, LOAD_WARPS = 8;
+constexpr int LOAD_THREADS = LOAD_WARPS * 32, EPI_THREADS = EPI_WARPS * 32;
+constexpr int TMA_WARP = EPI_WARPS + LOAD_WARPS, MMA_WARP = TMA_WARP + 1;
+constexpr int NTHREADS = (MMA_WARP + 1) * 32;
+constexpr int GROUP_PLANES = 16;     // 128 channels per activation-ring slot
 
 // ------------------------------ PTX wrappers -------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -78,6 +82,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+// One lane of a fully converged warp.  The producer / MMA warps run their loops warp-uniformly and
+// predicate only the issue on this: tcgen05.mma and TMA take uniform-register operands, and code
+// under `if (lane == 0)` makes the compiler emit per-operand waterfall loops around every issue.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -165,26 +181,33 @@ struct UmmaParams {
   void* y; int y_ld, y_coff;
   const float* bias; const float* bbias; int bbias_ld;
   const int* lens; int in_mask, out_mask;
-  const uint32_t* tapmask;     // [n_tiles] bit t set = tap t has non-zero weights (nullable)
+  const uint32_t* tapmask;     // [n_ntiles] bit t set = tap t has non-zero weights (nullable)
   int B, L;
   int Cin, Cout, K, dil, pad;
   int NT;                       // Cout tile (accumulator columns)
+  int n_row_tiles, n_ntiles, total_tiles;
   float in_slope, out_slope, out_scale;
   int act, accumulate;
-  int plane_bytes;              // A plane pitch (16 B * (rows_alloc + 1))
+  int plane_bytes;              // A plane pitch (16 B * (rows_alloc + pad))
   int KC;                       // channels per weight stage: 64 (SW128) or 32 (SW64)
-  int PG, n_groups, a_bufs;     // planes per A group, groups, group buffers
-  int stages, stage_bytes;      // weight ring
+  int PG, n_groups;             // planes per A group, groups per tile
+  int a_slots, a_slot_bytes;    // activation ring
+  int stages, stage_bytes;      // weight ring (or, when resident, all K*chunks tiles of the layer)
+  int resident;                 // 1: weights loaded once per CTA, no ring
+  int rotate;                   // ring mode: per-row-tile rotation of the (chunk, tap) walk
   int tmem_cols;
   uint32_t idesc;
+  int debug;   // PG_UMMA_DEBUG bitmask (timing experiments only): 1 no A loads, 2 no epilogue I/O, 4 no MMA
 };
 
 template <typename T> struct VecIO;
 template <> struct VecIO<__half> {
-  // 8 channels -> 8 floats
-  static __device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
-    const uint4 q = *reinterpret_cast<const uint4*>(p);
-    const __half2* h = reinterpret_cast<const __half2*>(&q);
+  static constexpr int RAW = 1;   // uint4 per 8 channels
+  static __device__ __forceinline__ void load_raw(const __half* p, uint4 (&q)[1]) {
+    q[0] = *reinterpret_cast<const uint4*>(p);
+  }
+  static __device__ __forceinline__ void unpack(const uint4 (&q)[1], float (&v)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&q[0]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 f = __half22float2(h[i]);
@@ -201,9 +224,16 @@ template <> struct VecIO<__half> {
   }
 };
 template <> struct VecIO<float> {
-  static __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  static constexpr int RAW = 2;
+  static __device__ __forceinline__ void load_raw(const float* p, uint4 (&q)[2]) {
+    q[0] = *reinterpret_cast<const uint4*>(p);
+    q[1] = *reinterpret_cast<const uint4*>(p + 4);
+  }
+  static __device__ __forceinline__ void unpack(const uint4 (&q)[2], float (&v)[8]) {
+    v[0] = __uint_as_float(q[0].x); v[1] = __uint_as_float(q[0].y);
+    v[2] = __uint_as_float(q[0].z); v[3] = __uint_as_float(q[0].w);
+    v[4] = __uint_as_float(q[1].x); v[5] = __uint_as_float(q[1].y);
+    v[6] = __uint_as_float(q[1].z); v[7] = __uint_as_float(q[1].w);
   }
   static __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -211,212 +241,455 @@ template <> struct VecIO<float> {
   }
 };
 
+// PG_UMMA_DEBUG & 8: CTA 0 records (role, event, tile, globaltimer) -- timing experiments only
+__device__ unsigned long long g_trace[8192];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ void trace(const UmmaParams& p, int role, int ev, int tile) {
+  if ((p.debug & 8) && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned int i = atomicAdd(&g_trace_n, 1u);
+    if (i < 8192) g_trace[i] = (t << 20) | ((unsigned long long)role << 16) | ((unsigned long long)ev << 12) | (unsigned)(tile & 0xFFF);
+  }
+}
+
+struct TileCoord { int rt, b, ntile; };
+__device__ __forceinline__ TileCoord decode_tile(int id, const UmmaParams& p) {
+  TileCoord c;
+  c.rt = id % p.n_row_tiles;
+  const int tmp = id / p.n_row_tiles;
+  c.b = tmp % p.B;
+  c.ntile = tmp / p.B;
+  return c;
+}
+
+// Persistent, warp-specialised: every CTA walks tiles id = blockIdx.x, +gridDim.x, ...
+//   warps 0-7   epilogue  (TMEM lane quarter = warp % 4, column half = warp / 4)
+//   warps 8-15  A loaders (global -> f16 planes in the activation ring)
+//   warp  16    TMA producer for the weight ring
+//   warp  17    TMEM owner + MMA issuer
+// Rings: activation slots (a_full/a_empty), weight stages (full/empty), two TMEM
+// accumulator sets (acc_full/acc_empty) so the epilogue of tile i overlaps the MMAs of i+1.
 template <int MT, typename TIn, typename TOut>
 __global__ void __launch_bounds__(NTHREADS)
 conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [W ring | A group buffers | barriers]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_ring = smem;
-  uint8_t* a_bufs = w_ring + (size_t)p.stages * p.stage_bytes;
-  const uint32_t a_buf_bytes = (uint32_t)p.PG * p.plane_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_bufs + (size_t)p.a_bufs * a_buf_bytes);
-  uint64_t* full = bars;                    // [stages]
-  uint64_t* empty = full + p.stages;        // [stages]
-  uint64_t* a_full = empty + p.stages;      // [a_bufs]
-  uint64_t* a_empty = a_full + p.a_bufs;    // [a_bufs]
-  uint64_t* d_ready = a_empty + p.a_bufs;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_ready + 1);
+  uint8_t* a_ring = w_ring + (size_t)p.stages * p.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + (size_t)p.a_slots * p.a_slot_bytes);
+  uint64_t* full = bars;                      // [stages]
+  uint64_t* empty = full + p.stages;          // [stages]
+  uint64_t* a_full = empty + p.stages;        // [a_slots]
+  uint64_t* a_empty = a_full + p.a_slots;     // [a_slots]
+  uint64_t* acc_full = a_empty + p.a_slots;   // [2]
+  uint64_t* acc_empty = acc_full + 2;         // [2]
+  uint64_t* w_ready = acc_empty + 2;          // resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_ready + 1);
+  // per-epilogue-warp transpose buffers (f16 output): 32 rows x 64 B, 80 B pitch (conflict-free)
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~uintptr_t(127));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * (BM * MT);
-  const int ntile = blockIdx.z;
-  const uint32_t tapmask = p.tapmask ? p.tapmask[ntile] : 0xFFFFFFFFu;
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int s = 0; s < p.a_bufs; ++s) {
-      mbar_init(&a_full[s], 128);
+    for (int s = 0; s < p.a_slots; ++s) {
+      mbar_init(&a_full[s], LOAD_THREADS);
       mbar_init(&a_empty[s], 1);
     }
-    mbar_init(d_ready, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], EPI_THREADS);
+    }
+    mbar_init(w_ready, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tcgen05_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  if (warp == 4 && lane == 0)
+  if (warp == MMA_WARP) tcgen05_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == TMA_WARP && lane == 0)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) trace(p, 4, 0, 0);
 
   const int chunks_per_group = p.PG * 8 / p.KC;
   const int n_chunks = p.Cin / p.KC;
+  const int planes_total = p.Cin / 8;
 
-  if (warp == 4) {
-    // ===== TMA producer: weights in (chunk, tap) order =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int chunk = 0; chunk < n_chunks; ++chunk) {
-        for (int tap = 0; tap < p.K; ++tap) {
-          if (!((tapmask >> tap) & 1u)) continue;
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], (uint32_t)p.stage_bytes);
-          tma_load_2d(w_ring + (size_t)stage * p.stage_bytes, &wmap, &full[stage], chunk * p.KC,
-                      tap * p.Cout + ntile * p.NT);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
+  if (warp == TMA_WARP) {
+    // ===== TMA producer: weights in (tile, chunk, tap) order =====
+    if (p.resident) {
+      // the whole layer's weights fit: one bulk load per (chunk, tap) tile, once per CTA
+      if (elect_one()) {
+        trace(p, 0, 0, 0);
+        mbar_expect_tx(w_ready, (uint32_t)(n_chunks * p.K * p.stage_bytes));
+        for (int chunk = 0; chunk < n_chunks; ++chunk)
+          for (int tap = 0; tap < p.K; ++tap)
+            tma_load_2d(w_ring + (size_t)(chunk * p.K + tap) * p.stage_bytes, &wmap, w_ready, chunk * p.KC,
+                        tap * p.Cout);
       }
-    }
-  } else if (warp == 5) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t w_layout = p.KC == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
-      const uint32_t w_sbo = 8u * (uint32_t)p.KC * 2u;
+      __syncwarp();
+    } else {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t started = 0;
-      for (int g = 0; g < p.n_groups; ++g) {
-        const int ab = g % p.a_bufs;
-        mbar_wait(&a_full[ab], (uint32_t)(g / p.a_bufs) & 1u);
-        tcgen05_fence_after();
-        const uint32_t a_base = smem_u32(a_bufs + (size_t)ab * a_buf_bytes);
-        const int c_end = min(n_chunks, (g + 1) * chunks_per_group);
-        for (int chunk = g * chunks_per_group; chunk < c_end; ++chunk) {
-          const int chunk_in_group = chunk - g * chunks_per_group;
-          for (int tap = 0; tap < p.K; ++tap) {
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(tile, p);
+        const uint32_t tapmask = p.tapmask ? p.tapmask[tc.ntile] : 0xFFFFFFFFu;
+        // Every CTA streams the same weight tiles: start each tile's (chunk, tap) walk at a
+        // row-tile dependent offset so the SMs do not hammer the same L2 lines in lock-step.
+        for (int g = 0; g < p.n_groups; ++g) {
+          const int c_begin = g * chunks_per_group;
+          const int n_it = (min(n_chunks, c_begin + chunks_per_group) - c_begin) * p.K;
+          const int rot = p.rotate ? (tc.rt * 5) % n_it : 0;
+          for (int i = 0; i < n_it; ++i) {
+            int idx = i + rot;
+            if (idx >= n_it) idx -= n_it;
+            const int chunk = c_begin + idx / p.K, tap = idx % p.K;
             if (!((tapmask >> tap) & 1u)) continue;
-            mbar_wait(&full[stage], phase);
-            tcgen05_fence_after();
-            const uint32_t w_base = smem_u32(w_ring + (size_t)stage * p.stage_bytes);
-            const uint32_t row_shift = (uint32_t)(tap * p.dil) * 16u;
-            for (int k16 = 0; k16 < p.KC / 16; ++k16) {
-              const uint32_t plane = (uint32_t)(chunk_in_group * (p.KC / 8) + 2 * k16);
-              const uint64_t bdesc = make_desc(w_base + k16 * 32, 0u, w_sbo, w_layout);
-#pragma unroll
-              for (int m = 0; m < MT; ++m) {
-                const uint64_t adesc = make_desc(a_base + plane * p.plane_bytes + row_shift + m * (BM * 16),
-                                                 (uint32_t)p.plane_bytes, 128u, LAYOUT_NONE);
-                umma_f16(tmem_base + (uint32_t)(m * p.NT), adesc, bdesc, p.idesc, started);
-              }
-              started = 1;
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&full[stage], (uint32_t)p.stage_bytes);
+              tma_load_2d(w_ring + (size_t)stage * p.stage_bytes, &wmap, &full[stage], chunk * p.KC,
+                          tap * p.Cout + tc.ntile * p.NT);
             }
-            tcgen05_commit(&empty[stage]);
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
-        tcgen05_commit(&a_empty[ab]);
       }
-      tcgen05_commit(d_ready);
     }
-  } else {
-    // ===== warps 0-3: stage the activation window group by group, then epilogue =====
-    const int len = p.lens ? p.lens[b] : p.L;
-    {
-      const int rows = BM * MT + (p.K - 1) * p.dil;
-      const TIn* xb = reinterpret_cast<const TIn*>(p.x) + (size_t)b * p.L * p.x_ld + p.x_coff;
-      const float slope = p.in_slope;
-      const int planes_total = p.Cin / 8;
-      for (int g = 0; g < p.n_groups; ++g) {
-        const int ab = g % p.a_bufs;
-        mbar_wait(&a_empty[ab], ((uint32_t)(g / p.a_bufs) & 1u) ^ 1u);
-        uint8_t* dst = a_bufs + (size_t)ab * a_buf_bytes;
+  } else if (warp == MMA_WARP) {
+    // ===== MMA issuer: the whole warp walks the loops, one elected lane issues =====
+    const uint32_t w_layout = p.KC == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
+    const uint32_t w_sbo = 8u * (uint32_t)p.KC * 2u;
+    // descriptor templates: start address (low 14 bits, 16-byte units) is OR-ed in per MMA
+    const uint64_t adesc0 = make_desc(0u, (uint32_t)p.plane_bytes, 128u, LAYOUT_NONE);
+    const uint64_t bdesc0 = make_desc(0u, 0u, w_sbo, w_layout);
+    const uint32_t plane_units = (uint32_t)p.plane_bytes >> 4;
+    const int kc16 = p.KC / 16, kc8 = p.KC / 8;
+    const uint32_t nt = (uint32_t)p.NT, idesc = p.idesc;
+    const bool do_mma = !(p.debug & 4);
+    int stage = 0;
+    uint32_t phase = 0, a_cnt = 0, t_cnt = 0;
+    if (p.resident) {
+      mbar_wait(w_ready, 0);
+      tcgen05_fence_after();
+      trace(p, 1, 0, 0);
+    }
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t_cnt) {
+      const TileCoord tc = decode_tile(tile, p);
+      const uint32_t tapmask = p.tapmask ? p.tapmask[tc.ntile] : 0xFFFFFFFFu;
+      const uint32_t accb = t_cnt & 1u;
+      mbar_wait(&acc_empty[accb], ((t_cnt >> 1) & 1u) ^ 1u);
+      tcgen05_fence_after();
+      if (lane == 0) trace(p, 1, 1, (int)t_cnt);
+      const uint32_t d_base = tmem_base + accb * (uint32_t)MT * nt;
+      uint32_t started = 0;
+      for (int g = 0; g < p.n_groups; ++g, ++a_cnt) {
+        const uint32_t slot = a_cnt % (uint32_t)p.a_slots;
+        mbar_wait(&a_full[slot], (a_cnt / (uint32_t)p.a_slots) & 1u);
+        tcgen05_fence_after();
+        if (lane == 0) trace(p, 1, 2, (int)t_cnt);
+        const uint32_t a_units = smem_u32(a_ring + (size_t)slot * p.a_slot_bytes) >> 4;
+        const int c_begin = g * chunks_per_group;
+        const int n_it = (min(n_chunks, c_begin + chunks_per_group) - c_begin) * p.K;
+        const int rot = p.rotate ? (tc.rt * 5) % n_it : 0;
+        for (int i = 0; i < n_it; ++i) {
+          int idx = i + rot;
+          if (idx >= n_it) idx -= n_it;
+          const int chunk_in_group = idx / p.K, tap = idx - chunk_in_group * p.K;
+          const int chunk = c_begin + chunk_in_group;
+          if (!((tapmask >> tap) & 1u)) continue;
+          if (!p.resident) {
+            mbar_wait(&full[stage], phase);
+            tcgen05_fence_after();
+          }
+          const uint32_t w_units =
+              smem_u32(w_ring + (size_t)(p.resident ? chunk * p.K + tap : stage) * p.stage_bytes) >> 4;
+          const uint32_t a_tap = a_units + (uint32_t)(chunk_in_group * kc8) * plane_units + (uint32_t)(tap * p.dil);
+          if (elect_one()) {
+            if (do_mma) {
+              for (int k16 = 0; k16 < kc16; ++k16) {
+                const uint64_t bdesc = bdesc0 | (uint64_t)(w_units + 2u * k16);
+                const uint32_t a_k = a_tap + 2u * (uint32_t)k16 * plane_units;
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                  const uint64_t adesc = adesc0 | (uint64_t)(a_k + (uint32_t)m * (BM * 16 / 16));
+                  umma_f16(d_base + (uint32_t)m * nt, adesc, bdesc, idesc, started | (uint32_t)k16);
+                }
+              }
+            }
+            if (!p.resident) tcgen05_commit(&empty[stage]);
+          }
+          __syncwarp();
+          started = 1;
+          if (!p.resident) {
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (elect_one()) tcgen05_commit(&a_empty[slot]);
+        __syncwarp();
+      }
+      if (elect_one()) tcgen05_commit(&acc_full[accb]);
+      __syncwarp();
+      if (lane == 0) trace(p, 1, 3, (int)t_cnt);
+    }
+  } else if (warp >= EPI_WARPS) {
+    // ===== A loaders: stage (tile, group) windows into the activation ring =====
+    const int ltid = tid - EPI_THREADS;
+    const int rows = BM * MT + (p.K - 1) * p.dil;
+    const float slope = p.in_slope;
+    constexpr int U = VecIO<TIn>::RAW == 1 ? 8 : 4;
+    uint32_t a_cnt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(tile, p);
+      const int t0 = tc.rt * (BM * MT);
+      const int len = p.lens ? p.lens[tc.b] : p.L;
+      const int t_hi = p.in_mask ? min(p.L, len) : p.L;
+      const TIn* xb = reinterpret_cast<const TIn*>(p.x) + (size_t)tc.b * p.L * p.x_ld + p.x_coff;
+      for (int g = 0; g < p.n_groups; ++g, ++a_cnt) {
+        const uint32_t slot = a_cnt % (uint32_t)p.a_slots;
+        mbar_wait(&a_empty[slot], ((a_cnt / (uint32_t)p.a_slots) & 1u) ^ 1u);
+        if (ltid == 0) trace(p, 2, 1, (int)a_cnt);
+        uint8_t* dst = a_ring + (size_t)slot * p.a_slot_bytes;
         const int pl0 = g * p.PG;
         const int npl = min(p.PG, planes_total - pl0);
         const int nvec = rows * npl;
-        for (int v = tid; v < nvec; v += 128) {
-          const int r = v / npl, pl = v - r * npl;
-          const int t = t0 - p.pad + r;
-          uint4 q = make_uint4(0u, 0u, 0u, 0u);
-          if (t >= 0 && t < p.L && (!p.in_mask || t < len)) {
+        const int npl_shift = (npl & (npl - 1)) == 0 ? 31 - __clz(npl) : -1;
+        for (int v0 = ltid; v0 < nvec; v0 += LOAD_THREADS * U) {
+          uint4 raw[U][VecIO<TIn>::RAW];
+          int rr[U], pp[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int v = v0 + u * LOAD_THREADS;
+            rr[u] = -1;
+            if (v < nvec) {
+              const int r = npl_shift >= 0 ? (v >> npl_shift) : v / npl;
+              const int pl = v - r * npl;
+              rr[u] = r;
+              pp[u] = pl;
+              const int t = t0 - p.pad + r;
+              if (t >= 0 && t < t_hi && !(p.debug & 1)) {
+                VecIO<TIn>::load_raw(xb + (size_t)t * p.x_ld + (pl0 + pl) * 8, raw[u]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < VecIO<TIn>::RAW; ++i) raw[u][i] = make_uint4(0u, 0u, 0u, 0u);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (rr[u] < 0) continue;
             float f[8];
-            VecIO<TIn>::load8(xb + (size_t)t * p.x_ld + (pl0 + pl) * 8, f);
+            VecIO<TIn>::unpack(raw[u], f);
             if (slope != 1.f) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * slope;
             }
+            uint4 q;
             __half2* h = reinterpret_cast<__half2*>(&q);
 #pragma unroll
             for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+            *reinterpret_cast<uint4*>(dst + (size_t)pp[u] * p.plane_bytes + (size_t)rr[u] * 16) = q;
           }
-          *reinterpret_cast<uint4*>(dst + (size_t)pl * p.plane_bytes + (size_t)r * 16) = q;
         }
         fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(&a_full[ab]);
+        mbar_arrive(&a_full[slot]);
+        if (ltid == 0) trace(p, 2, 2, (int)a_cnt);
       }
     }
-    mbar_wait(d_ready, 0);
-    tcgen05_fence_after();
-    const int n0 = ntile * p.NT;
-    const float* bbias = p.bbias ? p.bbias + (size_t)b * p.bbias_ld + n0 : nullptr;
-    const float* bias = p.bias ? p.bias + n0 : nullptr;
+  } else {
+    // ===== epilogue warps: quarter q = warp % 4 owns TMEM lanes 32q..32q+31 (one output row per
+    // lane); the two warps of a quarter split the NT columns in 32-column blocks (even / odd).
+    // f16 outputs go through a per-warp shared-memory transpose so that every global access is
+    // coalesced (8 rows x 64 B per instruction instead of 32 rows x 16 B).
+    constexpr int RV = VecIO<TOut>::RAW;   // uint4 per 8 output channels
+    constexpr int BV = 4 * RV;             // uint4 per 32-column block of one row
+    constexpr bool STAGED = RV == 1;
+    constexpr int EP = 80;                 // staging row pitch in bytes
+    const int quarter = warp & 3, half = warp >> 2;
+    const int n_blocks = p.NT / 32;        // 32-column blocks in the tile
+    uint8_t* stg = epi_stage + (size_t)warp * (32 * EP);
+    const int crow = lane >> 2, cchunk = lane & 3;   // coalesced mapping: rows crow + 8i, 16-byte chunk
+    uint32_t t_cnt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t_cnt) {
+      const TileCoord tc = decode_tile(tile, p);
+      const int t0 = tc.rt * (BM * MT);
+      const int len = p.lens ? p.lens[tc.b] : p.L;
+      const int n0 = tc.ntile * p.NT;
+      const float* bbias = p.bbias ? p.bbias + (size_t)tc.b * p.bbias_ld + n0 : nullptr;
+      const float* bias = p.bias ? p.bias + n0 : nullptr;
+      const uint32_t accb = t_cnt & 1u;
+      bool waited = false;
 #pragma unroll 1
-    for (int m = 0; m < MT; ++m) {
-      const int row = t0 + m * BM + warp * 32 + lane;
-      const bool row_ok = row < p.L;
-      const size_t grow = (size_t)b * p.L + (row_ok ? row : 0);
-      TOut* yrow = reinterpret_cast<TOut*>(p.y) + grow * p.y_ld + p.y_coff + n0;
-      const TOut* rrow = p.res ? reinterpret_cast<const TOut*>(p.res) + grow * p.res_ld + p.res_coff + n0 : nullptr;
-      const bool zero_row = p.out_mask && row >= len;
+      for (int m = 0; m < MT; ++m) {
+        const int wrow0 = t0 + m * BM + quarter * 32;     // first row of this warp
+        const int row = wrow0 + lane;
+        const bool row_ok = row < p.L;
+        const size_t grow = (size_t)tc.b * p.L + (row_ok ? row : 0);
+        TOut* yrow = reinterpret_cast<TOut*>(p.y) + grow * p.y_ld + p.y_coff + n0;
+        const TOut* rrow = p.res ? reinterpret_cast<const TOut*>(p.res) + grow * p.res_ld + p.res_coff + n0 : nullptr;
+        const bool zero_row = p.out_mask && row >= len;
+        // coalesced-mapping bases (row wrow0 + crow + 8i)
+        const TOut* rco = p.res ? reinterpret_cast<const TOut*>(p.res) + ((size_t)tc.b * p.L + wrow0) * p.res_ld +
+                                      p.res_coff + n0 + cchunk * 8 : nullptr;
+        TOut* yco = reinterpret_cast<TOut*>(p.y) + ((size_t)tc.b * p.L + wrow0) * p.y_ld + p.y_coff + n0 + cchunk * 8;
+        uint4 r0[BV];
+        uint4 r1[RV == 1 ? BV : 1];
+        auto fetch = [&](int blk, uint4 (&dst)[BV]) {
+          if (!p.res || blk >= n_blocks || (p.debug & 2)) return;
+          if constexpr (STAGED) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = crow + 8 * i;
+              dst[i] = make_uint4(0u, 0u, 0u, 0u);
+              if (wrow0 + r < p.L)
+                dst[i] = *reinterpret_cast<const uint4*>(rco + (size_t)r * p.res_ld + blk * 32);
+            }
+          } else {
+            if (row_ok) {
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                uint4 tmp[RV];
+                VecIO<TOut>::load_raw(rrow + blk * 32 + g8 * 8, tmp);
+#pragma unroll
+                for (int i = 0; i < RV; ++i) dst[g8 * RV + i] = tmp[i];
+              }
+            }
+          }
+        };
+        fetch(half, r0);
+        if constexpr (RV == 1) fetch(half + 2, r1);
+        if (!waited) {
+          mbar_wait(&acc_full[accb], (t_cnt >> 1) & 1u);
+          tcgen05_fence_after();
+          waited = true;
+          if (tid == 0) trace(p, 3, 1, (int)t_cnt);
+        }
+        auto process = [&](int blk, uint4 (&rb)[BV]) {
+          const int c0 = blk * 32;
+          if constexpr (STAGED) {
+            if (p.res) {   // coalesced residual -> staging -> per-row registers
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<uint4*>(stg + (crow + 8 * i) * EP + cchunk * 16) = rb[i];
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) rb[i] = *reinterpret_cast<const uint4*>(stg + lane * EP + i * 16);
+            }
+          }
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * (uint32_t)(MT * p.NT) +
+                        (uint32_t)(m * p.NT + c0), acc);
+          if constexpr (STAGED) __syncwarp();   // staging reads done before it is rewritten
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[q8 * 8 + j]);
+            const int c = c0 + q8 * 8;
+            if (bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (bbias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += __ldg(bbias + c + j);
+            }
+            if (p.res) {
+              uint4 tmp[RV];
+#pragma unroll
+              for (int i = 0; i < RV; ++i) tmp[i] = rb[q8 * RV + i];
+              float r[8];
+              VecIO<TOut>::unpack(tmp, r);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += p.res_scale * r[j];
+            }
+            if (p.out_scale != 1.f) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] *= p.out_scale;
+            }
+            if (p.accumulate && row_ok) {
+              uint4 oraw[RV];
+              float o[8];
+              VecIO<TOut>::load_raw(yrow + c, oraw);
+              VecIO<TOut>::unpack(oraw, o);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += o[j];
+            }
+            if (p.act == ACT_LRELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.out_slope;
+            } else if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (zero_row) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = 0.f;
+            }
+            if constexpr (STAGED) {
+              uint4 q;
+              __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+              *reinterpret_cast<uint4*>(stg + lane * EP + q8 * 16) = q;
+            } else {
+              if (row_ok && !(p.debug & 2)) VecIO<TOut>::store8(yrow + c, v);
+            }
+          }
+          if constexpr (STAGED) {
+            __syncwarp();
+            if (!(p.debug & 2)) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = crow + 8 * i;
+                if (wrow0 + r < p.L)
+                  *reinterpret_cast<uint4*>(yco + (size_t)r * p.y_ld + c0) =
+                      *reinterpret_cast<const uint4*>(stg + r * EP + cchunk * 16);
+              }
+            }
+          }
+        };
+        if constexpr (RV == 1) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.NT; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * p.NT + c0), acc);
-        if (!row_ok) continue;
-#pragma unroll
-        for (int q8 = 0; q8 < 4; ++q8) {
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[q8 * 8 + j]);
-          const int c = c0 + q8 * 8;
-          if (bias) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += __ldg(bias + c + j);
+          for (int blk = half; blk < n_blocks; blk += 4) {
+            process(blk, r0);
+            fetch(blk + 4, r0);
+            if (blk + 2 < n_blocks) {
+              process(blk + 2, r1);
+              fetch(blk + 6, r1);
+            }
           }
-          if (bbias) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += __ldg(bbias + c + j);
+        } else {   // f32 residual rows are twice as wide: one block in flight
+#pragma unroll 1
+          for (int blk = half; blk < n_blocks; blk += 2) {
+            process(blk, r0);
+            fetch(blk + 2, r0);
           }
-          if (rrow) {
-            float r[8];
-            VecIO<TOut>::load8(rrow + c, r);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += p.res_scale * r[j];
-          }
-          if (p.out_scale != 1.f) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] *= p.out_scale;
-          }
-          if (p.accumulate) {
-            float o[8];
-            VecIO<TOut>::load8(yrow + c, o);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += o[j];
-          }
-          if (p.act == ACT_LRELU) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.out_slope;
-          } else if (p.act == ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (zero_row) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = 0.f;
-          }
-          VecIO<TOut>::store8(yrow + c, v);
         }
       }
+      if (!waited) {   // this warp had no columns (NT == 32, half == 1): still track the phase
+        mbar_wait(&acc_full[accb], (t_cnt >> 1) & 1u);
+        tcgen05_fence_after();
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&acc_empty[accb]);
+      if (tid == 0) trace(p, 3, 2, (int)t_cnt);
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) tcgen05_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == MMA_WARP) tcgen05_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (tid == 0) trace(p, 4, 1, 0);
 }
 
 // ------------------------------ host side ----------------------------------
@@ -475,58 +748,91 @@ int pick_nt(int cout) {
 }
 
 struct Plan {
-  int MT, NT, KC, PG, n_groups, a_bufs, stages, stage_bytes, plane_bytes, tmem_cols;
+  int MT, NT, KC, PG, n_groups, a_slots, a_slot_bytes, stages, stage_bytes, plane_bytes, tmem_cols;
+  int ctas_per_sm, resident;
   size_t smem;
 };
 
-// Choose the row-tile multiplicity, A grouping and weight-ring depth.  Preference: fit two
-// CTAs per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's epilogue overlaps the
-// other's MMAs; more row tiles per CTA amortise the weight stream from L2.
+int env_int(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+}
+
+int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
+// Choose row-tile multiplicity, ring depths and CTAs per SM.  Narrow layers (little MMA work per
+// tile) want several resident CTAs to hide the staging / epilogue latency; wide layers want deep
+// rings in one CTA.  TMEM holds two accumulator sets per CTA (epilogue / MMA overlap).
 bool make_plan(const ConvArgs& a, Plan* out) {
   const int NT = pick_nt(a.Cout);
   if (!NT) return false;
   const int KC = a.Cin % 64 == 0 ? 64 : 32;
   const int planes = a.Cin / 8;
-  const int PG = planes < GROUP_PLANES ? planes : GROUP_PLANES;
+  int PG = planes < GROUP_PLANES ? planes : GROUP_PLANES;
+  if ((PG * 8) % KC) PG = planes;   // e.g. Cin = 96 with 32-channel chunks: one group
   if ((PG * 8) % KC) return false;
   const int n_groups = (planes + PG - 1) / PG;
-  const int a_bufs = n_groups > 1 ? 2 : 1;
   const int stage_bytes = NT * KC * 2;
-  const int n_tiles_rows = (a.L_out + BM - 1) / BM;
-  const size_t fixed = 1024 + 512;
-  static const int forced_mt = [] {
-    const char* e = getenv("PG_UMMA_MT");   // tuning aid
-    return e ? atoi(e) : 0;
-  }();
-  Plan best{};
-  bool have = false;
-  for (int pass = 0; pass < 2 && !have; ++pass) {
-    const size_t budget = pass == 0 ? 113 * 1024 : 227 * 1024;
-    const int tmem_budget = pass == 0 ? 256 : 512;
+  static const int forced_mt = env_int("PG_UMMA_MT"), no_resident = env_int("PG_UMMA_NORESIDENT");
+  const size_t fixed = 1024 + 1024 + EPI_WARPS * 32 * 80 + 256;   // align slack, barriers, epilogue staging
+  const size_t budget = (size_t)226 * 1024;
+  const int n_chunks = a.Cin / KC;
+  const size_t w_all = (size_t)n_chunks * a.K * stage_bytes;
+  const bool can_reside = !no_resident && a.Cout == NT && !a.tapmask;
+  const int n_rows128 = (a.L_out + BM - 1) / BM;
+  auto geometry = [&](int MT, int* plane_bytes, int* a_slot_bytes) {
+    const int rows = BM * MT + (a.K - 1) * a.dil;
+    const int rows_alloc = (rows + 7) & ~7;
+    const int row_pad = PG >= 8 ? 1 : (PG == 4 ? 2 : 1);   // keep plane pitches on distinct banks
+    *plane_bytes = 16 * (rows_alloc + row_pad);
+    *a_slot_bytes = (PG * *plane_bytes + 127) & ~127;
+  };
+  // Candidate row-tile multiplicities, largest first: more rows per tile amortise the barrier
+  // round trips and (ring mode) the weight stream from L2.  Two accumulator sets must fit TMEM.
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool resident = pass == 0;
+    if (resident && !can_reside) continue;
     for (int MT : {4, 2, 1}) {
-      if (MT > 1 && (NT & (NT - 1))) continue;          // multi-tile only with power-of-two N
-      if (MT * NT > tmem_budget) continue;
       if (forced_mt > 0 && MT != forced_mt && MT != 1) continue;
-      const long ctas = (long)((n_tiles_rows + MT - 1) / MT) * a.B * (a.Cout / NT);
-      if (MT > 1 && forced_mt <= 0 && ctas < 2 * 148) continue;   // do not starve the grid on short inputs
-      const int rows = BM * MT + (a.K - 1) * a.dil;
-      const int rows_alloc = (rows + 7) & ~7;
-      const int plane_bytes = 16 * (rows_alloc + 1);
-      const size_t a_bytes = (size_t)a_bufs * PG * plane_bytes;
-      if (a_bytes + 2 * (size_t)stage_bytes + fixed > budget) continue;
-      int stages = (int)((budget - fixed - a_bytes) / stage_bytes);
-      if (stages > 6) stages = 6;
+      if (MT > 1 && (NT & (NT - 1))) continue;
+      if (2 * MT * NT > 512) continue;
+      if (MT > 1 && (long)((n_rows128 + MT - 1) / MT) * a.B * (a.Cout / NT) < 2L * num_sms()) continue;
+      int plane_bytes, a_slot_bytes;
+      geometry(MT, &plane_bytes, &a_slot_bytes);
       int tm = 32;
-      while (tm < MT * NT) tm <<= 1;
-      best = Plan{MT, NT, KC, PG, n_groups, a_bufs, stages, stage_bytes, plane_bytes, tm,
-                  fixed + a_bytes + (size_t)stages * stage_bytes};
-      have = true;
-      break;
+      while (tm < 2 * MT * NT) tm <<= 1;
+      const size_t w_bytes = resident ? w_all : 3 * (size_t)stage_bytes;
+      if (fixed + 2 * (size_t)a_slot_bytes + w_bytes > budget) continue;
+      size_t left = budget - fixed - 2 * (size_t)a_slot_bytes - w_bytes;
+      int a_slots = 2, stages = resident ? n_chunks * a.K : 3;
+      if (!resident && env_int("PG_UMMA_STAGES") == 2) { stages = 2; left += stage_bytes; }
+      static const int forced_stages = env_int("PG_UMMA_STAGES");
+      const int max_stages = forced_stages > 0 ? forced_stages : 8;
+      if (!resident) {   // ring: up to 8 stages, then deeper activation ring
+        while (stages < max_stages && left >= (size_t)stage_bytes && stages < n_chunks * a.K) {
+          ++stages;
+          left -= stage_bytes;
+        }
+      }
+      while (a_slots < 4 && left >= (size_t)a_slot_bytes) {
+        ++a_slots;
+        left -= a_slot_bytes;
+      }
+      *out = Plan{MT, NT, KC, PG, n_groups, a_slots, a_slot_bytes, stages, stage_bytes, plane_bytes, tm, 1,
+                  resident ? 1 : 0,
+                  fixed + (size_t)a_slots * a_slot_bytes + (size_t)stages * stage_bytes};
+      return true;
     }
   }
-  if (!have) return false;
-  *out = best;
-  return true;
+  return false;
 }
 
 template <int MT, typename TIn, typename TOut>
@@ -542,12 +848,19 @@ cudaError_t launch_t(const ConvArgs& a, const Plan& pl, cudaStream_t s) {
   p.tapmask = a.tapmask;
   p.B = a.B; p.L = a.L_out; p.Cin = a.Cin; p.Cout = a.Cout; p.K = a.K; p.dil = a.dil; p.pad = a.pad;
   p.NT = pl.NT;
+  p.n_row_tiles = (a.L_out + BM * MT - 1) / (BM * MT);
+  p.n_ntiles = a.Cout / pl.NT;
+  p.total_tiles = p.n_row_tiles * a.B * p.n_ntiles;
   p.in_slope = a.in_slope; p.out_slope = a.out_slope; p.out_scale = a.out_scale;
   p.act = a.act; p.accumulate = a.accumulate;
   p.plane_bytes = pl.plane_bytes; p.KC = pl.KC; p.PG = pl.PG; p.n_groups = pl.n_groups;
-  p.a_bufs = pl.a_bufs; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes;
+  p.a_slots = pl.a_slots; p.a_slot_bytes = pl.a_slot_bytes;
+  p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.resident = pl.resident;
   p.tmem_cols = pl.tmem_cols;
   p.idesc = make_idesc(BM, pl.NT);
+  static const int dbg = env_int("PG_UMMA_DEBUG"), norot = env_int("PG_UMMA_NOROTATE");
+  p.debug = dbg;
+  p.rotate = (!pl.resident && !norot) ? 1 : 0;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<MT, TIn, TOut>,
@@ -555,8 +868,28 @@ cudaError_t launch_t(const ConvArgs& a, const Plan& pl, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  dim3 grid((a.L_out + BM * MT - 1) / (BM * MT), a.B, a.Cout / pl.NT);
+  int grid = num_sms() * pl.ctas_per_sm;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  if (p.debug & 8) {
+    unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero));
+  }
   conv_umma_kernel<MT, TIn, TOut><<<grid, NTHREADS, pl.smem, s>>>(wmap, p);
+  if (p.debug & 8) {
+    cudaDeviceSynchronize();
+    static unsigned long long host[8192];
+    unsigned int n = 0;
+    cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n));
+    cudaMemcpyFromSymbol(host, g_trace, sizeof(host));
+    if (n > 8192) n = 8192;
+    unsigned long long t0 = ~0ull;
+    for (unsigned i = 0; i < n; ++i) t0 = host[i] >> 20 < t0 ? host[i] >> 20 : t0;
+    fprintf(stderr, "TRACE MT=%d NT=%d resident=%d a_slots=%d stages=%d grid=%d tiles=%d smem=%zu\n", MT, pl.NT,
+            pl.resident, pl.a_slots, pl.stages, grid, p.total_tiles, pl.smem);
+    for (unsigned i = 0; i < n; ++i)
+      fprintf(stderr, "TR %llu role=%llu ev=%llu tile=%llu\n", (host[i] >> 20) - t0, (host[i] >> 16) & 15,
+              (host[i] >> 12) & 15, host[i] & 0xFFF);
+  }
   return cudaGetLastError();
 }
 

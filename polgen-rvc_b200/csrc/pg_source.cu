@@ -5,6 +5,8 @@
 //   leaky_relu(0.01) -> conv_post -> tanh   nsf.py:142-143
 #include <curand_kernel.h>
 
+#include <type_traits>
+
 #include "pg_common.cuh"
 
 namespace pg {
@@ -108,7 +110,8 @@ cudaError_t launch_source(const float* f0, const float* eps, uint64_t seed, floa
 // x[b][t][c] += bn[c] + sum_j wn[j][c] * src[b][t*stride + j - pad]   (nsf.py:131)
 // one thread per (t, channel pair); the source window is a warp broadcast.
 // ---------------------------------------------------------------------------
-__global__ void noise_inject_kernel(__half* __restrict__ x, const float* __restrict__ src,
+template <typename T>
+__global__ void noise_inject_kernel(T* __restrict__ x, const float* __restrict__ src,
                                     const float* __restrict__ wn /*[k][C]*/,
                                     const float* __restrict__ bn, int B, int L, int C, int Lsrc, int k,
                                     int stride, int pad) {
@@ -132,16 +135,28 @@ __global__ void noise_inject_kernel(__half* __restrict__ x, const float* __restr
     a0 = fmaf(w.x, sv, a0);
     a1 = fmaf(w.y, sv, a1);
   }
-  __half2* xp = reinterpret_cast<__half2*>(x + row * C + c);
-  const float2 v = __half22float2(*xp);
-  *xp = __floats2half2_rn(v.x + a0, v.y + a1);
+  if constexpr (sizeof(T) == 2) {
+    __half2* xp = reinterpret_cast<__half2*>(x + row * C + c);
+    const float2 v = __half22float2(*xp);
+    *xp = __floats2half2_rn(v.x + a0, v.y + a1);
+  } else {
+    float2* xp = reinterpret_cast<float2*>(x + row * C + c);
+    const float2 v = *xp;
+    *xp = make_float2(v.x + a0, v.y + a1);
+  }
 }
 
-cudaError_t launch_noise_inject(__half* x, const float* src, const float* wn, const float* bn, int B,
-                                int L, int C, int Lsrc, int k, int stride, int pad, cudaStream_t s) {
+cudaError_t launch_noise_inject(void* x, DType dt, const float* src, const float* wn, const float* bn,
+                                int B, int L, int C, int Lsrc, int k, int stride, int pad,
+                                cudaStream_t s) {
   const size_t total = (size_t)B * L * (C / 2);
-  noise_inject_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, src, wn, bn, B, L, C, Lsrc, k,
-                                                                      stride, pad);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dt == DT_F16)
+    noise_inject_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<__half*>(x), src, wn, bn, B, L, C,
+                                                     Lsrc, k, stride, pad);
+  else
+    noise_inject_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<float*>(x), src, wn, bn, B, L, C,
+                                                    Lsrc, k, stride, pad);
   return cudaGetLastError();
 }
 
@@ -150,21 +165,24 @@ cudaError_t launch_noise_inject(__half* x, const float* src, const float* wn, co
 // 256 outputs per block; the x tile sits in shared memory with a 1-word row pad
 // so the per-thread row reads are bank-conflict free.
 // ---------------------------------------------------------------------------
-template <int C, int K>
-__global__ void __launch_bounds__(256) conv_post_kernel(const __half* __restrict__ x,
+template <int C, int K, typename T>
+__global__ void __launch_bounds__(256) conv_post_kernel(const T* __restrict__ x,
                                                         const float* __restrict__ w,
                                                         float* __restrict__ wave, int L,
                                                         float in_slope) {
   constexpr int TILE = 256, W2 = C / 2, RS = W2 + 1;
-  __shared__ __half2 xs[(TILE + K - 1) * RS];
+  using Pair = typename std::conditional<sizeof(T) == 2, __half2, float2>::type;
+  __shared__ Pair xs[(TILE + K - 1) * RS];
   __shared__ float ws[K * C];
   const int b = blockIdx.y, n0 = blockIdx.x * TILE, tid = threadIdx.x;
   for (int i = tid; i < K * C; i += 256) ws[i] = w[i];
-  const __half2* xb = reinterpret_cast<const __half2*>(x + (size_t)b * L * C);
+  const Pair* xb = reinterpret_cast<const Pair*>(x + (size_t)b * L * C);
   for (int i = tid; i < (TILE + K - 1) * W2; i += 256) {
     const int r = i / W2, cw = i % W2;
     const int n = n0 + r - K / 2;
-    __half2 v = __floats2half2_rn(0.f, 0.f);
+    Pair v;
+    v.x = 0;
+    v.y = 0;
     if (n >= 0 && n < L) v = xb[(size_t)n * W2 + cw];
     xs[r * RS + cw] = v;
   }
@@ -176,7 +194,9 @@ __global__ void __launch_bounds__(256) conv_post_kernel(const __half* __restrict
   for (int j = 0; j < K; ++j) {
 #pragma unroll
     for (int cw = 0; cw < W2; ++cw) {
-      float2 v = __half22float2(xs[(tid + j) * RS + cw]);
+      float2 v;
+      if constexpr (sizeof(T) == 2) v = __half22float2(xs[(tid + j) * RS + cw]);
+      else v = xs[(tid + j) * RS + cw];
       v.x = v.x > 0.f ? v.x : v.x * in_slope;
       v.y = v.y > 0.f ? v.y : v.y * in_slope;
       acc = fmaf(ws[j * C + 2 * cw], v.x, acc);
@@ -186,19 +206,28 @@ __global__ void __launch_bounds__(256) conv_post_kernel(const __half* __restrict
   wave[(size_t)b * L + n] = tanhf(acc);
 }
 
-cudaError_t launch_conv_post(const __half* x, const float* w, float* wave, int B, int L, int C, int K,
-                             float in_slope, cudaStream_t s) {
-  if (K != 7) return cudaErrorInvalidValue;
+template <typename T>
+static cudaError_t launch_conv_post_t(const T* x, const float* w, float* wave, int B, int L, int C,
+                                      float in_slope, cudaStream_t s) {
   dim3 grid((L + 255) / 256, B);
   if (C == 32)
-    conv_post_kernel<32, 7><<<grid, 256, 0, s>>>(x, w, wave, L, in_slope);
+    conv_post_kernel<32, 7, T><<<grid, 256, 0, s>>>(x, w, wave, L, in_slope);
   else if (C == 16)
-    conv_post_kernel<16, 7><<<grid, 256, 0, s>>>(x, w, wave, L, in_slope);
-  else if (C == 64)
-    conv_post_kernel<64, 7><<<grid, 256, 0, s>>>(x, w, wave, L, in_slope);
+    conv_post_kernel<16, 7, T><<<grid, 256, 0, s>>>(x, w, wave, L, in_slope);
+  else if (C == 64 && sizeof(T) == 2)
+    conv_post_kernel<64, 7, __half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(x), w, wave, L,
+                                                          in_slope);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();
+}
+
+cudaError_t launch_conv_post(const void* x, DType dt, const float* w, float* wave, int B, int L, int C,
+                             int K, float in_slope, cudaStream_t s) {
+  if (K != 7) return cudaErrorInvalidValue;
+  if (dt == DT_F16)
+    return launch_conv_post_t(reinterpret_cast<const __half*>(x), w, wave, B, L, C, in_slope, s);
+  return launch_conv_post_t(reinterpret_cast<const float*>(x), w, wave, B, L, C, in_slope, s);
 }
 
 }  // namespace pg

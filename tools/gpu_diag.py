@@ -192,12 +192,9 @@ def run_jobs(jobs):
 
 def run_tune():
     run_jobs([
-        ["taps", "umma", "v2-40k", "24", "1"],
         ["taps", "umma", "v2-48k", "300", "1"],
-        (["convop"], {"PG_UMMA_MT": "1"}),
-        (["convop"], {"PG_UMMA_MT": "2"}),
-        (["convop"], {"PG_UMMA_MT": "4"}),
         ["convop"],
+        (["convop"], {"PG_UMMA_MT": "2"}),
         ["time", "v2-48k", "1000", "1", "umma"],
         ["time", "v2-48k", "4000", "1", "umma"],
     ])
