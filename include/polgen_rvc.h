@@ -85,6 +85,7 @@ typedef struct pg_config {
 #define PG_FLAG_FORCE_SIMT 1   /* run every conv on the CUDA-core fp32 kernels (validation aid) */
 #define PG_FLAG_KEEP_TAPS 2    /* keep copies of intermediates for pg_debug_fetch */
 #define PG_FLAG_PROFILE 4      /* CUDA events around every conv launch (pg_profile_read) */
+#define PG_FLAG_LEGACY_DECODER 16 /* decoder on the time-major tcgen05 kernel (A/B comparison aid) */
 #define PG_FLAG_F16_LATENTS 8  /* TextEncoder / flow GEMMs with single-pass f16 tensor-core operands (default: fp32-accurate) */
 
 typedef struct pg_handle_s* pg_handle;
@@ -171,7 +172,8 @@ int pg_profile_read(pg_handle h, double* ms_out, double* flops_out, int64_t* lau
 /* Single-layer entry used by the op-level parity tests and micro-benchmarks:
  * y[b][t][co] = sum_{tap,ci} w[co][ci][tap] * lrelu(x[b][t + tap*dil - pad][ci], in_slope) + bias
  * x, y are f16 [B][L][C] device buffers, w f32 host [Cout][Cin][K] (Conv1d
- * layout).  impl: 0 = CUDA-core fp32, 1 = tcgen05.  Returns elapsed ms of
+ * layout).  impl: 0 = CUDA-core fp32, 1 = tcgen05 time-major kernel, 2 = tcgen05
+ * channel-plane kernel (the decoder's; layout converted around it).  Returns elapsed ms of
  * `iters` launches (CUDA events) in *ms_out when non-NULL. */
 int pg_op_conv1d_f16(int device, int impl, int B, int L, int Cin, int Cout, int K, int dil,
                      const void* x_dev, const float* w_host, const float* bias_host,

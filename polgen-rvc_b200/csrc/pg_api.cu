@@ -252,7 +252,7 @@ int pack_conv_transpose(pg_handle h, const std::string& wname, const std::string
   if (rc) return rc;
   rc = upload(h, b, &st->up.bias);
   if (rc) return rc;
-  const int nt = umma_pick_nt(N);
+  const int nt = plane_pick_nt(N);
   if (nt > 0 && taps <= 32) {
     std::vector<uint32_t> mask(N / nt, 0u);
     for (int tap = 0; tap < taps; ++tap)
@@ -281,7 +281,7 @@ struct Plan {
 struct Ws {
   // offsets into the workspace
   size_t lens, pitch, sid, x, y, qkv, att, ffn, stats, m_p, logs_p, z_p, z, fh, fa, facts, fskip,
-      gcond, dcond, source, phase, stage[5];
+      gcond, dcond, source, phase, stage[5], zpl, h16[4];
   size_t stage_elems = 0;
   size_t total = 0;
 };
@@ -322,6 +322,8 @@ Ws plan_ws(const pg_config& c, int B, int T) {
   w.phase = p.take(sizeof(double) * BT);
   w.stage_elems = max_elems;
   for (int i = 0; i < 5; ++i) w.stage[i] = p.take(sizeof(float) * max_elems + 4096);
+  w.zpl = p.take(sizeof(__half) * BT * C);
+  for (int i = 0; i < 4; ++i) w.h16[i] = p.take(sizeof(__half) * max_elems + 4096);
   w.total = p.total;
   return w;
 }
@@ -618,6 +620,197 @@ int run_generator(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const 
   return PG_OK;
 }
 
+// parity tap of a plane tensor: converted to time-major f32, L-form storage undone
+int record_tap_planes(pg_handle h, cudaStream_t s, const std::string& name, const void* src, DType dt,
+                      float inv_slope, int64_t B, int64_t L, int64_t C) {
+  if (!(h->cfg.flags & PG_FLAG_KEEP_TAPS)) return PG_OK;
+  Tap& t = h->taps[name];
+  const size_t bytes = (size_t)B * L * C * 4;
+  if (t.bytes < bytes) {
+    if (t.p) PG_CUDA_CHECK(cudaFree(t.p));
+    PG_CUDA_CHECK(cudaMalloc(&t.p, bytes));
+    t.bytes = bytes;
+  }
+  t.dtype = DT_F32;
+  t.shape[0] = B;
+  t.shape[1] = L;
+  t.shape[2] = C;
+  PG_CUDA_CHECK(launch_planes_to_nlc(src, dt, reinterpret_cast<float*>(t.p), (int)B, (int)L, (int)C, inv_slope, s));
+  return PG_OK;
+}
+
+int run_plane_conv(pg_handle h, cudaStream_t s, PlaneConvArgs a, const ConvW& w) {
+  a.w16 = w.w16;
+  a.bias = w.bias;
+  a.Cin = w.Cin;
+  a.N = w.Cout;
+  a.K = w.K;
+  a.tapmask = w.tapmask;
+  if (a.Cout_real == 0) a.Cout_real = w.Cout;
+  if (!plane_conv_supported(a)) return fail(PG_ERR_UNSUPPORTED, "layer shape not supported by the plane conv kernel");
+  const bool prof = (h->cfg.flags & PG_FLAG_PROFILE) != 0;
+  pg_handle_s::ProfRec rec;
+  if (prof) {
+    rec.e0 = take_event(h);
+    rec.e1 = take_event(h);
+    rec.cls = 0;
+    rec.flops = 2.0 * a.B * a.L * (double)a.Cin * a.N * a.K;
+    cudaEventRecord(rec.e0, s);
+  }
+  PG_LAUNCH(h, launch_conv_planes(a, s));
+  if (prof) {
+    cudaEventRecord(rec.e1, s);
+    h->prof.push_back(rec);
+  }
+  return PG_OK;
+}
+
+// ---- GeneratorNSF.forward (nsf.py:120-144) on the channel-plane layout ------------------
+// Conv inputs live in HBM as f16 planes in L-form (already leaky-ReLU'd with the slope the next
+// conv applies, 0.1); residuals are recovered from them in the epilogue.  The LAST stage keeps
+// its residual stream (and the mean that feeds conv_post) additionally in fp32 planes.
+int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const float* z,
+                         const float* source, float* wave) {
+  const pg_config& c = h->cfg;
+  const int* lens = at<int>(h, w.lens);
+  const int C0 = c.upsample_initial_channel;
+  const float SL = 0.1f, INV = 10.f;
+  float* dcond = at<float>(h, w.dcond);
+  PG_LAUNCH(h, launch_cond_gemv(h->emb_g, at<int>(h, w.sid), h->dec_cond_w, h->dec_cond_b, dcond, B,
+                                c.gin_channels, C0, s));
+  char* buf[5];
+  for (int i = 0; i < 5; ++i) buf[i] = at<char>(h, w.stage[i]);
+  __half* h16[4];
+  for (int i = 0; i < 4; ++i) h16[i] = at<__half>(h, w.h16[i]);
+  // z * mask -> planes (raw); conv_pre + cond(g), stored as lrelu(., 0.1) for ups[0]
+  __half* zpl = at<__half>(h, w.zpl);
+  PG_LAUNCH(h, launch_nlc_to_planes(z, DT_F32, c.inter_channels, 0, zpl, B, T, c.inter_channels, lens, 1.f, s));
+  {
+    PlaneConvArgs a;
+    a.x = zpl; a.B = B; a.L = T; a.pad = 3;
+    a.bbias = dcond; a.bbias_ld = C0;
+    a.out16 = reinterpret_cast<__half*>(buf[0]); a.out16_slope = SL;
+    PG_TRY(run_plane_conv(h, s, a, h->conv_pre));
+  }
+  PG_TRY(record_tap_planes(h, s, "dec.conv_pre", buf[0], DT_F16, INV, B, T, C0));
+  int cur = 0;
+  int64_t L = T;
+  const int64_t Lsrc = (int64_t)T * h->upp;
+  const int nk = c.n_resblock_kernels, nd = c.n_dilations;
+  for (int i = 0; i < c.n_ups; ++i) {
+    const StageW& S = h->stages[i];
+    const int C = S.C;
+    const bool wide = i == c.n_ups - 1;   // fp32 residual stream
+    int fr[4], nf = 0;
+    for (int k = 0; k < 5; ++k)
+      if (k != cur) fr[nf++] = k;
+    const int64_t Lin = L;
+    L *= S.u;
+    if (!wide) {
+      __half* x0 = reinterpret_cast<__half*>(buf[fr[0]]);
+      __half* xa = reinterpret_cast<__half*>(buf[fr[1]]);
+      __half* xb = reinterpret_cast<__half*>(buf[fr[2]]);
+      __half* tmp = reinterpret_cast<__half*>(buf[fr[3]]);
+      __half* acc = reinterpret_cast<__half*>(buf[cur]);   // the ups input is dead once x0 exists
+      {
+        PlaneConvArgs a;
+        a.x = reinterpret_cast<const __half*>(buf[cur]); a.B = B; a.L = (int)Lin; a.pad = S.up_pad;
+        a.Cout_real = C; a.row_mul = S.u;
+        a.out16 = x0;   // raw
+        PG_TRY(run_plane_conv(h, s, a, S.up));
+      }
+      PG_LAUNCH(h, launch_noise_inject_planes(x0, DT_F16, x0, source, S.noise_w, S.noise_b, B, (int)L, C,
+                                              (int)Lsrc, S.noise_k, S.noise_stride, S.noise_pad, SL, s));
+      PG_TRY(record_tap_planes(h, s, "dec.ups" + std::to_string(i), x0, DT_F16, INV, B, L, C));
+      for (int j = 0; j < nk; ++j) {
+        const int ksz = c.resblock_kernel_sizes[j];
+        const __half* xc = x0;
+        for (int d = 0; d < nd; ++d) {
+          const int dil = c.resblock_dilations[j][d];
+          const bool last = d == nd - 1;
+          PlaneConvArgs a1;
+          a1.x = xc; a1.B = B; a1.L = (int)L; a1.dil = dil; a1.pad = (ksz * dil - dil) / 2;
+          a1.out16 = tmp; a1.out16_slope = SL;
+          PG_TRY(run_plane_conv(h, s, a1, S.c1[j * nd + d]));
+          PlaneConvArgs a2;
+          a2.x = tmp; a2.B = B; a2.L = (int)L; a2.pad = (ksz - 1) / 2;
+          a2.res16 = xc; a2.res_inv = INV;
+          __half* dst = last ? acc : (xc == xa ? xb : xa);
+          a2.out16 = dst;
+          if (last) {
+            a2.out_scale = 1.f / nk;
+            a2.accin16 = j > 0 ? acc : nullptr;
+            a2.out16_slope = j == nk - 1 ? SL : 1.f;   // the finished mean is stored for ups[i+1]
+          } else {
+            a2.out16_slope = SL;
+          }
+          PG_TRY(run_plane_conv(h, s, a2, S.c2[j * nd + d]));
+          xc = dst;
+        }
+      }
+      PG_TRY(record_tap_planes(h, s, "dec.stage" + std::to_string(i), acc, DT_F16, INV, B, L, C));
+    } else {
+      float* r0 = reinterpret_cast<float*>(buf[fr[0]]);
+      float* ra = reinterpret_cast<float*>(buf[fr[1]]);
+      float* rb = reinterpret_cast<float*>(buf[fr[2]]);
+      float* acc = reinterpret_cast<float*>(buf[fr[3]]);
+      __half *a0 = h16[0], *aa = h16[1], *ab = h16[2], *tmp = h16[3];
+      {
+        PlaneConvArgs a;
+        a.x = reinterpret_cast<const __half*>(buf[cur]); a.B = B; a.L = (int)Lin; a.pad = S.up_pad;
+        a.Cout_real = C; a.row_mul = S.u;
+        a.out32 = r0;
+        PG_TRY(run_plane_conv(h, s, a, S.up));
+      }
+      PG_LAUNCH(h, launch_noise_inject_planes(r0, DT_F32, a0, source, S.noise_w, S.noise_b, B, (int)L, C,
+                                              (int)Lsrc, S.noise_k, S.noise_stride, S.noise_pad, SL, s));
+      PG_TRY(record_tap_planes(h, s, "dec.ups" + std::to_string(i), r0, DT_F32, 1.f, B, L, C));
+      for (int j = 0; j < nk; ++j) {
+        const int ksz = c.resblock_kernel_sizes[j];
+        const __half* xc = a0;
+        const float* rc = r0;
+        for (int d = 0; d < nd; ++d) {
+          const int dil = c.resblock_dilations[j][d];
+          const bool last = d == nd - 1;
+          PlaneConvArgs a1;
+          a1.x = xc; a1.B = B; a1.L = (int)L; a1.dil = dil; a1.pad = (ksz * dil - dil) / 2;
+          a1.out16 = tmp; a1.out16_slope = SL;
+          PG_TRY(run_plane_conv(h, s, a1, S.c1[j * nd + d]));
+          PlaneConvArgs a2;
+          a2.x = tmp; a2.B = B; a2.L = (int)L; a2.pad = (ksz - 1) / 2;
+          a2.res32 = rc;
+          if (last) {
+            a2.out_scale = 1.f / nk;
+            a2.accin32 = j > 0 ? acc : nullptr;
+            a2.out32 = acc;
+          } else {
+            const bool to_b = xc == aa;
+            a2.out32 = to_b ? rb : ra;
+            a2.out16 = to_b ? ab : aa;
+            a2.out16_slope = SL;
+            xc = a2.out16;
+            rc = a2.out32;
+          }
+          PG_TRY(run_plane_conv(h, s, a2, S.c2[j * nd + d]));
+        }
+      }
+      PG_TRY(record_tap_planes(h, s, "dec.stage" + std::to_string(i), acc, DT_F32, 1.f, B, L, C));
+      const int Cl = C;
+      PG_LAUNCH(h, launch_conv_post_planes(acc, DT_F32, h->conv_post_w, wave, B, (int)L, Cl, 7, 0.01f, s));
+      return PG_OK;
+    }
+    // acc lives in buf[cur]: the next stage reads it
+  }
+  return fail(PG_ERR_UNSUPPORTED, "decoder needs at least one upsampling stage");
+}
+
+int run_decoder(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const float* z,
+                const float* source, float* wave) {
+  if (h->cfg.flags & (PG_FLAG_FORCE_SIMT | PG_FLAG_LEGACY_DECODER))
+    return run_generator(h, s, w, B, T, z, source, wave);
+  return run_generator_planes(h, s, w, B, T, z, source, wave);
+}
+
 int check_ready(pg_handle h, int B, int T) {
   if (!h) return fail(PG_ERR_INVALID, "null handle");
   if (!h->finalized) return fail(PG_ERR_STATE, "pg_finalize has not been called");
@@ -862,7 +1055,7 @@ int pg_infer(pg_handle h, void* stream, int B, int T, const float* phone, const 
                              nullptr, B, T, h->upp, c.sr, s));
   ++h->launches;   // launch_source issues two kernels
   PG_TRY(record_tap(h, s, "source", source, DT_F32, B, (int64_t)T * h->upp, 1));
-  PG_TRY(run_generator(h, s, w, B, T, z, source, wave));
+  PG_TRY(run_decoder(h, s, w, B, T, z, source, wave));
   if (aux) {
     const size_t n = (size_t)B * T * C * sizeof(float);
     char* a = reinterpret_cast<char*>(aux);
@@ -979,7 +1172,7 @@ int pg_generator(pg_handle h, void* stream, int B, int T, const float* z, const 
   PG_CUDA_CHECK(cudaStreamSynchronize(s));
   PG_LAUNCH(h, launch_prepare_ints(d_len, nullptr, sid, at<int>(h, w.lens), at<int>(h, w.pitch),
                                    at<int>(h, w.sid), B, T, h->cfg.spk_embed_dim, s));
-  PG_TRY(run_generator(h, s, w, B, T, z, source, wave));
+  PG_TRY(run_decoder(h, s, w, B, T, z, source, wave));
   return PG_OK;
 }
 
@@ -1087,7 +1280,37 @@ int pg_op_conv1d_f16(int device, int impl, int B, int L, int Cin, int Cout, int 
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  if (impl == 1 && !umma_conv_supported(a)) {
+  if (impl == 2) {
+    // channel-plane kernel: convert in, run, convert out (only the conv launches are timed)
+    const size_t n_in = (size_t)B * L * Cin, n_out = (size_t)B * L * Cout;
+    __half *xp = nullptr, *rp = nullptr, *yp = nullptr;
+    PG_CUDA_CHECK(cudaMalloc(&xp, n_in * 2 + 256));
+    PG_CUDA_CHECK(cudaMalloc(&yp, n_out * 2 + 256));
+    if (res_dev) PG_CUDA_CHECK(cudaMalloc(&rp, n_out * 2 + 256));
+    PlaneConvArgs pa;
+    pa.x = xp; pa.B = B; pa.L = L; pa.Cin = Cin; pa.w16 = d_w16; pa.N = Cout; pa.K = K; pa.dil = dil;
+    pa.pad = (K * dil - dil) / 2; pa.bias = d_b; pa.Cout_real = Cout; pa.row_mul = 1;
+    pa.res16 = rp; pa.res_inv = 1.f; pa.out16 = yp; pa.out16_slope = out_slope;
+    cudaError_t e = launch_nlc_to_planes(x_dev, DT_F16, Cin, 0, xp, B, L, Cin, nullptr, in_slope, 0);
+    if (e == cudaSuccess && res_dev)
+      e = launch_nlc_to_planes(res_dev, DT_F16, Cout, 0, rp, B, L, Cout, nullptr, 1.f, 0);
+    if (e == cudaSuccess && !plane_conv_supported(pa)) {
+      rc = fail(PG_ERR_UNSUPPORTED, "shape not supported by the plane conv kernel");
+    } else {
+      cudaEventRecord(e0, 0);
+      for (int it = 0; it < (iters > 0 ? iters : 1) && e == cudaSuccess; ++it) e = launch_conv_planes(pa, 0);
+      cudaEventRecord(e1, 0);
+      if (e == cudaSuccess) e = launch_planes_to_nlc_f16(yp, reinterpret_cast<__half*>(y_dev), B, L, Cout, 0);
+      cudaError_t e2 = cudaDeviceSynchronize();
+      if (e != cudaSuccess || e2 != cudaSuccess)
+        rc = fail(PG_ERR_CUDA, std::string("plane conv launch: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+      else if (ms_out)
+        cudaEventElapsedTime(ms_out, e0, e1);
+    }
+    cudaFree(xp);
+    cudaFree(yp);
+    if (rp) cudaFree(rp);
+  } else if (impl == 1 && !umma_conv_supported(a)) {
     rc = fail(PG_ERR_UNSUPPORTED, "shape not supported by the tcgen05 conv");
   } else {
     cudaEventRecord(e0, 0);

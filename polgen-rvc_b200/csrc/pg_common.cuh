@@ -54,6 +54,48 @@ bool umma_conv_supported(const ConvArgs& a);
 int umma_pick_nt(int cout);   // Cout tile the tcgen05 conv will use (0 = unsupported)
 cudaError_t launch_conv_umma(const ConvArgs& a, DType in_dt, DType out_dt, cudaStream_t s);
 
+// ---- channel-plane layout (decoder): f16/f32 [B][C/8][L][8] ------------------------------
+// One conv layer over plane activations on the tcgen05 kernel (pg_conv_planes.cu):
+//   v = out_scale * (sum_{tap,ci} W[tap][n][ci] * x[b][t + tap*dil - pad][ci] + bias[n] + bbias[b][n]
+//                    + raw(res16) + res32) + accin
+//   out32 = v ; out16 = lrelu(v, out16_slope)           (either may be null)
+// Column n of the GEMM maps to output row t*row_mul + n / Cout_real, channel n % Cout_real
+// (row_mul > 1: polyphase ConvTranspose1d).  res16 is stored post-activation: raw = v<0 ? v*res_inv : v.
+struct PlaneConvArgs {
+  const __half* x = nullptr; int B = 0, L = 0, Cin = 0;
+  const int* lens = nullptr; int in_mask = 0;            // input rows >= lens[b] read as zero
+  const void* w16 = nullptr;                              // [K][N][Cin] f16
+  int N = 0, K = 1, dil = 1, pad = 0;
+  const float* bias = nullptr; const float* bbias = nullptr; int bbias_ld = 0;
+  const uint32_t* tapmask = nullptr;
+  int Cout_real = 0, row_mul = 1;
+  const __half* res16 = nullptr; float res_inv = 1.f; const float* res32 = nullptr;
+  const __half* accin16 = nullptr; const float* accin32 = nullptr;
+  __half* out16 = nullptr; float out16_slope = 1.f; float* out32 = nullptr;
+  float out_scale = 1.f;
+};
+bool plane_conv_supported(const PlaneConvArgs& a);
+int plane_pick_nt(int n);
+cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s);
+
+// time-major [B][L][x_ld] (channels x_coff..x_coff+C) -> planes f16, rows >= lens[b] zeroed when lens,
+// stored as lrelu(x, slope)
+cudaError_t launch_nlc_to_planes(const void* x, DType dt, int x_ld, int x_coff, __half* y, int B, int L,
+                                 int C, const int* lens, float slope, cudaStream_t s);
+// planes (f16 or f32) -> time-major f32 [B][L][C]; inv_slope undoes an L-form storage (1 = raw)
+cudaError_t launch_planes_to_nlc(const void* x, DType dt, float* y, int B, int L, int C, float inv_slope,
+                                 cudaStream_t s);
+// planes f16 -> time-major f16 [B][L][C]
+cudaError_t launch_planes_to_nlc_f16(const __half* x, __half* y, int B, int L, int C, cudaStream_t s);
+// x_raw (planes, f16 or f32, in place) += bn[c] + sum_j wn[j][c] * src[b][t*stride + j - pad];
+// a16 = lrelu(x, slope) (f16 planes); f32 raw kept in x when dt == DT_F32
+cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, const float* src, const float* wn,
+                                       const float* bn, int B, int L, int C, int Lsrc, int k, int stride,
+                                       int pad, float slope, cudaStream_t s);
+// wave = tanh(conv_post(lrelu(x, in_slope))) over planes (f16 or f32)
+cudaError_t launch_conv_post_planes(const void* x, DType dt, const float* w /*[K][C]*/, float* wave, int B,
+                                    int L, int C, int K, float in_slope, cudaStream_t s);
+
 cudaError_t launch_prepare_ints(const int64_t* lengths, const int64_t* pitch, const int64_t* sid,
                                 int* lens32, int* pitch32, int* sid32, int B, int T, int n_spk,
                                 cudaStream_t s);

@@ -1,0 +1,225 @@
+// Bandwidth kernels of the decoder over the channel-plane layout f16/f32 [B][C/8][L][8]
+// (see pg_conv_planes.cu): layout conversion at the decoder's input and at the parity taps,
+// the NSF source injection (reference rvc/lib/algorithm/nsf.py:93-101, :131) and
+// leaky_relu(0.01) -> conv_post -> tanh (nsf.py:142-143).
+// Thread mapping everywhere: consecutive threads = consecutive time rows of one plane, so every
+// plane access is a coalesced 16-byte (f16) / 32-byte (f32) per-lane vector.
+#include "pg_common.cuh"
+
+namespace pg {
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 q;
+  __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  return q;
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+  unpack8(*reinterpret_cast<const uint4*>(p), v);
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = pack8(v);
+}
+
+// (b, plane, t) of a flat index with t fastest
+struct Idx { int b, pl, t; };
+__device__ __forceinline__ Idx split(size_t i, int L, int CP) {
+  Idx r;
+  r.t = (int)(i % L);
+  const size_t q = i / L;
+  r.pl = (int)(q % CP);
+  r.b = (int)(q / CP);
+  return r;
+}
+
+template <typename TIn>
+__global__ void nlc_to_planes_kernel(const TIn* __restrict__ x, int x_ld, int x_coff, __half* __restrict__ y,
+                                     int B, int L, int C, const int* __restrict__ lens, float slope) {
+  const int CP = C / 8;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * CP * L) return;
+  const Idx id = split(i, L, CP);
+  float v[8];
+  if (lens && id.t >= lens[id.b]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+  } else {
+    load8(x + ((size_t)id.b * L + id.t) * x_ld + x_coff + id.pl * 8, v);
+    if (slope != 1.f) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
+    }
+  }
+  store8(y + i * 8, v);
+}
+
+template <typename TIn, typename TOut>
+__global__ void planes_to_nlc_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, int B, int L, int C,
+                                     float inv_slope) {
+  const int CP = C / 8;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * CP * L) return;
+  const Idx id = split(i, L, CP);
+  float v[8];
+  load8(x + i * 8, v);
+  if (inv_slope != 1.f) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = v[k] < 0.f ? v[k] * inv_slope : v[k];
+  }
+  store8(y + ((size_t)id.b * L + id.t) * C + id.pl * 8, v);
+}
+
+// nsf.py:131  x = x + noise_convs[i](har_source), then the L-form copy the next conv reads
+template <typename T>
+__global__ void __launch_bounds__(256) noise_inject_planes_kernel(
+    T* __restrict__ x, __half* __restrict__ a16, const float* __restrict__ src, const float* __restrict__ wn,
+    const float* __restrict__ bn, int B, int L, int C, int Lsrc, int k, int stride, int pad, float slope) {
+  const int CP = C / 8;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * CP * L) return;
+  const Idx id = split(i, L, CP);
+  const int c0 = id.pl * 8;
+  float acc[8];
+  load8(bn + c0, acc);
+  const float* sp = src + (size_t)id.b * Lsrc;
+  const int s0 = id.t * stride - pad;
+  for (int j = 0; j < k; ++j) {
+    const int n = s0 + j;
+    if (n < 0 || n >= Lsrc) continue;
+    const float sv = sp[n];
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wn + (size_t)j * C + c0));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wn + (size_t)j * C + c0 + 4));
+    acc[0] = fmaf(w0.x, sv, acc[0]); acc[1] = fmaf(w0.y, sv, acc[1]);
+    acc[2] = fmaf(w0.z, sv, acc[2]); acc[3] = fmaf(w0.w, sv, acc[3]);
+    acc[4] = fmaf(w1.x, sv, acc[4]); acc[5] = fmaf(w1.y, sv, acc[5]);
+    acc[6] = fmaf(w1.z, sv, acc[6]); acc[7] = fmaf(w1.w, sv, acc[7]);
+  }
+  float v[8];
+  load8(x + i * 8, v);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] += acc[q];
+  if (sizeof(T) == 4) store8(x + i * 8, v);   // fp32 residual stream keeps the raw value
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * slope;
+  store8(a16 + i * 8, v);
+}
+
+// nsf.py:142-143  wave = tanh(conv_post(leaky_relu(x)))  (Cout = 1, no bias); one thread per sample
+template <typename T, int K>
+__global__ void __launch_bounds__(256) conv_post_planes_kernel(const T* __restrict__ x,
+                                                               const float* __restrict__ w /*[K][C]*/,
+                                                               float* __restrict__ wave, int L, int C,
+                                                               float in_slope) {
+  extern __shared__ float ws[];
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L) return;
+  const int CP = C / 8;
+  float acc = 0.f;
+  for (int pl = 0; pl < CP; ++pl) {
+    const T* plane = x + ((size_t)b * CP + pl) * (size_t)L * 8;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int n = t + j - K / 2;
+      if (n < 0 || n >= L) continue;
+      float v[8];
+      load8(plane + (size_t)n * 8, v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float a = v[q] > 0.f ? v[q] : v[q] * in_slope;
+        acc = fmaf(ws[j * C + pl * 8 + q], a, acc);
+      }
+    }
+  }
+  wave[(size_t)b * L + t] = tanhf(acc);
+}
+
+unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
+
+}  // namespace
+
+cudaError_t launch_nlc_to_planes(const void* x, DType dt, int x_ld, int x_coff, __half* y, int B, int L,
+                                 int C, const int* lens, float slope, cudaStream_t s) {
+  if (C % 8 || x_ld % 8 || x_coff % 8) return cudaErrorInvalidValue;
+  const size_t n = (size_t)B * (C / 8) * L;
+  if (dt == DT_F32)
+    nlc_to_planes_kernel<float><<<blocks_for(n), 256, 0, s>>>(reinterpret_cast<const float*>(x), x_ld, x_coff,
+                                                             y, B, L, C, lens, slope);
+  else
+    nlc_to_planes_kernel<__half><<<blocks_for(n), 256, 0, s>>>(reinterpret_cast<const __half*>(x), x_ld,
+                                                              x_coff, y, B, L, C, lens, slope);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_planes_to_nlc(const void* x, DType dt, float* y, int B, int L, int C, float inv_slope,
+                                 cudaStream_t s) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const size_t n = (size_t)B * (C / 8) * L;
+  if (dt == DT_F32)
+    planes_to_nlc_kernel<float, float><<<blocks_for(n), 256, 0, s>>>(reinterpret_cast<const float*>(x), y, B, L,
+                                                                    C, inv_slope);
+  else
+    planes_to_nlc_kernel<__half, float><<<blocks_for(n), 256, 0, s>>>(reinterpret_cast<const __half*>(x), y, B,
+                                                                     L, C, inv_slope);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_planes_to_nlc_f16(const __half* x, __half* y, int B, int L, int C, cudaStream_t s) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const size_t n = (size_t)B * (C / 8) * L;
+  planes_to_nlc_kernel<__half, __half><<<blocks_for(n), 256, 0, s>>>(x, y, B, L, C, 1.f);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, const float* src, const float* wn,
+                                       const float* bn, int B, int L, int C, int Lsrc, int k, int stride,
+                                       int pad, float slope, cudaStream_t s) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const size_t n = (size_t)B * (C / 8) * L;
+  if (dt == DT_F32)
+    noise_inject_planes_kernel<float><<<blocks_for(n), 256, 0, s>>>(reinterpret_cast<float*>(x), a16, src, wn, bn,
+                                                                   B, L, C, Lsrc, k, stride, pad, slope);
+  else
+    noise_inject_planes_kernel<__half><<<blocks_for(n), 256, 0, s>>>(reinterpret_cast<__half*>(x), a16, src, wn,
+                                                                    bn, B, L, C, Lsrc, k, stride, pad, slope);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_post_planes(const void* x, DType dt, const float* w, float* wave, int B, int L, int C,
+                                    int K, float in_slope, cudaStream_t s) {
+  if (K != 7 || C % 8 || C > 256) return cudaErrorInvalidValue;
+  dim3 grid((L + 255) / 256, B);
+  const size_t smem = sizeof(float) * K * C;
+  if (dt == DT_F32)
+    conv_post_planes_kernel<float, 7><<<grid, 256, smem, s>>>(reinterpret_cast<const float*>(x), w, wave, L, C,
+                                                             in_slope);
+  else
+    conv_post_planes_kernel<__half, 7><<<grid, 256, smem, s>>>(reinterpret_cast<const __half*>(x), w, wave, L, C,
+                                                              in_slope);
+  return cudaGetLastError();
+}
+
+}  // namespace pg

@@ -211,7 +211,7 @@ def test_conv_op_tcgen05_bit_level(shape):
         torch.nn.functional.leaky_relu(xd.float(), 0.1).half().float().transpose(1, 2), w.to(d), bias.to(d),
         dilation=dil, padding=(K * dil - dil) // 2).transpose(1, 2) + rd.float()
     outs = {}
-    for impl in (0, 1):
+    for impl in (0, 1, 2):
         y = torch.full((B, L, Cc), 7.0, device=d, dtype=torch.half)
         rc = lib.pg_op_conv1d_f16(0, impl, B, L, Cc, Cc, K, dil, C.c_void_p(xd.data_ptr()),
                                   C.c_void_p(w.data_ptr()), C.c_void_p(bias.data_ptr()), C.c_float(0.1),
@@ -222,6 +222,7 @@ def test_conv_op_tcgen05_bit_level(shape):
     tol = 2e-3 * max(1.0, ref.abs().max().item())     # one f16 ulp of the output range
     assert (outs[1] - ref).abs().max().item() <= tol
     assert (outs[0] - ref).abs().max().item() <= tol
+    assert (outs[2] - ref).abs().max().item() <= tol      # channel-plane kernel (the decoder's)
 
 
 def test_full_size_properties_v2_48k():

@@ -126,7 +126,7 @@ def convop():
             torch.nn.functional.leaky_relu(xd.float(), 0.1).transpose(1, 2), w.half().float().to(d), bias.to(d),
             dilation=dil, padding=(K * dil - dil) // 2).transpose(1, 2) + rd.float()
         rec = {"stage": "convop", "C": Cc, "K": K, "dil": dil, "L": L, "B": B, "mt": os.environ.get("PG_UMMA_MT", "auto")}
-        for impl, nm in [(0, "simt"), (1, "umma")]:
+        for impl, nm in [(0, "simt"), (1, "umma"), (2, "planes")]:
             y = torch.zeros(B, L, Cc, device=d, dtype=torch.half)
             ms = C.c_float(0)
             iters = 5
