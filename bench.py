@@ -184,6 +184,7 @@ def run_ours(args):
         step_device()
     torch.cuda.synchronize()
     eng.profile_read()
+    eng.profile_table()     # drop the warm-up records
 
     # ---- timed region: K steps, device time per step via CUDA events, L2 flushed between steps
     sampler = ClockSampler(local)
@@ -203,6 +204,7 @@ def run_ours(args):
     t_wall1 = time.time()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     prof = eng.profile_read()
+    table = eng.profile_table()
     clocks = sampler.stop(t_wall0, t_wall1)
 
     # launches per step: pg_launch_count reports the last call, so run the segments once more
@@ -239,7 +241,7 @@ def run_ours(args):
         umma_ms, umma_fl, umma_n = prof["conv_umma"]
         achieved = umma_fl / (umma_ms * 1e-3) / 1e12 if umma_ms > 0 else 0.0
         roofline = {
-            "bound": "tensor", "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM ResBlock conv)",
+            "bound": "tensor", "kernel": "conv_planes_kernel (tcgen05/TMEM implicit-GEMM conv over channel planes: ResBlocks, ups, conv_pre)",
             "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
             "peak_source": peak_src, "traffic": None,
             "launches": umma_n, "avg_launch_ms": umma_ms / max(umma_n, 1),
@@ -263,6 +265,14 @@ def run_ours(args):
             "clocks": clocks,
             "generator_tflops": cfg.generator_flops_per_frame() * 100 * total_audio / (dev_ms_max * 1e-3) / 1e12,
         }
+        if args.table:
+            # per-layer-shape breakdown of the tensor-core conv launches inside the timed region
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", args.table), "w") as f:
+                f.write("class,Cin,N,K,dil,launches,ms_total,ms_per_launch,tflops,share_of_step\n")
+                for cls, cin, n, k, dil, cnt, ms, fl in sorted(table, key=lambda r: -r[6]):
+                    f.write(f"{'tcgen05' if cls == 0 else 'cuda-core'},{int(cin)},{int(n)},{int(k)},{int(dil)},{int(cnt)},"
+                            f"{ms:.3f},{ms / cnt:.4f},{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.1f},{ms / dev_ms:.4f}\n")
         if world == 1 and not args.no_cpu:
             frames = 500
             rate, sec, threads = cpu_reference_rate(cfg, frames, 2, 1)
@@ -283,6 +293,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="v2-48k", choices=["v2-48k", "v2-40k", "v2-32k", "v1-40k"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--table", default="", help="write the per-layer-shape conv timing table to gpurun_out/<name>")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -169,6 +169,11 @@ int64_t pg_launch_count(pg_handle h);
  * [1] CUDA-core conv.  Each array has 2 entries.  Synchronises on the recorded events. */
 int pg_profile_read(pg_handle h, double* ms_out, double* flops_out, int64_t* launches_out);
 
+/* PG_FLAG_PROFILE: the same records aggregated per layer shape since the previous call (the
+ * records pass through pg_profile_read first).  Each row is 8 doubles: class, Cin, N, K, dilation,
+ * launches, ms, algorithmic FLOPs.  Returns the number of rows written (<= max_rows). */
+int pg_profile_table(pg_handle h, double* rows, int max_rows);
+
 /* Single-layer entry used by the op-level parity tests and micro-benchmarks:
  * y[b][t][co] = sum_{tap,ci} w[co][ci][tap] * lrelu(x[b][t + tap*dil - pad][ci], in_slope) + bias
  * x, y are f16 [B][L][C] device buffers, w f32 host [Cout][Cin][K] (Conv1d

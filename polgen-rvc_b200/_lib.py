@@ -56,6 +56,7 @@ SYMBOLS = {
     "pg_debug_fetch": (C.c_int64, [_P, _P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "pg_launch_count": (C.c_int64, [_P]),
     "pg_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "pg_profile_table": (_I, [_P, C.POINTER(C.c_double), _I]),
     "pg_op_conv1d_f16": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _I,
                               C.POINTER(_F)]),
     "pg_destroy": (_I, [_P]),

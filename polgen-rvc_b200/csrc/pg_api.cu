@@ -106,7 +106,8 @@ struct pg_handle_s {
   DevBuf host_stage;
 
   // PG_FLAG_PROFILE: CUDA events around every conv launch, per kernel class
-  struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; };
+  struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; int shape[5]; };
+  std::map<std::vector<int>, std::vector<double>> prof_table;   // (cls,Cin,N,K,dil,MT..) -> {launches, ms, flops}
   std::vector<ProfRec> prof;       // records of the calls since the last pg_profile_read
   std::vector<cudaEvent_t> ev_pool;
 };
@@ -410,6 +411,7 @@ int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_d
     rec.e1 = take_event(h);
     rec.cls = umma ? 0 : 1;
     rec.flops = 2.0 * a.B * a.L_out * (double)a.Cin * a.Cout * a.K;
+    rec.shape[0] = a.Cin; rec.shape[1] = a.Cout; rec.shape[2] = a.K; rec.shape[3] = a.dil; rec.shape[4] = a.L_out;
     cudaEventRecord(rec.e0, s);
   }
   if (umma) {
@@ -655,6 +657,7 @@ int run_plane_conv(pg_handle h, cudaStream_t s, PlaneConvArgs a, const ConvW& w)
     rec.e1 = take_event(h);
     rec.cls = 0;
     rec.flops = 2.0 * a.B * a.L * (double)a.Cin * a.N * a.K;
+    rec.shape[0] = a.Cin; rec.shape[1] = a.N; rec.shape[2] = a.K; rec.shape[3] = a.dil; rec.shape[4] = a.L;
     cudaEventRecord(rec.e0, s);
   }
   PG_LAUNCH(h, launch_conv_planes(a, s));
@@ -1219,11 +1222,32 @@ int pg_profile_read(pg_handle h, double* ms_out, double* flops_out, int64_t* lau
     ms_out[r.cls] += ms;
     flops_out[r.cls] += r.flops;
     launches_out[r.cls] += 1;
+    std::vector<double>& row = h->prof_table[{r.cls, r.shape[0], r.shape[1], r.shape[2], r.shape[3]}];
+    row.resize(3, 0.0);
+    row[0] += 1;
+    row[1] += ms;
+    row[2] += r.flops;
     h->ev_pool.push_back(r.e0);
     h->ev_pool.push_back(r.e1);
   }
   h->prof.clear();
   return PG_OK;
+}
+
+int pg_profile_table(pg_handle h, double* rows, int max_rows) {
+  if (!h || !rows) return fail(PG_ERR_INVALID, "null argument");
+  int n = 0;
+  for (auto& kv : h->prof_table) {
+    if (n >= max_rows) break;
+    double* r = rows + (size_t)n * 8;
+    for (int i = 0; i < 5; ++i) r[i] = kv.first[i];
+    r[5] = kv.second[0];
+    r[6] = kv.second[1];
+    r[7] = kv.second[2];
+    ++n;
+  }
+  h->prof_table.clear();
+  return n;
 }
 
 int pg_destroy(pg_handle h) {

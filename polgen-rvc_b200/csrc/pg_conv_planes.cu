@@ -24,12 +24,15 @@
 //   warp 0      A loader (bulk copies + boundary zero fill)
 //   warp 1      weight TMA producer
 //   warp 2      TMEM owner + MMA issuer
-//   warps 4-11  epilogue: TMEM -> registers -> bias / residual / scale / accumulate / leaky-ReLU
+//   warp 3      residual loader: bulk copies of the epilogue's residual items into a shared ring
+//   warps 4-19  epilogue: TMEM -> registers -> bias / residual / scale / accumulate / leaky-ReLU
 //               -> global.  Two accumulator sets so the epilogue of tile i overlaps the MMAs of i+1.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdio.h>
 #include <stdlib.h>
+
+#include <algorithm>
 
 #include "pg_common.cuh"
 #include "pg_umma.cuh"
@@ -41,7 +44,9 @@ namespace {
 using namespace umma;
 
 constexpr int BM = 128;
-constexpr int LOAD_WARP = 0, TMA_WARP = 1, MMA_WARP = 2, EPI_WARP0 = 4, EPI_WARPS = 8;
+constexpr int LOAD_WARP = 0, TMA_WARP = 1, MMA_WARP = 2, RES_WARP = 3, EPI_WARP0 = 4, EPI_WARPS = 16;
+constexpr int EPI_GROUPS = EPI_WARPS / 4;   // warps per TMEM lane quarter
+constexpr int EPI_COLS = 16;                // accumulator columns per epilogue item
 constexpr int NTHREADS = (EPI_WARP0 + EPI_WARPS) * 32;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GROUP_PLANES = 16;   // 128 channels per activation-ring slot
@@ -59,9 +64,24 @@ struct PlaneParams {
   __half* out16; float out16_slope; float* out32;
   float out_scale;
   int plane_bytes, KC, PG, n_groups, a_slots, a_slot_bytes, stages, stage_bytes, resident, tmem_cols;
+  int r_slots, r_slot_bytes, res_cols;  // residual ring: one slot = 128 rows x res_cols columns
+  int bias_smem;                        // bias[N] staged in shared memory (N <= 1024)
   uint32_t idesc;
-  int debug;   // PG_PLANES_DEBUG bitmask (timing experiments only): 1 no A copies, 2 no epilogue I/O, 4 no MMA
+  int debug;   // PG_PLANES_DEBUG bitmask (timing experiments only): 1 no A copies, 2 no epilogue I/O, 4 no MMA,
+               // 8 trace, 16 consumers skip their waits (free-running roles), 32 epilogue idle, 64 no producers
 };
+
+// PG_PLANES_DEBUG & 8: CTA 0 records (role, event, tile, globaltimer) -- timing experiments only
+__device__ unsigned long long g_ptrace[4096];
+__device__ unsigned int g_ptrace_n;
+__device__ __forceinline__ void trace(const PlaneParams& p, int role, int ev, int tile) {
+  if ((p.debug & 8) && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned int i = atomicAdd(&g_ptrace_n, 1u);
+    if (i < 4096) g_ptrace[i] = (t << 20) | ((unsigned long long)role << 16) | ((unsigned long long)ev << 12) | (unsigned)(tile & 0xFFF);
+  }
+}
 
 struct TileCoord { int rt, b, ntile; };
 __device__ __forceinline__ TileCoord decode_tile(int id, const PlaneParams& p) {
@@ -90,14 +110,15 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   return q;
 }
 
-template <int MT>
+template <int MT, int KC16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_ring = smem;
   uint8_t* a_ring = w_ring + (size_t)p.stages * p.stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + (size_t)p.a_slots * p.a_slot_bytes);
+  uint8_t* r_ring = a_ring + (size_t)p.a_slots * p.a_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(r_ring + (size_t)p.r_slots * p.r_slot_bytes);
   uint64_t* full = bars;                      // [stages]
   uint64_t* empty = full + p.stages;          // [stages]
   uint64_t* a_full = empty + p.stages;        // [a_slots]
@@ -105,7 +126,10 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
   uint64_t* acc_full = a_empty + p.a_slots;   // [2]
   uint64_t* acc_empty = acc_full + 2;         // [2]
   uint64_t* w_ready = acc_empty + 2;          // resident weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_ready + 1);
+  uint64_t* r_full = w_ready + 1;             // [r_slots]
+  uint64_t* r_empty = r_full + p.r_slots;     // [r_slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_empty + p.r_slots);
+  float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [N] when p.bias_smem
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -120,11 +144,17 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], EPI_THREADS);
+      mbar_init(&acc_empty[s], EPI_WARPS);
+    }
+    for (int s = 0; s < p.r_slots; ++s) {
+      mbar_init(&r_full[s], 1);
+      mbar_init(&r_empty[s], (uint32_t)(4 * p.res_cols / EPI_COLS));   // every warp-item that reads the slot
     }
     mbar_init(w_ready, 1);
     fence_barrier_init();
   }
+  if (p.bias_smem)
+    for (int i = tid; i < p.N; i += NTHREADS) bias_s[i] = p.bias[i];
   if (warp == MMA_WARP) tcgen05_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   if (warp == TMA_WARP && lane == 0)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
@@ -132,12 +162,14 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) trace(p, 4, 0, 0);
 
   const int chunks_per_group = p.PG * 8 / p.KC;
   const int n_chunks = p.Cin / p.KC;
   const int planes_total = p.Cin / 8;
 
-  if (warp == LOAD_WARP) {
+  const bool freerun = (p.debug & 16) != 0;
+  if (warp == LOAD_WARP && !(p.debug & 64)) {
     // ===== A loader: one bulk copy per plane of the (tile, group) window =====
     const int rows = BM * MT + (p.K - 1) * p.dil;
     uint32_t a_cnt = 0;
@@ -153,6 +185,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       for (int g = 0; g < p.n_groups; ++g, ++a_cnt) {
         const uint32_t slot = a_cnt % (uint32_t)p.a_slots;
         mbar_wait(&a_empty[slot], ((a_cnt / (uint32_t)p.a_slots) & 1u) ^ 1u);
+        if (lane == 0) trace(p, 0, 1, (int)a_cnt);
         uint8_t* dst = a_ring + (size_t)slot * p.a_slot_bytes;
         const int pl0 = g * p.PG;
         const int npl = min(p.PG, planes_total - pl0);
@@ -173,7 +206,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
                    xb + ((size_t)(pl0 + lane) * p.L + (tstart + lo)) * 8, bytes, &a_full[slot]);
       }
     }
-  } else if (warp == TMA_WARP) {
+  } else if (warp == TMA_WARP && !(p.debug & 64)) {
     // ===== weight producer: (tile, group, chunk, tap) order =====
     if (p.resident) {
       if (elect_one()) {
@@ -205,82 +238,124 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         }
       }
     }
-  } else if (warp == MMA_WARP) {
-    // ===== MMA issuer: the whole warp walks the loops, one elected lane issues =====
+  } else if (warp == MMA_WARP && !(p.debug & 128)) {
+    // ===== MMA issuer: ONE elected lane runs the whole role (waits, issues, commits); inside the
+    // single-lane region the compiler moves operands to uniform registers without waterfall loops =====
+    if (elect_one()) {
     const uint32_t w_layout = p.KC == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
     const uint32_t w_sbo = 8u * (uint32_t)p.KC * 2u;
     const uint64_t adesc0 = make_desc(0u, (uint32_t)p.plane_bytes, 128u, LAYOUT_NONE);
     const uint64_t bdesc0 = make_desc(0u, 0u, w_sbo, w_layout);
+    const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+    const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;   // LBO field, start = 0
     const uint32_t plane_units = (uint32_t)p.plane_bytes >> 4;
-    const int kc16 = p.KC / 16, kc8 = p.KC / 8;
+    const uint32_t plane2 = 2u * plane_units;
+    const int kc8 = p.KC / 8;
     const uint32_t nt = (uint32_t)p.NT, idesc = p.idesc;
-    const bool do_mma = !(p.debug & 4);
+    const bool do_mma = !(p.debug & 4), do_commit = !(p.debug & 512);
+    const uint32_t w_ring_units = smem_u32(w_ring) >> 4, stage_units = (uint32_t)p.stage_bytes >> 4;
+    const uint32_t a_ring_units = smem_u32(a_ring) >> 4, slot_units = (uint32_t)p.a_slot_bytes >> 4;
     int stage = 0;
     uint32_t phase = 0, a_cnt = 0, t_cnt = 0;
-    if (p.resident) {
+    if (p.resident && !freerun) {
       mbar_wait(w_ready, 0);
       tcgen05_fence_after();
     }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t_cnt) {
-      const TileCoord tc = decode_tile(tile, p);
-      const uint32_t tapmask = p.tapmask ? p.tapmask[tc.ntile] : 0xFFFFFFFFu;
+      const uint32_t tapmask = p.tapmask ? p.tapmask[(tile % p.n_ntiles)] : 0xFFFFFFFFu;
       const uint32_t accb = t_cnt & 1u;
-      mbar_wait(&acc_empty[accb], ((t_cnt >> 1) & 1u) ^ 1u);
+      if (!freerun) mbar_wait(&acc_empty[accb], ((t_cnt >> 1) & 1u) ^ 1u);
       tcgen05_fence_after();
+      trace(p, 1, 1, (int)t_cnt);
       const uint32_t d_base = tmem_base + accb * (uint32_t)MT * nt;
       uint32_t started = 0;
       for (int g = 0; g < p.n_groups; ++g, ++a_cnt) {
         const uint32_t slot = a_cnt % (uint32_t)p.a_slots;
-        mbar_wait(&a_full[slot], (a_cnt / (uint32_t)p.a_slots) & 1u);
+        if (!freerun) mbar_wait(&a_full[slot], (a_cnt / (uint32_t)p.a_slots) & 1u);
         tcgen05_fence_after();
-        const uint32_t a_units = smem_u32(a_ring + (size_t)slot * p.a_slot_bytes) >> 4;
+        trace(p, 1, 2, (int)t_cnt);
+        const uint32_t a_units = a_ring_units + slot * slot_units;
         const int c_begin = g * chunks_per_group;
         const int c_end = min(n_chunks, c_begin + chunks_per_group);
         for (int chunk = c_begin; chunk < c_end; ++chunk) {
-          const int chunk_in_group = chunk - c_begin;
-          for (int tap = 0; tap < p.K; ++tap) {
+          const uint32_t a_chunk = a_lo0 + a_units + (uint32_t)((chunk - c_begin) * kc8) * plane_units;
+          uint32_t w_res = b_lo0 + w_ring_units + (uint32_t)(chunk * p.K) * stage_units;   // resident tile
+#pragma unroll 1
+          for (int tap = 0; tap < p.K; ++tap, w_res += stage_units) {
             if (!((tapmask >> tap) & 1u)) continue;
+            uint32_t w_lo = w_res;
             if (!p.resident) {
-              mbar_wait(&full[stage], phase);
+              if (!freerun) mbar_wait(&full[stage], phase);
               tcgen05_fence_after();
+              w_lo = b_lo0 + w_ring_units + (uint32_t)stage * stage_units;
             }
-            const uint32_t w_units =
-                smem_u32(w_ring + (size_t)(p.resident ? chunk * p.K + tap : stage) * p.stage_bytes) >> 4;
-            const uint32_t a_tap = a_units + (uint32_t)(chunk_in_group * kc8) * plane_units + (uint32_t)(tap * p.dil);
-            if (elect_one()) {
-              if (do_mma) {
-                for (int k16 = 0; k16 < kc16; ++k16) {
-                  const uint64_t bdesc = bdesc0 | (uint64_t)(w_units + 2u * k16);
-                  const uint32_t a_k = a_tap + 2u * (uint32_t)k16 * plane_units;
+            const uint32_t a_lo = a_chunk + (uint32_t)(tap * p.dil);
 #pragma unroll
-                  for (int m = 0; m < MT; ++m) {
-                    const uint64_t adesc = adesc0 | (uint64_t)(a_k + (uint32_t)m * BM);
-                    umma_f16(d_base + (uint32_t)m * nt, adesc, bdesc, idesc, started | (uint32_t)k16);
-                  }
-                }
-              }
-              if (!p.resident) tcgen05_commit(&empty[stage]);
+            for (int k16 = 0; k16 < KC16; ++k16) {
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                if (do_mma)
+                  umma_f16_lh(d_base + (uint32_t)m * nt, a_lo + (uint32_t)k16 * plane2 + (uint32_t)(m * BM), a_hi,
+                              w_lo + 2u * (uint32_t)k16, b_hi, idesc, started | (uint32_t)k16);
             }
-            __syncwarp();
             started = 1;
             if (!p.resident) {
+              if (do_commit) tcgen05_commit(&empty[stage]);
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
         }
-        if (elect_one()) tcgen05_commit(&a_empty[slot]);
-        __syncwarp();
+        if (do_commit) tcgen05_commit(&a_empty[slot]);
       }
-      if (elect_one()) tcgen05_commit(&acc_full[accb]);
-      __syncwarp();
+      if (do_commit) tcgen05_commit(&acc_full[accb]);
+      trace(p, 1, 3, (int)t_cnt);
     }
-  } else if (warp >= EPI_WARP0) {
-    // ===== epilogue: quarter q = warp % 4 owns TMEM lanes 32q..32q+31 (one output row per lane);
-    // the two warps of a quarter alternate over the (row tile m, 32-column block) items.
-    const int quarter = warp & 3, grp = (warp - EPI_WARP0) >> 2;
-    const int n_cb = p.NT / 32, items = MT * n_cb;
+    }
+  } else if (warp == RES_WARP && p.r_slots > 0 && !(p.debug & (64 | 16384))) {
+    // ===== residual loader: slot = (row tile m, res_cols-column block) -> res_cols/8 planes x 128 rows.
+    // The <= 4 slots of a tile are issued together: lanes [8w, 8w + res_cols/8) serve slot w.
+    const int n_rb = p.NT / p.res_cols, per_tile = MT * n_rb, rb_shift = 31 - __clz(n_rb);
+    const int rplanes = p.res_cols / 8;
     const int CP = p.Cout_real / 8;
-    const bool f32io = p.res32 || p.accin32;
+    const uint32_t esz = p.res32 ? 32u : 16u;   // bytes per (row, 8-channel chunk)
+    const char* rbase = p.res32 ? reinterpret_cast<const char*>(p.res32) : reinterpret_cast<const char*>(p.res16);
+    const int sub = lane >> 3, pl = lane & 7;
+    const int batch = min(min(per_tile, p.r_slots), 4);   // slots issued together (distinct ring entries)
+    uint32_t s_cnt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, s_cnt += (uint32_t)per_tile) {
+      const TileCoord tc = decode_tile(tile, p);
+      const int t0 = tc.rt * (BM * MT), n0 = tc.ntile * p.NT;
+      const size_t plane0 = (size_t)tc.b * CP;
+      for (int base = 0; base < per_tile; base += batch) {
+        const int which = base + sub;
+        const bool mine = sub < batch && which < per_tile && pl < rplanes;
+        const uint32_t sidx = s_cnt + (uint32_t)which;
+        const uint32_t slot = sidx % (uint32_t)p.r_slots;
+        const int m = which >> rb_shift, rb = which & (n_rb - 1);
+        const int row0 = t0 + m * BM;
+        const int nrows = min(BM, p.L - row0);
+        const uint32_t bytes = (nrows > 0 && !(p.debug & (2 | 4096))) ? (uint32_t)nrows * esz : 0u;
+        if (mine) mbar_wait(&r_empty[slot], ((sidx / (uint32_t)p.r_slots) & 1u) ^ 1u);
+        __syncwarp();
+        if (mine && pl == 0) mbar_expect_tx(&r_full[slot], (uint32_t)rplanes * bytes);
+        __syncwarp();
+        if (mine && bytes) {
+          const int co = n0 + rb * p.res_cols + pl * 8;      // residual: row_mul == 1, column == channel
+          const size_t off = (plane0 + (co >> 3)) * p.L_out + row0;
+          bulk_g2s(r_ring + (size_t)slot * p.r_slot_bytes + (size_t)pl * (BM * esz), rbase + off * esz, bytes,
+                   &r_full[slot]);
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0 && !(p.debug & 256)) {
+    // ===== epilogue: quarter q = warp % 4 owns TMEM lanes 32q..32q+31 (one output row per lane);
+    // the EPI_GROUPS warps of a quarter interleave over the (row tile m, 16-column block cb) items.
+    const int quarter = warp & 3, grp = (warp - EPI_WARP0) >> 2;
+    const int n_cb = p.NT / EPI_COLS, items = MT * n_cb, cb_shift = 31 - __clz(n_cb);
+    const int CP = p.Cout_real / 8;
+    const int cout_shift = 31 - __clz(p.Cout_real);       // Cout_real is a power of two (checked on the host)
+    constexpr int NCH = EPI_COLS / 8;                     // 8-channel chunks per item
+    const bool io = !(p.debug & (2 | 2048));
     uint32_t t_cnt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t_cnt) {
       const TileCoord tc = decode_tile(tile, p);
@@ -290,87 +365,121 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       const float* bias = p.bias ? p.bias + n0 : nullptr;
       const float* bbias = p.bbias ? p.bbias + (size_t)tc.b * p.bbias_ld + n0 : nullptr;
       const size_t plane0 = (size_t)tc.b * CP;
-
-      // output offset (in 8-element units) of chunk j of item `it` for this lane's row
-      auto chunk_off = [&](int it, int j, bool* ok) -> size_t {
-        const int m = it / n_cb, cb = it - m * n_cb;
-        const int q = t0 + m * BM + quarter * 32 + lane;
-        *ok = q < p.L;
-        const int n = n0 + cb * 32 + j * 8;
-        const int r = n / p.Cout_real, co = n - r * p.Cout_real;
-        return (plane0 + (co >> 3)) * p.L_out + (size_t)(*ok ? q : 0) * p.row_mul + r;
-      };
-      uint4 rnext[4];
-      auto fetch16 = [&](int it) {
-        if (!p.res16 || it >= items || (p.debug & 2)) return;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          bool ok;
-          const size_t off = chunk_off(it, j, &ok);
-          rnext[j] = ok ? __ldg(reinterpret_cast<const uint4*>(p.res16) + off) : make_uint4(0u, 0u, 0u, 0u);
-        }
-      };
-      fetch16(grp);
-      mbar_wait(&acc_full[accb], (t_cnt >> 1) & 1u);
+      const int qbase = t0 + quarter * 32 + lane;
+      if (!freerun) mbar_wait(&acc_full[accb], (t_cnt >> 1) & 1u);
       tcgen05_fence_after();
+      if (tid == EPI_WARP0 * 32) trace(p, 3, 1, (int)t_cnt);
 #pragma unroll 1
-      for (int it = grp; it < items; it += 2) {
-        const int m = it / n_cb, cb = it - m * n_cb;
-        uint4 rcur[4];
+      for (int it = (p.debug & 32) ? items : grp; it < items; it += EPI_GROUPS) {
+        const int m = it >> cb_shift, cb = it & (n_cb - 1);
+        const int q = qbase + m * BM;
+        const bool ok = q < p.L && io;
+        const int c0 = cb * EPI_COLS;                      // column inside the tile
+        const int n = n0 + c0;                             // GEMM column -> (phase r, channel co)
+        const int r = n >> cout_shift, co = n & (p.Cout_real - 1);
+        const size_t off0 = (plane0 + (co >> 3)) * p.L_out + (size_t)(q < p.L ? q : 0) * p.row_mul + r;
+        // independent loads first: accumulate-input, bias
+        uint4 ain[2 * NCH];
+        if (ok && p.accin16) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * (uint32_t)(MT * p.NT) +
-                      (uint32_t)(m * p.NT + cb * 32), acc);
-        if (!f32io) fetch16(it + 2);
+          for (int j = 0; j < NCH; ++j) ain[j] = *(reinterpret_cast<const uint4*>(p.accin16) + off0 + (size_t)j * p.L_out);
+        }
+        if (ok && p.accin32) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          bool ok;
-          const size_t off = chunk_off(it, j, &ok);
-          const int c = cb * 32 + j * 8;
+          for (int j = 0; j < NCH; ++j) {
+            ain[2 * j] = *(reinterpret_cast<const uint4*>(p.accin32) + (off0 + (size_t)j * p.L_out) * 2);
+            ain[2 * j + 1] = *(reinterpret_cast<const uint4*>(p.accin32) + (off0 + (size_t)j * p.L_out) * 2 + 1);
+          }
+        }
+        float bv[EPI_COLS];
+#pragma unroll
+        for (int i = 0; i < EPI_COLS; ++i) bv[i] = 0.f;
+        if (p.bias_smem) {
+#pragma unroll
+          for (int i = 0; i < EPI_COLS / 4; ++i) {
+            const float4 b4 = *(reinterpret_cast<const float4*>(bias_s + n0 + c0) + i);
+            bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
+          }
+        } else if (bias) {
+#pragma unroll
+          for (int i = 0; i < EPI_COLS / 4; ++i) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0) + i);
+            bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
+          }
+        }
+        if (bbias) {
+#pragma unroll
+          for (int i = 0; i < EPI_COLS / 4; ++i) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bbias + c0) + i);
+            bv[4 * i] += b4.x; bv[4 * i + 1] += b4.y; bv[4 * i + 2] += b4.z; bv[4 * i + 3] += b4.w;
+          }
+        }
+        // residual item from the shared ring (the loader runs a ring ahead of the MMAs)
+        uint4 rcur[2 * NCH];
+        if (p.r_slots > 0 && !(p.debug & 16384)) {
+          const int n_rb = p.NT / p.res_cols;
+          const uint32_t sidx = (t_cnt * (uint32_t)MT + (uint32_t)m) * (uint32_t)n_rb + (uint32_t)(c0 / p.res_cols);
+          const uint32_t slot = sidx % (uint32_t)p.r_slots;
+          if (!freerun) mbar_wait(&r_full[slot], (sidx / (uint32_t)p.r_slots) & 1u);
+          const uint32_t esz = p.res32 ? 32u : 16u;
+          const uint8_t* rs = r_ring + (size_t)slot * p.r_slot_bytes + (size_t)((c0 % p.res_cols) >> 3) * (BM * esz);
+          const int rrow = quarter * 32 + lane;
+          if (p.res32) {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+              rcur[2 * j] = *reinterpret_cast<const uint4*>(rs + j * (BM * 32) + rrow * 32);
+              rcur[2 * j + 1] = *reinterpret_cast<const uint4*>(rs + j * (BM * 32) + rrow * 32 + 16);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) rcur[j] = *reinterpret_cast<const uint4*>(rs + j * (BM * 16) + rrow * 16);
+          }
+          __syncwarp();
+          if (lane == 0 && !freerun) mbar_arrive(&r_empty[slot]);
+        }
+        uint32_t acc[EPI_COLS];
+#pragma unroll
+        for (int i = 0; i < EPI_COLS; ++i) acc[i] = 0u;
+        if (!(p.debug & 32768))
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * (uint32_t)(MT * p.NT) +
+                      (uint32_t)(m * p.NT + c0), acc);
+        if (!(p.debug & 65536))
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          const size_t off = off0 + (size_t)j * p.L_out;
           float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[j * 8 + i]);
-          if (bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
-          if (bbias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bbias + c));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bbias + c + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[j * 8 + i]) + bv[j * 8 + i];
           if (p.res16) {
-            float r[8];
-            unpack8(rcur[j], r);
+            float rr[8];
+            unpack8(rcur[j], rr);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += r[i] < 0.f ? r[i] * p.res_inv : r[i];
+            for (int i = 0; i < 8; ++i) v[i] += fminf(rr[i], rr[i] * p.res_inv);   // res_inv >= 1: undo lrelu
           }
-          if (p.res32 && ok && !(p.debug & 2)) {
-            const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.res32) + off * 2);
-            const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.res32) + off * 2 + 1);
-            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+          if (p.res32) {
+            const uint4 q0 = rcur[2 * j], q1 = rcur[2 * j + 1];
+            v[0] += __uint_as_float(q0.x); v[1] += __uint_as_float(q0.y);
+            v[2] += __uint_as_float(q0.z); v[3] += __uint_as_float(q0.w);
+            v[4] += __uint_as_float(q1.x); v[5] += __uint_as_float(q1.y);
+            v[6] += __uint_as_float(q1.z); v[7] += __uint_as_float(q1.w);
           }
           if (p.out_scale != 1.f) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] *= p.out_scale;
           }
-          if (ok && !(p.debug & 2)) {
+          if (ok) {
             if (p.accin16) {
               float o[8];
-              unpack8(*(reinterpret_cast<const uint4*>(p.accin16) + off), o);
+              unpack8(ain[j], o);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] += o[i];
             }
             if (p.accin32) {
-              const float4 o0 = *(reinterpret_cast<const float4*>(p.accin32) + off * 2);
-              const float4 o1 = *(reinterpret_cast<const float4*>(p.accin32) + off * 2 + 1);
-              v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
-              v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+              const uint4 q0 = ain[2 * j], q1 = ain[2 * j + 1];
+              v[0] += __uint_as_float(q0.x); v[1] += __uint_as_float(q0.y);
+              v[2] += __uint_as_float(q0.z); v[3] += __uint_as_float(q0.w);
+              v[4] += __uint_as_float(q1.x); v[5] += __uint_as_float(q1.y);
+              v[6] += __uint_as_float(q1.z); v[7] += __uint_as_float(q1.w);
             }
             if (p.out32) {
               float4* o = reinterpret_cast<float4*>(p.out32) + off * 2;
@@ -380,7 +489,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
             if (p.out16) {
               if (p.out16_slope != 1.f) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.out16_slope;
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * p.out16_slope);   // slope <= 1
               }
               *(reinterpret_cast<uint4*>(p.out16) + off) = pack8(v);
             }
@@ -388,16 +497,20 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         }
       }
       tcgen05_fence_before();
-      mbar_arrive(&acc_empty[accb]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[accb]);
+      if (tid == EPI_WARP0 * 32) trace(p, 3, 2, (int)t_cnt);
     }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (tid == 0) trace(p, 4, 1, 0);
   if (warp == MMA_WARP) tcgen05_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 struct Plan {
   int MT, NT, KC, PG, n_groups, a_slots, a_slot_bytes, stages, stage_bytes, plane_bytes, tmem_cols, resident;
+  int r_slots, r_slot_bytes, res_cols, bias_smem;
   size_t smem;
 };
 
@@ -427,7 +540,8 @@ bool make_plan(const PlaneConvArgs& a, Plan* out) {
   static const int forced_mt = env_int("PG_PLANES_MT", 0), forced_res = env_int("PG_PLANES_RESIDENT", -1),
                    forced_stages = env_int("PG_PLANES_STAGES", 0), forced_slots = env_int("PG_PLANES_SLOTS", 0);
   const bool can_reside = a.N == NT && !a.tapmask && forced_res != 0;
-  const size_t fixed = 1024 + 1024;          // alignment slack + barriers
+  const int bias_smem = a.bias && a.N <= 1024 ? 1 : 0;
+  const size_t fixed = 1024 + 1024 + (bias_smem ? 4 * (size_t)a.N : 0);   // alignment slack, barriers, bias
   const size_t budget = (size_t)227 * 1024;
   const long rows128 = (a.L + BM - 1) / BM;
   const int sms = device_sm_count();
@@ -444,32 +558,42 @@ bool make_plan(const PlaneConvArgs& a, Plan* out) {
       const int plane_bytes = 16 * ((rows + 7) & ~7);
       const int a_slot_bytes = (PG * plane_bytes + 127) & ~127;
       const size_t w_min = resident ? w_all : 2 * (size_t)stage_bytes;
-      if (fixed + 2 * (size_t)a_slot_bytes + w_min > budget) continue;
-      size_t left = budget - fixed - 2 * (size_t)a_slot_bytes - w_min;
+      const bool has_res = a.res16 || a.res32;
+      const int res_cols = NT < 64 ? NT : 64;
+      const int r_slot_bytes = has_res ? BM * (res_cols / 8) * (a.res32 ? 32 : 16) : 0;
+      const int items = MT * (NT / res_cols);   // residual slots per tile
+      int r_slots = has_res ? 2 : 0;
+      if (fixed + 2 * (size_t)a_slot_bytes + w_min + (size_t)r_slots * r_slot_bytes > budget) continue;
+      size_t left = budget - fixed - 2 * (size_t)a_slot_bytes - w_min - (size_t)r_slots * r_slot_bytes;
       int a_slots = 2, stages = resident ? n_chunks * a.K : 2;
-      if (!resident) {
-        const int max_stages = forced_stages > 0 ? forced_stages : 6;
-        while (stages < max_stages && stages < n_chunks * a.K && left >= (size_t)stage_bytes) {
-          ++stages;
-          left -= stage_bytes;
+      const int total_w = n_chunks * a.K;
+      auto grow = [&](int* v, int cap, size_t unit) {
+        while (*v < cap && left >= unit) {
+          ++*v;
+          left -= unit;
         }
-      }
+      };
+      const int max_stages = forced_stages > 0 ? forced_stages : 6;
       const int max_slots = forced_slots > 0 ? forced_slots : 4;
-      while (a_slots < max_slots && left >= (size_t)a_slot_bytes) {
-        ++a_slots;
-        left -= a_slot_bytes;
-      }
+      if (!resident) grow(&stages, std::min(std::min(4, max_stages), total_w), stage_bytes);
+      if (has_res) grow(&r_slots, items + 1, r_slot_bytes);      // one tile of residual slots ahead
+      grow(&a_slots, std::min(3, max_slots), a_slot_bytes);
+      if (!resident) grow(&stages, std::min(max_stages, total_w), stage_bytes);
+      grow(&a_slots, max_slots, a_slot_bytes);
+      if (has_res) grow(&r_slots, 2 * items, r_slot_bytes);
       int tm = 32;
       while (tm < 2 * MT * NT) tm <<= 1;
       *out = Plan{MT, NT, KC, PG, n_groups, a_slots, a_slot_bytes, stages, stage_bytes, plane_bytes, tm,
-                  resident ? 1 : 0, fixed + (size_t)a_slots * a_slot_bytes + (size_t)stages * stage_bytes};
+                  resident ? 1 : 0, r_slots, r_slot_bytes, res_cols, bias_smem,
+                  fixed + (size_t)a_slots * a_slot_bytes + (size_t)stages * stage_bytes +
+                      (size_t)r_slots * r_slot_bytes};
       return true;
     }
   }
   return false;
 }
 
-template <int MT>
+template <int MT, int KC16>
 cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
   CUtensorMap wmap;
   if (!get_weight_map(a.w16, a.Cin, a.N, a.K, pl.KC, pl.NT, &wmap)) return cudaErrorNotSupported;
@@ -487,19 +611,39 @@ cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
   p.plane_bytes = pl.plane_bytes; p.KC = pl.KC; p.PG = pl.PG; p.n_groups = pl.n_groups;
   p.a_slots = pl.a_slots; p.a_slot_bytes = pl.a_slot_bytes; p.stages = pl.stages;
   p.stage_bytes = pl.stage_bytes; p.resident = pl.resident; p.tmem_cols = pl.tmem_cols;
+  p.r_slots = pl.r_slots; p.r_slot_bytes = pl.r_slot_bytes; p.res_cols = pl.res_cols; p.bias_smem = pl.bias_smem;
   p.idesc = make_idesc(BM, pl.NT);
   static const int dbg = env_int("PG_PLANES_DEBUG", 0);
   p.debug = dbg;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_planes_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_planes_kernel<MT, KC16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   int grid = device_sm_count();
   if (grid > p.total_tiles) grid = p.total_tiles;
-  conv_planes_kernel<MT><<<grid, NTHREADS, pl.smem, s>>>(wmap, p);
+  if (p.debug & 8) {
+    unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_ptrace_n, &zero, sizeof(zero));
+  }
+  conv_planes_kernel<MT, KC16><<<grid, NTHREADS, pl.smem, s>>>(wmap, p);
+  if (p.debug & 8) {
+    cudaDeviceSynchronize();
+    static unsigned long long host[4096];
+    unsigned int n = 0;
+    cudaMemcpyFromSymbol(&n, g_ptrace_n, sizeof(n));
+    cudaMemcpyFromSymbol(host, g_ptrace, sizeof(host));
+    if (n > 4096) n = 4096;
+    unsigned long long t0 = ~0ull;
+    for (unsigned i = 0; i < n; ++i) t0 = host[i] >> 20 < t0 ? host[i] >> 20 : t0;
+    fprintf(stderr, "TRACE MT=%d NT=%d resident=%d a_slots=%d stages=%d r_slots=%d grid=%d tiles=%d smem=%zu\n", MT,
+            pl.NT, pl.resident, pl.a_slots, pl.stages, pl.r_slots, grid, p.total_tiles, pl.smem);
+    for (unsigned i = 0; i < n; ++i)
+      fprintf(stderr, "TR %llu role=%llu ev=%llu tile=%llu\n", (host[i] >> 20) - t0, (host[i] >> 16) & 15,
+              (host[i] >> 12) & 15, host[i] & 0xFFF);
+  }
   return cudaGetLastError();
 }
 
@@ -511,8 +655,11 @@ bool plane_conv_supported(const PlaneConvArgs& a) {
   if (!a.x || !a.w16 || (!a.out16 && !a.out32)) return false;
   if (a.Cin % 32 || a.Cin < 32 || a.N % 32) return false;
   if (a.K < 1 || a.K > 32 || a.L <= 0 || a.B <= 0) return false;
-  if (a.row_mul < 1 || a.Cout_real % 8 || a.Cout_real * a.row_mul != a.N) return false;
+  if (a.row_mul < 1 || a.Cout_real % EPI_COLS || (a.Cout_real & (a.Cout_real - 1)) || a.Cout_real * a.row_mul != a.N)
+    return false;
   if (a.in_mask && !a.lens) return false;
+  if ((a.res16 || a.res32) && a.row_mul != 1) return false;
+  if (a.res16 && a.res32) return false;
   Plan pl;
   return make_plan(a, &pl);
 }
@@ -520,10 +667,18 @@ bool plane_conv_supported(const PlaneConvArgs& a) {
 cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s) {
   Plan pl;
   if (!plane_conv_supported(a) || !make_plan(a, &pl)) return cudaErrorInvalidValue;
-  switch (pl.MT) {
-    case 1: return launch_t<1>(a, pl, s);
-    case 2: return launch_t<2>(a, pl, s);
-    case 4: return launch_t<4>(a, pl, s);
+  if (pl.KC == 64) {
+    switch (pl.MT) {
+      case 1: return launch_t<1, 4>(a, pl, s);
+      case 2: return launch_t<2, 4>(a, pl, s);
+      case 4: return launch_t<4, 4>(a, pl, s);
+    }
+  } else {
+    switch (pl.MT) {
+      case 1: return launch_t<1, 2>(a, pl, s);
+      case 2: return launch_t<2, 2>(a, pl, s);
+      case 4: return launch_t<4, 2>(a, pl, s);
+    }
   }
   return cudaErrorInvalidValue;
 }

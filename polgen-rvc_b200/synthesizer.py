@@ -117,6 +117,14 @@ class Engine:
         _lib.check(self.lib.pg_profile_read(self._h, ms, fl, n), "pg_profile_read")
         return {"conv_umma": (ms[0], fl[0], int(n[0])), "conv_simt": (ms[1], fl[1], int(n[1]))}
 
+    def profile_table(self, max_rows: int = 256):
+        """Per-shape rows (cls, Cin, N, K, dil, launches, ms, flops) of the records profile_read() consumed."""
+        buf = (C.c_double * (8 * max_rows))()
+        n = self.lib.pg_profile_table(self._h, buf, max_rows)
+        if n < 0:
+            raise RuntimeError(self.lib.pg_last_error().decode())
+        return [tuple(buf[8 * i + k] for k in range(8)) for i in range(n)]
+
     def infer(self, phone, lengths, pitch, f0, sid, eps_zp=None, eps_src=None, seed: int = 0,
               want_aux: bool = True):
         """Time-major tensors on this engine's GPU.  Returns (wave [B][L], aux [4][B][T][C] | None)."""
