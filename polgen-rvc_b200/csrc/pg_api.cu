@@ -37,6 +37,7 @@ struct DevBuf {
 struct ConvW {
   float* w = nullptr;      // [K][Cin][Cout] f32   (CUDA-core path)
   __half* w16 = nullptr;   // [K][Cout][Cin] f16   (tcgen05 path)
+  __half* w16s = nullptr;  // [2][K][Cout][Cin] f16 hi, lo  (tcgen05 split-precision path, latent layers)
   float* bias = nullptr;   // [Cout]
   uint32_t* tapmask = nullptr;   // per Cout tile, taps with non-zero weights (polyphase upsampler)
   int Cin = 0, Cout = 0, K = 1;
@@ -159,7 +160,7 @@ const HostTensor* find(pg_handle h, const std::string& name, std::initializer_li
 }
 
 // w [K][Cin][Cout] f32 -> device f32 copy + f16 [K][Cout][Cin] copy for the tcgen05 path
-int upload_conv(pg_handle h, const std::vector<float>& w, int K, int Cin, int Cout, ConvW* out) {
+int upload_conv(pg_handle h, const std::vector<float>& w, int K, int Cin, int Cout, ConvW* out, bool split = false) {
   std::vector<__half> w16(w.size());
   for (int k = 0; k < K; ++k)
     for (int ci = 0; ci < Cin; ++ci)
@@ -169,6 +170,18 @@ int upload_conv(pg_handle h, const std::vector<float>& w, int K, int Cin, int Co
   if (rc) return rc;
   rc = upload(h, w16, &out->w16);
   if (rc) return rc;
+  if (split) {
+    std::vector<__half> ws(2 * w.size());
+    for (size_t i = 0; i < w16.size(); ++i) ws[i] = w16[i];
+    for (int k = 0; k < K; ++k)
+      for (int ci = 0; ci < Cin; ++ci)
+        for (int co = 0; co < Cout; ++co) {
+          const size_t d = ((size_t)k * Cout + co) * Cin + ci;
+          ws[w.size() + d] = __float2half_rn(w[((size_t)k * Cin + ci) * Cout + co] - __half2float(w16[d]));
+        }
+    rc = upload(h, ws, &out->w16s);
+    if (rc) return rc;
+  }
   out->Cin = Cin;
   out->Cout = Cout;
   out->K = K;
@@ -178,7 +191,7 @@ int upload_conv(pg_handle h, const std::vector<float>& w, int K, int Cin, int Co
 // Conv1d weight W[Cout][Cin][K] (rows co_begin..co_begin+co_count) ->
 //   w   [K][Cin][co_count] f32,  w16 [K][co_count][Cin] f16,  bias [co_count]
 int pack_conv(pg_handle h, const std::string& wname, const std::string& bname, int Cout, int Cin,
-              int K, int co_begin, int co_count, bool flip_ci, bool flip_co, bool want16, ConvW* out) {
+              int K, int co_begin, int co_count, bool flip_ci, bool flip_co, bool split, ConvW* out) {
   const HostTensor* W = find(h, wname, {Cout, Cin, K});
   if (!W) return PG_ERR_INVALID;
   std::vector<float> w((size_t)K * Cin * co_count);
@@ -190,8 +203,7 @@ int pack_conv(pg_handle h, const std::string& wname, const std::string& bname, i
         w[((size_t)k * Cin + ci) * co_count + co] = W->data[((size_t)src_co * Cin + src_ci) * K + k];
     }
   }
-  (void)want16;
-  int rc = upload_conv(h, w, K, Cin, co_count, out);
+  int rc = upload_conv(h, w, K, Cin, co_count, out, split);
   if (rc) return rc;
   if (!bname.empty()) {
     const HostTensor* Bv = find(h, bname, {Cout});
@@ -282,7 +294,7 @@ struct Plan {
 struct Ws {
   // offsets into the workspace
   size_t lens, pitch, sid, x, y, qkv, att, ffn, stats, m_p, logs_p, z_p, z, fh, fa, facts, fskip,
-      gcond, dcond, source, phase, stage[5], zpl, h16[4];
+      gcond, dcond, source, phase, stage[5], zpl, h16[4], attn;
   size_t stage_elems = 0;
   size_t total = 0;
 };
@@ -324,6 +336,7 @@ Ws plan_ws(const pg_config& c, int B, int T) {
   w.stage_elems = max_elems;
   for (int i = 0; i < 5; ++i) w.stage[i] = p.take(sizeof(float) * max_elems + 4096);
   w.zpl = p.take(sizeof(__half) * BT * C);
+  w.attn = p.take(rel_attention_scratch_bytes(B, T, H));
   for (int i = 0; i < 4; ++i) w.h16[i] = p.take(sizeof(__half) * max_elems + 4096);
   w.total = p.total;
   return w;
@@ -390,8 +403,8 @@ cudaEvent_t take_event(pg_handle h) {
 }
 
 // `latent` marks the TextEncoder / flow GEMMs: their results are returned to the caller (m_p,
-// logs_p, z_p, z) and feed the whole decoder, so unless PG_FLAG_F16_LATENTS is set they stay on
-// the fp32 path (single-pass f16 operands cost ~5 dB of waveform SNR on short clips).
+// logs_p, z_p, z) and feed the whole decoder, so unless PG_FLAG_F16_LATENTS is set they run the
+// tensor cores in split precision (two-term f16 operands, 3 MMAs per product: ~2^-22 relative).
 int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_dt, DType out_dt,
              bool latent = false) {
   a.w = w.w;
@@ -400,8 +413,11 @@ int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_d
   a.Cin = w.Cin;
   a.Cout = w.Cout;
   a.K = w.K;
-  const bool force_simt = (h->cfg.flags & PG_FLAG_FORCE_SIMT) != 0 ||
-                          (latent && !(h->cfg.flags & PG_FLAG_F16_LATENTS));
+  const bool force_simt = (h->cfg.flags & PG_FLAG_FORCE_SIMT) != 0;
+  if (latent && !(h->cfg.flags & PG_FLAG_F16_LATENTS) && w.w16s) {
+    a.split = 1;
+    a.w16s = w.w16s;
+  }
   a.tapmask = w.tapmask;
   const bool umma = !force_simt && w.w16 && umma_conv_supported(a);
   const bool prof = (h->cfg.flags & PG_FLAG_PROFILE) != 0;
@@ -453,8 +469,14 @@ int run_text_encoder(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, con
     // q, k, v 1x1 convs fused into one GEMM (attentions.py:64-66)
     a.x = x; a.x_ld = H; a.y = qkv; a.y_ld = 3 * H;
     PG_TRY(run_conv(h, s, a, L.qkv, DT_F32, DT_F32, true));
-    PG_LAUNCH(h, launch_rel_attention(qkv, L.rel_k, L.rel_v, lens, att, B, T, H, c.n_heads,
-                                      c.attn_window, s));
+    if (h->cfg.flags & PG_FLAG_FORCE_SIMT) {
+      PG_LAUNCH(h, launch_rel_attention(qkv, L.rel_k, L.rel_v, lens, att, B, T, H, c.n_heads,
+                                        c.attn_window, s));
+    } else {
+      PG_LAUNCH(h, launch_rel_attention_mma(qkv, L.rel_k, L.rel_v, lens, att, at<char>(h, w.attn), B, T, H,
+                                            c.n_heads, c.attn_window, s));
+      ++h->launches;   // prep + attention kernels
+    }
     a.x = att; a.x_ld = H; a.y = y; a.y_ld = H;
     PG_TRY(run_conv(h, s, a, L.o, DT_F32, DT_F32, true));
     PG_LAUNCH(h, launch_add_layernorm(x, y, L.g1, L.b1, B * T, H, s));
@@ -885,7 +907,7 @@ int pg_finalize(pg_handle h) {
   const int R = 2 * c.attn_window + 1, D = H / c.n_heads;
   // --- TextEncoder ---
   PG_TRY(pack_conv(h, "enc_p.emb_phone.weight", "enc_p.emb_phone.bias", H, c.input_dim, 1, 0, H,
-                   false, false, false, &h->emb_phone));
+                   false, false, true, &h->emb_phone));
   PG_TRY(upload_named(h, "enc_p.emb_pitch.weight", {256, H}, &h->emb_pitch));
   PG_TRY(upload_named(h, "emb_g.weight", {c.spk_embed_dim, c.gin_channels}, &h->emb_g));
   h->enc.resize(c.n_layers);
@@ -904,10 +926,10 @@ int pg_finalize(pg_handle h) {
           for (int ci = 0; ci < H; ++ci) w[(size_t)ci * 3 * H + q * H + co] = W->data[(size_t)co * H + ci];
         }
       }
-      PG_TRY(upload_conv(h, w, 1, H, 3 * H, &L.qkv));
+      PG_TRY(upload_conv(h, w, 1, H, 3 * H, &L.qkv, true));
       PG_TRY(upload(h, b, &L.qkv.bias));
     }
-    PG_TRY(pack_conv(h, p + "conv_o.weight", p + "conv_o.bias", H, H, 1, 0, H, false, false, false, &L.o));
+    PG_TRY(pack_conv(h, p + "conv_o.weight", p + "conv_o.bias", H, H, 1, 0, H, false, false, true, &L.o));
     PG_TRY(upload_named(h, p + "emb_rel_k", {1, R, D}, &L.rel_k));
     PG_TRY(upload_named(h, p + "emb_rel_v", {1, R, D}, &L.rel_v));
     const std::string n1 = "enc_p.encoder.norm_layers_1." + std::to_string(i) + ".";
@@ -918,12 +940,12 @@ int pg_finalize(pg_handle h) {
     PG_TRY(upload_named(h, n2 + "beta", {H}, &L.b2));
     const std::string f = "enc_p.encoder.ffn_layers." + std::to_string(i) + ".";
     PG_TRY(pack_conv(h, f + "conv_1.weight", f + "conv_1.bias", F, H, c.kernel_size, 0, F, false,
-                     false, false, &L.ffn1));
+                     false, true, &L.ffn1));
     PG_TRY(pack_conv(h, f + "conv_2.weight", f + "conv_2.bias", H, F, c.kernel_size, 0, H, false,
-                     false, false, &L.ffn2));
+                     false, true, &L.ffn2));
   }
   PG_TRY(pack_conv(h, "enc_p.proj.weight", "enc_p.proj.bias", 2 * C, H, 1, 0, 2 * C, false, false,
-                   false, &h->proj));
+                   true, &h->proj));
   // --- flow: reversed iteration applies Flip before each coupling layer, so the
   // layers visited 1st, 3rd, ... (f = n-1, n-3, ...) see channel-reversed data.
   const int half = C / 2, nl = c.flow_wn_layers;
@@ -932,10 +954,10 @@ int pg_finalize(pg_handle h) {
     FlowW& Fw = h->flows[f];
     Fw.flipped = ((c.flow_n_flows - 1 - f) % 2) == 0;
     const std::string p = "flow.flows." + std::to_string(2 * f) + ".";
-    PG_TRY(pack_conv(h, p + "pre.weight", p + "pre.bias", H, half, 1, 0, H, Fw.flipped, false, false,
+    PG_TRY(pack_conv(h, p + "pre.weight", p + "pre.bias", H, half, 1, 0, H, Fw.flipped, false, true,
                      &Fw.pre));
     PG_TRY(pack_conv(h, p + "post.weight", p + "post.bias", half, H, 1, 0, half, false, Fw.flipped,
-                     false, &Fw.post));
+                     true, &Fw.post));
     PG_TRY(upload_named(h, p + "enc.cond_layer.weight", {2 * H * nl, c.gin_channels, 1}, &Fw.cond_w));
     PG_TRY(upload_named(h, p + "enc.cond_layer.bias", {2 * H * nl}, &Fw.cond_b));
     Fw.in_layers.resize(nl);
@@ -944,13 +966,13 @@ int pg_finalize(pg_handle h) {
     for (int l = 0; l < nl; ++l) {
       const std::string q = p + "enc.in_layers." + std::to_string(l) + ".";
       PG_TRY(pack_conv(h, q + "weight", q + "bias", 2 * H, H, c.flow_wn_kernel, 0, 2 * H, false, false,
-                       false, &Fw.in_layers[l]));
+                       true, &Fw.in_layers[l]));
       const std::string r = p + "enc.res_skip_layers." + std::to_string(l) + ".";
       if (l < nl - 1) {
-        PG_TRY(pack_conv(h, r + "weight", r + "bias", 2 * H, H, 1, 0, H, false, false, false, &Fw.res[l]));
-        PG_TRY(pack_conv(h, r + "weight", r + "bias", 2 * H, H, 1, H, H, false, false, false, &Fw.skip[l]));
+        PG_TRY(pack_conv(h, r + "weight", r + "bias", 2 * H, H, 1, 0, H, false, false, true, &Fw.res[l]));
+        PG_TRY(pack_conv(h, r + "weight", r + "bias", 2 * H, H, 1, H, H, false, false, true, &Fw.skip[l]));
       } else {
-        PG_TRY(pack_conv(h, r + "weight", r + "bias", H, H, 1, 0, H, false, false, false, &Fw.skip[l]));
+        PG_TRY(pack_conv(h, r + "weight", r + "bias", H, H, 1, 0, H, false, false, true, &Fw.skip[l]));
       }
     }
   }
@@ -1001,10 +1023,10 @@ int pg_finalize(pg_handle h) {
         const int ksz = c.resblock_kernel_sizes[j];
         PG_TRY(pack_conv(h, rb + "convs1." + std::to_string(d) + ".weight",
                          rb + "convs1." + std::to_string(d) + ".bias", cout, cout, ksz, 0, cout, false,
-                         false, true, &S.c1[j * nd + d]));
+                         false, false, &S.c1[j * nd + d]));
         PG_TRY(pack_conv(h, rb + "convs2." + std::to_string(d) + ".weight",
                          rb + "convs2." + std::to_string(d) + ".bias", cout, cout, ksz, 0, cout, false,
-                         false, true, &S.c2[j * nd + d]));
+                         false, false, &S.c2[j * nd + d]));
       }
     cin = cout;
   }

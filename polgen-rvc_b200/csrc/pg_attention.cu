@@ -1,0 +1,355 @@
+// Windowed relative-position multi-head attention of the TextEncoder on tensor cores
+// (reference rvc/lib/algorithm/attentions.py:63-113, helpers :115-158):
+//   scores[i,j] = q_i.k_j/sqrt(d) + [|j-i|<=w] q_i.Ek[j-i+w]/sqrt(d)
+//   masked_fill(mask_i*mask_j == 0, -1e4); softmax_j
+//   out_i = sum_j p_ij v_j + sum_{|j-i|<=w} p_ij Ev[j-i+w]
+// 1.5 % of the path's FLOPs, but O(T^2): flash-style, 64 queries x 64 keys per step with online
+// softmax, both GEMMs on mma.sync m16n8k16 (f16 operands, fp32 accumulate).  The latents this
+// feeds are returned to the caller and drive the whole decoder, so every operand is split into
+// two f16 terms (x = hi + lo) and each product is evaluated as hi*hi + hi*lo + lo*hi: ~2^-22
+// relative error, i.e. fp32-class results at tensor-core speed.
+// The relative-position terms are tiny (21 taps) and stay on CUDA cores in fp32.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "pg_common.cuh"
+
+namespace pg {
+
+namespace {
+
+constexpr int AQ = 64, AK = 64, AD = 96;   // queries / keys per step, head dim
+constexpr int KP = 104;                    // K tile row pitch (halves): conflict-free B-fragment loads
+constexpr int VP = 72;                     // V^T tile row pitch (halves)
+constexpr int RP = 24;                     // rel-pos table pitch (floats), 2*window+1 <= RP
+constexpr int ATT_THREADS = 128;
+
+__device__ __forceinline__ void split_f16(float x, __half* hi, __half* lo) {
+  const __half h = __float2half_rn(x);
+  *hi = h;
+  *lo = __float2half_rn(x - __half2float(h));
+}
+
+// qkv [B][T][3H] f32 -> Q (pre-scaled), K as [B][heads][Tp][96] hi/lo and V^T as [B][heads][96][Tp]
+// hi/lo; rows >= T are zero.
+__global__ void attn_prep_kernel(const float* __restrict__ qkv, __half* __restrict__ qh, __half* __restrict__ ql,
+                                 __half* __restrict__ kh, __half* __restrict__ kl, __half* __restrict__ vth,
+                                 __half* __restrict__ vtl, int B, int T, int Tp, int H, int heads, float qscale) {
+  const size_t total = (size_t)B * heads * Tp * AD;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % AD);
+  const size_t r = i / AD;
+  const int j = (int)(r % Tp);
+  const size_t bh = r / Tp;
+  const int h = (int)(bh % heads), b = (int)(bh / heads);
+  float q = 0.f, k = 0.f, v = 0.f;
+  if (j < T) {
+    const float* row = qkv + ((size_t)b * T + j) * 3 * H + h * AD + c;
+    q = row[0] * qscale;
+    k = row[H];
+    v = row[2 * H];
+  }
+  split_f16(q, qh + i, ql + i);
+  split_f16(k, kh + i, kl + i);
+  const size_t vt = (bh * AD + c) * Tp + j;
+  split_f16(v, vth + vt, vtl + vt);
+}
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  const __half2 h = __halves2half2(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+struct AttnSmem {
+  __half k[2][2][AK][KP];    // [buffer][hi/lo][key][dim]
+  __half v[2][2][AD][VP];    // [buffer][hi/lo][dim][key]
+  float rl[AQ][RP];          // rel-key logits q_i . Ek[r]
+  float sb[AQ][RP];          // band scores (raw, masked) for the rel-value term
+  float ev[RP][AD];          // rel-value table
+  float m[AQ], inv_l[AQ];
+};
+
+__global__ void __launch_bounds__(ATT_THREADS) rel_attention_mma_kernel(
+    const __half* __restrict__ qh, const __half* __restrict__ ql, const __half* __restrict__ kh,
+    const __half* __restrict__ kl, const __half* __restrict__ vth, const __half* __restrict__ vtl,
+    const float* __restrict__ qkv, const float* __restrict__ rel_k, const float* __restrict__ rel_v,
+    const int* __restrict__ lens, float* __restrict__ out, int T, int Tp, int H, int heads, int window,
+    float qscale) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  AttnSmem& sm = *reinterpret_cast<AttnSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
+  const int len = lens[b];
+  const int R = 2 * window + 1;
+  const size_t bh = (size_t)b * heads + h;
+  const __half* kh_b = kh + bh * Tp * AD;
+  const __half* kl_b = kl + bh * Tp * AD;
+  const __half* vth_b = vth + bh * AD * Tp;
+  const __half* vtl_b = vtl + bh * AD * Tp;
+
+  auto load_block = [&](int kb, int buf) {
+    const int k0 = kb * AK;
+    // K: 64 rows x 12 chunks of 16 B, hi and lo
+    for (int i = tid; i < AK * 12; i += ATT_THREADS) {
+      const int r = i / 12, ch = i - r * 12;
+      cp_async16(&sm.k[buf][0][r][ch * 8], kh_b + (size_t)(k0 + r) * AD + ch * 8);
+      cp_async16(&sm.k[buf][1][r][ch * 8], kl_b + (size_t)(k0 + r) * AD + ch * 8);
+    }
+    // V^T: 96 rows x 8 chunks
+    for (int i = tid; i < AD * 8; i += ATT_THREADS) {
+      const int r = i >> 3, ch = i & 7;
+      cp_async16(&sm.v[buf][0][r][ch * 8], vth_b + (size_t)r * Tp + k0 + ch * 8);
+      cp_async16(&sm.v[buf][1][r][ch * 8], vtl_b + (size_t)r * Tp + k0 + ch * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int nblk = Tp / AK;
+  load_block(0, 0);
+
+  // ---- prologue: rel tables, rel-key logits (fp32), Q fragments
+  for (int i = tid; i < RP * AD; i += ATT_THREADS) {
+    const int r = i / AD;
+    sm.ev[r][i - r * AD] = r < R ? rel_v[i] : 0.f;
+  }
+  for (int i = tid; i < AQ * RP; i += ATT_THREADS) {
+    const int il = i / RP, r = i - il * RP;
+    sm.sb[il][r] = -INFINITY;
+    float s = 0.f;
+    const int qi = q0 + il;
+    if (r < R && qi < T) {
+      const float* qrow = qkv + ((size_t)b * T + qi) * 3 * H + h * AD;
+      const float* ek = rel_k + (size_t)r * AD;
+      for (int c = 0; c < AD; ++c) s = fmaf(qrow[c] * qscale, ek[c], s);
+    }
+    sm.rl[il][r] = s;
+  }
+  const int r0 = q0 + warp * 16;            // this warp's 16 query rows
+  const int i0 = r0 + g, i1 = r0 + g + 8;   // this lane's two rows
+  uint32_t aqh[6][4], aql[6][4];
+  {
+    const __half* qh_b = qh + bh * Tp * AD;
+    const __half* ql_b = ql + bh * Tp * AD;
+#pragma unroll
+    for (int ks = 0; ks < 6; ++ks) {
+      const int c = ks * 16 + 2 * t;
+      aqh[ks][0] = *reinterpret_cast<const uint32_t*>(qh_b + (size_t)i0 * AD + c);
+      aqh[ks][1] = *reinterpret_cast<const uint32_t*>(qh_b + (size_t)i1 * AD + c);
+      aqh[ks][2] = *reinterpret_cast<const uint32_t*>(qh_b + (size_t)i0 * AD + c + 8);
+      aqh[ks][3] = *reinterpret_cast<const uint32_t*>(qh_b + (size_t)i1 * AD + c + 8);
+      aql[ks][0] = *reinterpret_cast<const uint32_t*>(ql_b + (size_t)i0 * AD + c);
+      aql[ks][1] = *reinterpret_cast<const uint32_t*>(ql_b + (size_t)i1 * AD + c);
+      aql[ks][2] = *reinterpret_cast<const uint32_t*>(ql_b + (size_t)i0 * AD + c + 8);
+      aql[ks][3] = *reinterpret_cast<const uint32_t*>(ql_b + (size_t)i1 * AD + c + 8);
+    }
+  }
+  float o[12][4];
+#pragma unroll
+  for (int n = 0; n < 12; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[n][e] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int buf = kb & 1, k0 = kb * AK;
+    if (kb + 1 < nblk) {
+      load_block(kb + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---- S = Q K^T (3-term split)
+    float s[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[n][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 6; ++ks) {
+      // independent accumulators back to back: the three split terms of one tile are issued
+      // 8 MMAs apart so no MMA waits on its predecessor
+      uint32_t bh0[8], bh1[8], bl0[8], bl1[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const __half* kr_h = &sm.k[buf][0][n * 8 + g][ks * 16 + 2 * t];
+        const __half* kr_l = &sm.k[buf][1][n * 8 + g][ks * 16 + 2 * t];
+        bh0[n] = *reinterpret_cast<const uint32_t*>(kr_h);
+        bh1[n] = *reinterpret_cast<const uint32_t*>(kr_h + 8);
+        bl0[n] = *reinterpret_cast<const uint32_t*>(kr_l);
+        bl1[n] = *reinterpret_cast<const uint32_t*>(kr_l + 8);
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) mma16816(s[n], aqh[ks], bh0[n], bh1[n]);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) mma16816(s[n], aqh[ks], bl0[n], bl1[n]);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) mma16816(s[n], aql[ks], bh0[n], bh1[n]);
+    }
+    // ---- rel-key logits on the band, masks
+    const bool band = (k0 < q0 + AQ + window) && (k0 + AK > q0 - window);
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = k0 + n * 8 + 2 * t + (e & 1);
+        const int i = e < 2 ? i0 : i1;
+        float v = s[n][e];
+        const int rel = j - i + window;
+        const bool inband = band && rel >= 0 && rel < R;
+        if (inband) v += sm.rl[i - q0][rel];
+        if (!(i < len && j < len)) v = -1e4f;
+        if (j >= T) v = -INFINITY;
+        if (inband && j < T) sm.sb[i - q0][rel] = v;
+        s[n][e] = v;
+        if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float al0 = __expf(m0 - mn0), al1 = __expf(m1 - mn1);
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      s[n][0] = __expf(s[n][0] - mn0);
+      s[n][1] = __expf(s[n][1] - mn0);
+      s[n][2] = __expf(s[n][2] - mn1);
+      s[n][3] = __expf(s[n][3] - mn1);
+      rs0 += s[n][0] + s[n][1];
+      rs1 += s[n][2] + s[n][3];
+    }
+    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1);
+    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1);
+    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+    l0 = l0 * al0 + rs0;
+    l1 = l1 * al1 + rs1;
+    m0 = mn0;
+    m1 = mn1;
+#pragma unroll
+    for (int n = 0; n < 12; ++n) {
+      o[n][0] *= al0; o[n][1] *= al0;
+      o[n][2] *= al1; o[n][3] *= al1;
+    }
+    // ---- O += P V (3-term split; P fragments come straight from the S accumulators)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int n = 2 * kk + half;
+        __half h0, h1, h2, h3, e0, e1, e2, e3;
+        split_f16(s[n][0], &h0, &e0);
+        split_f16(s[n][1], &h1, &e1);
+        split_f16(s[n][2], &h2, &e2);
+        split_f16(s[n][3], &h3, &e3);
+        ph[2 * half] = pack_h2(h0, h1);
+        ph[2 * half + 1] = pack_h2(h2, h3);
+        pl[2 * half] = pack_h2(e0, e1);
+        pl[2 * half + 1] = pack_h2(e2, e3);
+      }
+#pragma unroll
+      for (int n6 = 0; n6 < 12; n6 += 6) {
+        uint32_t bh0[6], bh1[6], bl0[6], bl1[6];
+#pragma unroll
+        for (int n = 0; n < 6; ++n) {
+          const __half* vr_h = &sm.v[buf][0][(n6 + n) * 8 + g][kk * 16 + 2 * t];
+          const __half* vr_l = &sm.v[buf][1][(n6 + n) * 8 + g][kk * 16 + 2 * t];
+          bh0[n] = *reinterpret_cast<const uint32_t*>(vr_h);
+          bh1[n] = *reinterpret_cast<const uint32_t*>(vr_h + 8);
+          bl0[n] = *reinterpret_cast<const uint32_t*>(vr_l);
+          bl1[n] = *reinterpret_cast<const uint32_t*>(vr_l + 8);
+        }
+#pragma unroll
+        for (int n = 0; n < 6; ++n) mma16816(o[n6 + n], ph, bh0[n], bh1[n]);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) mma16816(o[n6 + n], ph, bl0[n], bl1[n]);
+#pragma unroll
+        for (int n = 0; n < 6; ++n) mma16816(o[n6 + n], pl, bh0[n], bh1[n]);
+      }
+    }
+    __syncthreads();   // this buffer is refilled by the next iteration's prefetch
+  }
+
+  // ---- epilogue: normalise, add the rel-value term
+  if (t == 0) {
+    sm.m[i0 - q0] = m0;
+    sm.inv_l[i0 - q0] = 1.f / l0;
+    sm.m[i1 - q0] = m1;
+    sm.inv_l[i1 - q0] = 1.f / l1;
+  }
+  __syncthreads();
+  for (int i = tid; i < AQ * RP; i += ATT_THREADS) {
+    const int il = i / RP, r = i - il * RP;
+    sm.sb[il][r] = r < R ? __expf(sm.sb[il][r] - sm.m[il]) * sm.inv_l[il] : 0.f;   // band probabilities
+  }
+  __syncthreads();
+  const float il0 = sm.inv_l[i0 - q0], il1 = sm.inv_l[i1 - q0];
+#pragma unroll
+  for (int n = 0; n < 12; ++n) {
+    const int c = n * 8 + 2 * t;
+    float v00 = o[n][0] * il0, v01 = o[n][1] * il0, v10 = o[n][2] * il1, v11 = o[n][3] * il1;
+    for (int r = 0; r < R; ++r) {
+      const float p0 = sm.sb[i0 - q0][r], p1 = sm.sb[i1 - q0][r];
+      const float e0 = sm.ev[r][c], e1 = sm.ev[r][c + 1];
+      v00 = fmaf(p0, e0, v00);
+      v01 = fmaf(p0, e1, v01);
+      v10 = fmaf(p1, e0, v10);
+      v11 = fmaf(p1, e1, v11);
+    }
+    if (i0 < T) *reinterpret_cast<float2*>(out + ((size_t)b * T + i0) * H + h * AD + c) = make_float2(v00, v01);
+    if (i1 < T) *reinterpret_cast<float2*>(out + ((size_t)b * T + i1) * H + h * AD + c) = make_float2(v10, v11);
+  }
+}
+
+}  // namespace
+
+size_t rel_attention_scratch_bytes(int B, int T, int H) {
+  const int Tp = (T + AK - 1) / AK * AK;
+  return (size_t)6 * B * H * Tp * sizeof(__half) + 256;
+}
+
+cudaError_t launch_rel_attention_mma(const float* qkv, const float* rel_k, const float* rel_v, const int* lens,
+                                     float* out, void* scratch, int B, int T, int H, int n_heads, int window,
+                                     cudaStream_t s) {
+  if (H / n_heads != AD || H % n_heads || 2 * window + 1 > RP) return cudaErrorInvalidValue;
+  const int Tp = (T + AK - 1) / AK * AK;
+  const size_t n = (size_t)B * H * Tp;
+  __half* base = reinterpret_cast<__half*>(scratch);
+  __half *qh = base, *ql = base + n, *kh = base + 2 * n, *kl = base + 3 * n, *vth = base + 4 * n, *vtl = base + 5 * n;
+  const float qscale = rsqrtf((float)AD);
+  attn_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(qkv, qh, ql, kh, kl, vth, vtl, B, T, Tp, H, n_heads,
+                                                                qscale);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(rel_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(AttnSmem));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(Tp / AQ, n_heads, B);
+  rel_attention_mma_kernel<<<grid, ATT_THREADS, sizeof(AttnSmem), s>>>(qh, ql, kh, kl, vth, vtl, qkv, rel_k, rel_v,
+                                                                       lens, out, T, Tp, H, n_heads, window, qscale);
+  return cudaGetLastError();
+}
+
+}  // namespace pg

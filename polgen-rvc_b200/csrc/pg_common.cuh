@@ -32,6 +32,8 @@ struct ConvArgs {
   int Cin = 0, Cout = 0, K = 1, dil = 1, pad = 0;
   const float* w = nullptr;          // SIMT: [K][Cin][Cout] f32
   const void* w16 = nullptr;         // UMMA: [K][Cout][Cin] f16 (K-major tiles)
+  const void* w16s = nullptr;        // UMMA split mode: [2][K][Cout][Cin] f16, hi then lo (w = hi + lo)
+  int split = 0;                     // two-term f16 operands, 3 MMAs per product (fp32-class accuracy)
   const float* bias = nullptr;       // [Cout]
   const float* bbias = nullptr; int bbias_ld = 0;   // [B][bbias_ld]
   float in_slope = 1.f; int in_mask = 0;
@@ -112,6 +114,12 @@ cudaError_t launch_add_layernorm(float* x, const float* y, const float* gamma, c
 cudaError_t launch_rel_attention(const float* qkv, const float* rel_k, const float* rel_v,
                                  const int* lens, float* out, int B, int T, int H, int n_heads,
                                  int window, cudaStream_t s);
+// same on tensor cores (pg_attention.cu): mma.sync f16 with two-term operand splitting (fp32-class
+// accuracy); scratch holds the split Q/K/V^T copies (rel_attention_scratch_bytes)
+size_t rel_attention_scratch_bytes(int B, int T, int H);
+cudaError_t launch_rel_attention_mma(const float* qkv, const float* rel_k, const float* rel_v,
+                                     const int* lens, float* out, void* scratch, int B, int T, int H,
+                                     int n_heads, int window, cudaStream_t s);
 // z_p = (m + exp(logs) * eps * 0.66666) * mask ; stats [B][T][2C] -> m, logs, z_p, z(copy)
 cudaError_t launch_reparam(const float* stats, const float* eps, uint64_t seed, const int* lens,
                            float* m_p, float* logs_p, float* z_p, float* z, int B, int T, int C,

@@ -67,6 +67,9 @@ struct UmmaParams {
   int a_slots, a_slot_bytes;    // activation ring
   int stages, stage_bytes;      // weight ring (or, when resident, all K*chunks tiles of the layer)
   int resident;                 // 1: weights loaded once per CTA, no ring
+  int split;                    // 1: two-term f16 operands (x = hi + lo), 3 MMAs per product: fp32-class accuracy
+  int lo_off;                   // byte offset of the lo planes inside an activation slot
+  int w_lo_rows;                // row offset (K*Cout) of the lo weight copy in the tensor map
   int rotate;                   // ring mode: per-row-tile rotation of the (chunk, tap) walk
   int tmem_cols;
   uint32_t idesc;
@@ -201,10 +204,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
       if (elect_one()) {
         trace(p, 0, 0, 0);
         mbar_expect_tx(w_ready, (uint32_t)(n_chunks * p.K * p.stage_bytes));
+        const int tile_b = p.split ? p.stage_bytes / 2 : p.stage_bytes;
         for (int chunk = 0; chunk < n_chunks; ++chunk)
-          for (int tap = 0; tap < p.K; ++tap)
-            tma_load_2d(w_ring + (size_t)(chunk * p.K + tap) * p.stage_bytes, &wmap, w_ready, chunk * p.KC,
-                        tap * p.Cout);
+          for (int tap = 0; tap < p.K; ++tap) {
+            uint8_t* dstw = w_ring + (size_t)(chunk * p.K + tap) * p.stage_bytes;
+            tma_load_2d(dstw, &wmap, w_ready, chunk * p.KC, tap * p.Cout);
+            if (p.split) tma_load_2d(dstw + tile_b, &wmap, w_ready, chunk * p.KC, p.w_lo_rows + tap * p.Cout);
+          }
       }
       __syncwarp();
     } else {
@@ -229,6 +235,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
               mbar_expect_tx(&full[stage], (uint32_t)p.stage_bytes);
               tma_load_2d(w_ring + (size_t)stage * p.stage_bytes, &wmap, &full[stage], chunk * p.KC,
                           tap * p.Cout + tc.ntile * p.NT);
+              if (p.split)
+                tma_load_2d(w_ring + (size_t)stage * p.stage_bytes + p.stage_bytes / 2, &wmap, &full[stage],
+                            chunk * p.KC, p.w_lo_rows + tap * p.Cout + tc.ntile * p.NT);
             }
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -294,6 +303,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
                 for (int m = 0; m < MT; ++m) {
                   const uint64_t adesc = adesc0 | (uint64_t)(a_k + (uint32_t)m * (BM * 16 / 16));
                   umma_f16(d_base + (uint32_t)m * nt, adesc, bdesc, idesc, started | (uint32_t)k16);
+                  if (p.split) {   // + lo(A)*hi(B) + hi(A)*lo(B)
+                    const uint64_t adesc_lo = adesc0 | (uint64_t)(a_k + (uint32_t)m * (BM * 16 / 16) + ((uint32_t)p.lo_off >> 4));
+                    const uint64_t bdesc_lo = bdesc0 | (uint64_t)(w_units + 2u * k16 + ((uint32_t)p.stage_bytes >> 5));
+                    umma_f16(d_base + (uint32_t)m * nt, adesc_lo, bdesc, idesc, 1u);
+                    umma_f16(d_base + (uint32_t)m * nt, adesc, bdesc_lo, idesc, 1u);
+                  }
                 }
               }
             }
@@ -369,6 +384,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
             *reinterpret_cast<uint4*>(dst + (size_t)pp[u] * p.plane_bytes + (size_t)rr[u] * 16) = q;
+            if (p.split) {
+              uint4 ql;
+              __half2* hl = reinterpret_cast<__half2*>(&ql);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 back = __half22float2(h[i]);
+                hl[i] = __floats2half2_rn(f[2 * i] - back.x, f[2 * i + 1] - back.y);
+              }
+              *reinterpret_cast<uint4*>(dst + p.lo_off + (size_t)pp[u] * p.plane_bytes + (size_t)rr[u] * 16) = ql;
+            }
           }
         }
         fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -624,6 +649,7 @@ struct Plan {
   int MT, NT, KC, PG, n_groups, a_slots, a_slot_bytes, stages, stage_bytes, plane_bytes, tmem_cols;
   int ctas_per_sm, resident;
   size_t smem;
+  int lo_off;
 };
 
 int env_int(const char* name) {
@@ -644,16 +670,27 @@ int num_sms() {
 // Choose row-tile multiplicity, ring depths and CTAs per SM.  Narrow layers (little MMA work per
 // tile) want several resident CTAs to hide the staging / epilogue latency; wide layers want deep
 // rings in one CTA.  TMEM holds two accumulator sets per CTA (epilogue / MMA overlap).
+bool make_plan_nt(const ConvArgs& a, int NT, Plan* out);
+
+// Split precision doubles every operand tile: walk down the Cout tile sizes until the rings fit.
 bool make_plan(const ConvArgs& a, Plan* out) {
-  const int NT = pick_nt(a.Cout);
-  if (!NT) return false;
+  if (!a.split) {
+    const int NT = pick_nt(a.Cout);
+    return NT && make_plan_nt(a, NT, out);
+  }
+  for (int nt : {128, 96, 64, 32})
+    if (a.Cout % nt == 0 && make_plan_nt(a, nt, out)) return true;
+  return false;
+}
+
+bool make_plan_nt(const ConvArgs& a, int NT, Plan* out) {
   const int KC = a.Cin % 64 == 0 ? 64 : 32;
   const int planes = a.Cin / 8;
   int PG = planes < GROUP_PLANES ? planes : GROUP_PLANES;
   if ((PG * 8) % KC) PG = planes;   // e.g. Cin = 96 with 32-channel chunks: one group
   if ((PG * 8) % KC) return false;
   const int n_groups = (planes + PG - 1) / PG;
-  const int stage_bytes = NT * KC * 2;
+  const int stage_bytes = NT * KC * 2 * (a.split ? 2 : 1);
   static const int forced_mt = env_int("PG_UMMA_MT"), no_resident = env_int("PG_UMMA_NORESIDENT");
   const size_t fixed = 1024 + 1024 + EPI_WARPS * 32 * 80 + 256;   // align slack, barriers, epilogue staging
   const size_t budget = (size_t)226 * 1024;
@@ -666,7 +703,7 @@ bool make_plan(const ConvArgs& a, Plan* out) {
     const int rows_alloc = (rows + 7) & ~7;
     const int row_pad = PG >= 8 ? 1 : (PG == 4 ? 2 : 1);   // keep plane pitches on distinct banks
     *plane_bytes = 16 * (rows_alloc + row_pad);
-    *a_slot_bytes = (PG * *plane_bytes + 127) & ~127;
+    *a_slot_bytes = ((PG * *plane_bytes + 127) & ~127) * (a.split ? 2 : 1);
   };
   // Candidate row-tile multiplicities, largest first: more rows per tile amortise the barrier
   // round trips and (ring mode) the weight stream from L2.  Two accumulator sets must fit TMEM.
@@ -682,10 +719,11 @@ bool make_plan(const ConvArgs& a, Plan* out) {
       geometry(MT, &plane_bytes, &a_slot_bytes);
       int tm = 32;
       while (tm < 2 * MT * NT) tm <<= 1;
-      const size_t w_bytes = resident ? w_all : 3 * (size_t)stage_bytes;
+      const int min_stages = a.split ? 2 : 3;
+      const size_t w_bytes = resident ? w_all : min_stages * (size_t)stage_bytes;
       if (fixed + 2 * (size_t)a_slot_bytes + w_bytes > budget) continue;
       size_t left = budget - fixed - 2 * (size_t)a_slot_bytes - w_bytes;
-      int a_slots = 2, stages = resident ? n_chunks * a.K : 3;
+      int a_slots = 2, stages = resident ? n_chunks * a.K : min_stages;
       if (!resident && env_int("PG_UMMA_STAGES") == 2) { stages = 2; left += stage_bytes; }
       static const int forced_stages = env_int("PG_UMMA_STAGES");
       const int max_stages = forced_stages > 0 ? forced_stages : 8;
@@ -701,7 +739,8 @@ bool make_plan(const ConvArgs& a, Plan* out) {
       }
       *out = Plan{MT, NT, KC, PG, n_groups, a_slots, a_slot_bytes, stages, stage_bytes, plane_bytes, tm, 1,
                   resident ? 1 : 0,
-                  fixed + (size_t)a_slots * a_slot_bytes + (size_t)stages * stage_bytes};
+                  fixed + (size_t)a_slots * a_slot_bytes + (size_t)stages * stage_bytes,
+                  a.split ? a_slot_bytes / 2 : 0};
       return true;
     }
   }
@@ -711,8 +750,10 @@ bool make_plan(const ConvArgs& a, Plan* out) {
 template <int MT, typename TIn, typename TOut>
 cudaError_t launch_t(const ConvArgs& a, const Plan& pl, cudaStream_t s) {
   CUtensorMap wmap;
-  if (!get_wmap(a.w16, a.Cin, a.Cout, a.K, pl.KC, pl.NT, &wmap)) return cudaErrorNotSupported;
+  if (!get_wmap(a.split ? a.w16s : a.w16, a.Cin, a.Cout, a.split ? 2 * a.K : a.K, pl.KC, pl.NT, &wmap))
+    return cudaErrorNotSupported;
   UmmaParams p;
+  p.split = a.split; p.lo_off = pl.lo_off; p.w_lo_rows = a.K * a.Cout;
   p.x = a.x; p.x_ld = a.x_ld; p.x_coff = a.x_coff;
   p.res = a.res; p.res_ld = a.res_ld; p.res_coff = a.res_coff; p.res_scale = a.res_scale;
   p.y = a.y; p.y_ld = a.y_ld; p.y_coff = a.y_coff;
@@ -787,6 +828,7 @@ int umma_pick_nt(int cout) { return pick_nt(cout); }
 
 bool umma_conv_supported(const ConvArgs& a) {
   if (!a.w16) return false;
+  if (a.split && (!a.w16s || a.tapmask)) return false;
   if (a.Cin % 32 || a.Cin < 32) return false;
   if (a.x_ld % 8 || a.x_coff % 8 || a.y_ld % 8 || a.y_coff % 8) return false;
   if (a.res && (a.res_ld % 8 || a.res_coff % 8)) return false;
