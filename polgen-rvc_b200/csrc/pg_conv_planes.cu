@@ -74,8 +74,8 @@ struct PlaneParams {
 // PG_PLANES_DEBUG & 8: CTA 0 records (role, event, tile, globaltimer) -- timing experiments only
 __device__ unsigned long long g_ptrace[4096];
 __device__ unsigned int g_ptrace_n;
-__device__ __forceinline__ void trace(const PlaneParams& p, int role, int ev, int tile) {
-  if ((p.debug & 8) && blockIdx.x == 0) {
+__device__ __forceinline__ void trace(int dbg, int role, int ev, int tile) {
+  if ((dbg & 8) && blockIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     const unsigned int i = atomicAdd(&g_ptrace_n, 1u);
@@ -110,9 +110,10 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   return q;
 }
 
-template <int MT, int KC16>
+template <int MT, int KC16, bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p) {
+  const int dbg = DBG ? p.debug : 0;   // production instantiation: every debug switch folds away
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_ring = smem;
@@ -162,14 +163,14 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (tid == 0) trace(p, 4, 0, 0);
+  if (tid == 0) trace(dbg, 4, 0, 0);
 
   const int chunks_per_group = p.PG * 8 / p.KC;
   const int n_chunks = p.Cin / p.KC;
   const int planes_total = p.Cin / 8;
 
-  const bool freerun = (p.debug & 16) != 0;
-  if (warp == LOAD_WARP && !(p.debug & 64)) {
+  const bool freerun = (dbg & 16) != 0;
+  if (warp == LOAD_WARP && !(dbg & 64)) {
     // ===== A loader: one bulk copy per plane of the (tile, group) window =====
     const int rows = BM * MT + (p.K - 1) * p.dil;
     uint32_t a_cnt = 0;
@@ -185,7 +186,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       for (int g = 0; g < p.n_groups; ++g, ++a_cnt) {
         const uint32_t slot = a_cnt % (uint32_t)p.a_slots;
         mbar_wait(&a_empty[slot], ((a_cnt / (uint32_t)p.a_slots) & 1u) ^ 1u);
-        if (lane == 0) trace(p, 0, 1, (int)a_cnt);
+        if (lane == 0) trace(dbg, 0, 1, (int)a_cnt);
         uint8_t* dst = a_ring + (size_t)slot * p.a_slot_bytes;
         const int pl0 = g * p.PG;
         const int npl = min(p.PG, planes_total - pl0);
@@ -198,7 +199,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
           fence_proxy_async_smem();   // generic-proxy zeros -> visible to the tensor core
         }
         __syncwarp();
-        const uint32_t bytes = (p.debug & 1) ? 0u : (uint32_t)(hi - lo) * 16u;
+        const uint32_t bytes = (dbg & 1) ? 0u : (uint32_t)(hi - lo) * 16u;
         if (lane == 0) mbar_expect_tx(&a_full[slot], bytes * (uint32_t)npl);
         __syncwarp();
         if (bytes && lane < npl)
@@ -206,7 +207,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
                    xb + ((size_t)(pl0 + lane) * p.L + (tstart + lo)) * 8, bytes, &a_full[slot]);
       }
     }
-  } else if (warp == TMA_WARP && !(p.debug & 64)) {
+  } else if (warp == TMA_WARP && !(dbg & 64)) {
     // ===== weight producer: (tile, group, chunk, tap) order =====
     if (p.resident) {
       if (elect_one()) {
@@ -238,7 +239,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         }
       }
     }
-  } else if (warp == MMA_WARP && !(p.debug & 128)) {
+  } else if (warp == MMA_WARP && !(dbg & 128)) {
     // ===== MMA issuer: ONE elected lane runs the whole role (waits, issues, commits); inside the
     // single-lane region the compiler moves operands to uniform registers without waterfall loops =====
     if (elect_one()) {
@@ -252,7 +253,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
     const uint32_t plane2 = 2u * plane_units;
     const int kc8 = p.KC / 8;
     const uint32_t nt = (uint32_t)p.NT, idesc = p.idesc;
-    const bool do_mma = !(p.debug & 4), do_commit = !(p.debug & 512);
+    const bool do_mma = !(dbg & 4), do_commit = !(dbg & 512);
     const uint32_t w_ring_units = smem_u32(w_ring) >> 4, stage_units = (uint32_t)p.stage_bytes >> 4;
     const uint32_t a_ring_units = smem_u32(a_ring) >> 4, slot_units = (uint32_t)p.a_slot_bytes >> 4;
     int stage = 0;
@@ -266,14 +267,14 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       const uint32_t accb = t_cnt & 1u;
       if (!freerun) mbar_wait(&acc_empty[accb], ((t_cnt >> 1) & 1u) ^ 1u);
       tcgen05_fence_after();
-      trace(p, 1, 1, (int)t_cnt);
+      trace(dbg, 1, 1, (int)t_cnt);
       const uint32_t d_base = tmem_base + accb * (uint32_t)MT * nt;
       uint32_t started = 0;
       for (int g = 0; g < p.n_groups; ++g, ++a_cnt) {
         const uint32_t slot = a_cnt % (uint32_t)p.a_slots;
         if (!freerun) mbar_wait(&a_full[slot], (a_cnt / (uint32_t)p.a_slots) & 1u);
         tcgen05_fence_after();
-        trace(p, 1, 2, (int)t_cnt);
+        trace(dbg, 1, 2, (int)t_cnt);
         const uint32_t a_units = a_ring_units + slot * slot_units;
         const int c_begin = g * chunks_per_group;
         const int c_end = min(n_chunks, c_begin + chunks_per_group);
@@ -308,10 +309,10 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         if (do_commit) tcgen05_commit(&a_empty[slot]);
       }
       if (do_commit) tcgen05_commit(&acc_full[accb]);
-      trace(p, 1, 3, (int)t_cnt);
+      trace(dbg, 1, 3, (int)t_cnt);
     }
     }
-  } else if (warp == RES_WARP && p.r_slots > 0 && !(p.debug & (64 | 16384))) {
+  } else if (warp == RES_WARP && p.r_slots > 0 && !(dbg & (64 | 16384))) {
     // ===== residual loader: slot = (row tile m, res_cols-column block) -> res_cols/8 planes x 128 rows.
     // The <= 4 slots of a tile are issued together: lanes [8w, 8w + res_cols/8) serve slot w.
     const int n_rb = p.NT / p.res_cols, per_tile = MT * n_rb, rb_shift = 31 - __clz(n_rb);
@@ -334,7 +335,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         const int m = which >> rb_shift, rb = which & (n_rb - 1);
         const int row0 = t0 + m * BM;
         const int nrows = min(BM, p.L - row0);
-        const uint32_t bytes = (nrows > 0 && !(p.debug & (2 | 4096))) ? (uint32_t)nrows * esz : 0u;
+        const uint32_t bytes = (nrows > 0 && !(dbg & (2 | 4096))) ? (uint32_t)nrows * esz : 0u;
         if (mine) mbar_wait(&r_empty[slot], ((sidx / (uint32_t)p.r_slots) & 1u) ^ 1u);
         __syncwarp();
         if (mine && pl == 0) mbar_expect_tx(&r_full[slot], (uint32_t)rplanes * bytes);
@@ -347,7 +348,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         }
       }
     }
-  } else if (warp >= EPI_WARP0 && !(p.debug & 256)) {
+  } else if (warp >= EPI_WARP0 && !(dbg & 256)) {
     // ===== epilogue: quarter q = warp % 4 owns TMEM lanes 32q..32q+31 (one output row per lane);
     // the EPI_GROUPS warps of a quarter interleave over the (row tile m, 16-column block cb) items.
     const int quarter = warp & 3, grp = (warp - EPI_WARP0) >> 2;
@@ -355,7 +356,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
     const int CP = p.Cout_real / 8;
     const int cout_shift = 31 - __clz(p.Cout_real);       // Cout_real is a power of two (checked on the host)
     constexpr int NCH = EPI_COLS / 8;                     // 8-channel chunks per item
-    const bool io = !(p.debug & (2 | 2048));
+    const bool io = !(dbg & (2 | 2048));
     uint32_t t_cnt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t_cnt) {
       const TileCoord tc = decode_tile(tile, p);
@@ -368,9 +369,9 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       const int qbase = t0 + quarter * 32 + lane;
       if (!freerun) mbar_wait(&acc_full[accb], (t_cnt >> 1) & 1u);
       tcgen05_fence_after();
-      if (tid == EPI_WARP0 * 32) trace(p, 3, 1, (int)t_cnt);
+      if (tid == EPI_WARP0 * 32) trace(dbg, 3, 1, (int)t_cnt);
 #pragma unroll 1
-      for (int it = (p.debug & 32) ? items : grp; it < items; it += EPI_GROUPS) {
+      for (int it = (dbg & 32) ? items : grp; it < items; it += EPI_GROUPS) {
         const int m = it >> cb_shift, cb = it & (n_cb - 1);
         const int q = qbase + m * BM;
         const bool ok = q < p.L && io;
@@ -416,7 +417,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         }
         // residual item from the shared ring (the loader runs a ring ahead of the MMAs)
         uint4 rcur[2 * NCH];
-        if (p.r_slots > 0 && !(p.debug & 16384)) {
+        if (p.r_slots > 0 && !(dbg & 16384)) {
           const int n_rb = p.NT / p.res_cols;
           const uint32_t sidx = (t_cnt * (uint32_t)MT + (uint32_t)m) * (uint32_t)n_rb + (uint32_t)(c0 / p.res_cols);
           const uint32_t slot = sidx % (uint32_t)p.r_slots;
@@ -440,10 +441,10 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         uint32_t acc[EPI_COLS];
 #pragma unroll
         for (int i = 0; i < EPI_COLS; ++i) acc[i] = 0u;
-        if (!(p.debug & 32768))
+        if (!(dbg & 32768))
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * (uint32_t)(MT * p.NT) +
                       (uint32_t)(m * p.NT + c0), acc);
-        if (!(p.debug & 65536))
+        if (!(dbg & 65536))
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
           const size_t off = off0 + (size_t)j * p.L_out;
@@ -499,12 +500,12 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[accb]);
-      if (tid == EPI_WARP0 * 32) trace(p, 3, 2, (int)t_cnt);
+      if (tid == EPI_WARP0 * 32) trace(dbg, 3, 2, (int)t_cnt);
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (tid == 0) trace(p, 4, 1, 0);
+  if (tid == 0) trace(dbg, 4, 1, 0);
   if (warp == MMA_WARP) tcgen05_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -593,7 +594,7 @@ bool make_plan(const PlaneConvArgs& a, Plan* out) {
   return false;
 }
 
-template <int MT, int KC16>
+template <int MT, int KC16, bool DBG>
 cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
   CUtensorMap wmap;
   if (!get_weight_map(a.w16, a.Cin, a.N, a.K, pl.KC, pl.NT, &wmap)) return cudaErrorNotSupported;
@@ -617,7 +618,7 @@ cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
   p.debug = dbg;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_planes_kernel<MT, KC16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_planes_kernel<MT, KC16, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return e;
     attr_done = true;
@@ -628,7 +629,7 @@ cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
     unsigned int zero = 0;
     cudaMemcpyToSymbol(g_ptrace_n, &zero, sizeof(zero));
   }
-  conv_planes_kernel<MT, KC16><<<grid, NTHREADS, pl.smem, s>>>(wmap, p);
+  conv_planes_kernel<MT, KC16, DBG><<<grid, NTHREADS, pl.smem, s>>>(wmap, p);
   if (p.debug & 8) {
     cudaDeviceSynchronize();
     static unsigned long long host[4096];
@@ -667,19 +668,22 @@ bool plane_conv_supported(const PlaneConvArgs& a) {
 cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s) {
   Plan pl;
   if (!plane_conv_supported(a) || !make_plan(a, &pl)) return cudaErrorInvalidValue;
+  static const bool dbg = env_int("PG_PLANES_DEBUG", 0) != 0;
+#define PG_DISPATCH(MT_, KC16_) return dbg ? launch_t<MT_, KC16_, true>(a, pl, s) : launch_t<MT_, KC16_, false>(a, pl, s)
   if (pl.KC == 64) {
     switch (pl.MT) {
-      case 1: return launch_t<1, 4>(a, pl, s);
-      case 2: return launch_t<2, 4>(a, pl, s);
-      case 4: return launch_t<4, 4>(a, pl, s);
+      case 1: PG_DISPATCH(1, 4);
+      case 2: PG_DISPATCH(2, 4);
+      case 4: PG_DISPATCH(4, 4);
     }
   } else {
     switch (pl.MT) {
-      case 1: return launch_t<1, 2>(a, pl, s);
-      case 2: return launch_t<2, 2>(a, pl, s);
-      case 4: return launch_t<4, 2>(a, pl, s);
+      case 1: PG_DISPATCH(1, 2);
+      case 2: PG_DISPATCH(2, 2);
+      case 4: PG_DISPATCH(4, 2);
     }
   }
+#undef PG_DISPATCH
   return cudaErrorInvalidValue;
 }
 
