@@ -47,6 +47,8 @@ constexpr int BM = 128;
 constexpr int LOAD_WARP = 0, TMA_WARP = 1, MMA_WARP = 2, RES_WARP = 3, EPI_WARP0 = 4, EPI_WARPS = 16;
 constexpr int EPI_GROUPS = EPI_WARPS / 4;   // warps per TMEM lane quarter
 constexpr int EPI_COLS = 16;                // accumulator columns per epilogue item
+// epilogue specialisations: the two shapes that make up 5/6 of the ResBlock convs get straight-line code
+constexpr int EPI_GENERIC = 0, EPI_C1 = 1 /* y16 = lrelu(acc + bias) */, EPI_C2 = 2 /* y16 = lrelu(acc + bias + raw(res16)) */;
 constexpr int NTHREADS = (EPI_WARP0 + EPI_WARPS) * 32;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GROUP_PLANES = 16;   // 128 channels per activation-ring slot
@@ -110,7 +112,7 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   return q;
 }
 
-template <int MT, int KC16, bool DBG>
+template <int MT, int KC16, int EPI, bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p) {
   const int dbg = DBG ? p.debug : 0;   // production instantiation: every debug switch folds away
@@ -347,6 +349,70 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
                    &r_full[slot]);
         }
       }
+    }
+  } else if (warp >= EPI_WARP0 && EPI != EPI_GENERIC) {
+    // ===== specialised epilogue (EPI_C1 / EPI_C2): one Cout tile, row_mul == 1, bias in shared memory,
+    // f16 L-form output; per item: tcgen05.ld 16 columns -> + bias (+ residual) -> leaky-ReLU -> 2 x 16 B.
+    const int quarter = warp & 3, grp = (warp - EPI_WARP0) >> 2;
+    const int n_cb = p.NT / EPI_COLS, items = MT * n_cb, cb_shift = 31 - __clz(n_cb);
+    const int CP = p.Cout_real / 8;
+    const float slope = p.out16_slope, rinv = p.res_inv;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int rrow16 = (quarter * 32 + lane) * 16;
+    uint32_t t_cnt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t_cnt) {
+      const int rt = tile % p.n_row_tiles, b = tile / p.n_row_tiles;     // n_ntiles == 1
+      const int qbase = rt * (BM * MT) + quarter * 32 + lane;
+      const uint32_t accb = t_cnt & 1u;
+      uint4* out_b = reinterpret_cast<uint4*>(p.out16) + (size_t)b * CP * p.L;
+      mbar_wait(&acc_full[accb], (t_cnt >> 1) & 1u);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int it = grp; it < items; it += EPI_GROUPS) {
+        const int m = it >> cb_shift, cb = it & (n_cb - 1);
+        const int q = qbase + m * BM;
+        const int c0 = cb * EPI_COLS;
+        float bv[EPI_COLS];
+#pragma unroll
+        for (int i = 0; i < EPI_COLS / 4; ++i) {
+          const float4 b4 = *(reinterpret_cast<const float4*>(bias_s + c0) + i);
+          bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
+        }
+        uint4 rcur[2];
+        if (EPI == EPI_C2) {
+          const uint32_t sidx = (t_cnt * (uint32_t)MT + (uint32_t)m) * (uint32_t)(p.NT / p.res_cols) + (uint32_t)(c0 / p.res_cols);
+          const uint32_t slot = sidx % (uint32_t)p.r_slots;
+          mbar_wait(&r_full[slot], (sidx / (uint32_t)p.r_slots) & 1u);
+          const uint8_t* rs = r_ring + (size_t)slot * p.r_slot_bytes + (size_t)((c0 % p.res_cols) >> 3) * (BM * 16) + rrow16;
+          rcur[0] = *reinterpret_cast<const uint4*>(rs);
+          rcur[1] = *reinterpret_cast<const uint4*>(rs + BM * 16);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&r_empty[slot]);
+        }
+        uint32_t acc[EPI_COLS];
+        tmem_ld16(lane_taddr + accb * (uint32_t)(MT * p.NT) + (uint32_t)(m * p.NT + c0), acc);
+        if (q < p.L) {
+          uint4* dst = out_b + (size_t)(c0 >> 3) * p.L + q;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[j * 8 + i]) + bv[j * 8 + i];
+            if (EPI == EPI_C2) {
+              float rr[8];
+              unpack8(rcur[j], rr);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += fminf(rr[i], rr[i] * rinv);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * slope);
+            dst[(size_t)j * p.L] = pack8(v);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[accb]);
     }
   } else if (warp >= EPI_WARP0 && !(dbg & 256)) {
     // ===== epilogue: quarter q = warp % 4 owns TMEM lanes 32q..32q+31 (one output row per lane);
@@ -594,7 +660,7 @@ bool make_plan(const PlaneConvArgs& a, Plan* out) {
   return false;
 }
 
-template <int MT, int KC16, bool DBG>
+template <int MT, int KC16, int EPI, bool DBG>
 cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
   CUtensorMap wmap;
   if (!get_weight_map(a.w16, a.Cin, a.N, a.K, pl.KC, pl.NT, &wmap)) return cudaErrorNotSupported;
@@ -618,7 +684,7 @@ cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
   p.debug = dbg;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_planes_kernel<MT, KC16, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_planes_kernel<MT, KC16, EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return e;
     attr_done = true;
@@ -629,7 +695,7 @@ cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
     unsigned int zero = 0;
     cudaMemcpyToSymbol(g_ptrace_n, &zero, sizeof(zero));
   }
-  conv_planes_kernel<MT, KC16, DBG><<<grid, NTHREADS, pl.smem, s>>>(wmap, p);
+  conv_planes_kernel<MT, KC16, EPI, DBG><<<grid, NTHREADS, pl.smem, s>>>(wmap, p);
   if (p.debug & 8) {
     cudaDeviceSynchronize();
     static unsigned long long host[4096];
@@ -669,7 +735,16 @@ cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s) {
   Plan pl;
   if (!plane_conv_supported(a) || !make_plan(a, &pl)) return cudaErrorInvalidValue;
   static const bool dbg = env_int("PG_PLANES_DEBUG", 0) != 0;
-#define PG_DISPATCH(MT_, KC16_) return dbg ? launch_t<MT_, KC16_, true>(a, pl, s) : launch_t<MT_, KC16_, false>(a, pl, s)
+  // straight-line epilogues for the plain ResBlock shapes
+  int epi = EPI_GENERIC;
+  if (!dbg && pl.bias_smem && a.N == pl.NT && a.row_mul == 1 && !a.bbias && !a.res32 && !a.accin16 && !a.accin32 &&
+      !a.out32 && a.out16 && a.out_scale == 1.f && a.out16_slope <= 1.f && a.res_inv >= 1.f)
+    epi = a.res16 ? EPI_C2 : EPI_C1;
+#define PG_DISPATCH(MT_, KC16_)                                                        \
+  return dbg ? launch_t<MT_, KC16_, EPI_GENERIC, true>(a, pl, s)                       \
+             : (epi == EPI_C1 ? launch_t<MT_, KC16_, EPI_C1, false>(a, pl, s)          \
+                              : (epi == EPI_C2 ? launch_t<MT_, KC16_, EPI_C2, false>(a, pl, s) \
+                                               : launch_t<MT_, KC16_, EPI_GENERIC, false>(a, pl, s)))
   if (pl.KC == 64) {
     switch (pl.MT) {
       case 1: PG_DISPATCH(1, 4);
