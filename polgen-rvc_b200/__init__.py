@@ -11,8 +11,8 @@ from .configs import CONFIGS, SynthConfig, config_from_ctor, synth_inputs, synth
 
 __all__ = ["CONFIGS", "SynthConfig", "config_from_ctor", "synth_inputs", "synth_noise",
            "synth_weights"]
-from .synthesizer import (Engine, Synthesizer, SynthesizerTrnMs256NSFsid, SynthesizerTrnMs768NSFsid,
-                          fold_state_dict)
+from .synthesizer import (Engine, SegmentScheduler, Synthesizer, SynthesizerTrnMs256NSFsid,
+                          SynthesizerTrnMs768NSFsid, fold_state_dict)
 
-__all__ += ["Engine", "Synthesizer", "SynthesizerTrnMs256NSFsid", "SynthesizerTrnMs768NSFsid",
+__all__ += ["Engine", "SegmentScheduler", "Synthesizer", "SynthesizerTrnMs256NSFsid", "SynthesizerTrnMs768NSFsid",
             "fold_state_dict"]

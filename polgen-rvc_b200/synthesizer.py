@@ -468,3 +468,66 @@ class SynthesizerTrnMs256NSFsid(Synthesizer):
         kwargs.setdefault("use_f0", 1)
         kwargs["input_dim"] = 256
         super().__init__(*args, **kwargs)
+
+
+# --------------------------------------------------------------------------
+# Segment scheduler: the reference decodes the silence-split segments of
+# a clip one after another (rvc/infer/pipeline.py:381-447).  Segments are independent, so this
+# host-side scheduler keeps `lanes` engines (handle + workspace + CUDA stream each) on one GPU and
+# deals the segments round-robin: the latency-bound TextEncoder / flow kernels of one segment overlap
+# the SM-filling decoder kernels of another.  Results are identical to sequential decoding.
+# --------------------------------------------------------------------------
+class SegmentScheduler:
+    def __init__(self, cfg: SynthConfig, weights: Dict[str, torch.Tensor], device: int = 0, lanes: int = 2,
+                 flags: int = 0):
+        self.cfg = cfg
+        self.device = int(device)
+        self.engines = [Engine(cfg, weights, device, flags) for _ in range(max(1, lanes))]
+        with torch.cuda.device(self.device):
+            self.streams = [torch.cuda.Stream(device=self.device) for _ in self.engines]
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+    def decode(self, segments, seeds=None, host_out=None):
+        """segments: list of (phone, lengths, pitch, f0, sid) -- CUDA tensors, or pinned CPU tensors
+        (copied to the device on the lane's stream).  Returns the list of waveforms [B][T*upp]: CUDA
+        tensors, or the pinned CPU tensors of `host_out` filled by async D2H copies.  The caller's
+        current stream waits for every lane before this returns control to it (no host sync unless
+        host_out is given)."""
+        dev = torch.device("cuda", self.device)
+        cur = torch.cuda.current_stream(self.device)
+        ev0 = torch.cuda.Event()
+        ev0.record(cur)
+        outs = [None] * len(segments)
+        keep = []
+        self.last_launches = 0
+        for i, seg in enumerate(segments):
+            lane = i % len(self.engines)
+            st = self.streams[lane]
+            st.wait_event(ev0)
+            with torch.cuda.stream(st):
+                args = [t if t.is_cuda else t.to(dev, non_blocking=True) for t in seg]
+                keep.append(args)
+                seed = 0 if seeds is None else int(seeds[i])
+                wave, _ = self.engines[lane].infer(*args, None, None, seed, want_aux=False)
+                self.last_launches += self.engines[lane].launch_count()
+                if host_out is not None:
+                    host_out[i].copy_(wave, non_blocking=True)
+                    outs[i] = host_out[i]
+                else:
+                    outs[i] = wave
+                wave.record_stream(cur)
+        for st in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
+        if host_out is not None:
+            cur.synchronize()
+        self._keep = keep     # inputs stay alive until the next call
+        return outs
+
+    def launch_count(self) -> int:
+        """kernels launched by the last decode() call"""
+        return getattr(self, "last_launches", 0)

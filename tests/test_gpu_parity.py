@@ -308,3 +308,27 @@ def test_dropin_synthesizer_surface():
     head = int(T * (1.0 - 0.5))
     assert o_r.shape == (B, 1, (T - head) * cfg.upp) and m_r.shape == (B, 1, T - head)
     assert z_r.shape == (B, cfg.inter_channels, T - head)
+
+
+def test_segment_scheduler_matches_sequential():
+    """SegmentScheduler (two engines / streams on one GPU) returns bit-identical waveforms to decoding
+    the same segments one after another, for device and pinned-host inputs (pipeline.py:381-447)."""
+    import polgen_rvc_b200 as pg
+    cfg = pg.CONFIGS["v2-48k"]
+    sd = pg.synth_weights(cfg, seed=0)
+    folded = pg.fold_state_dict(sd)
+    d = _dev()
+    frames = [130, 97, 64]
+    segs = [pg.synth_inputs(cfg, 1, T, seed=40 + i) for i, T in enumerate(frames)]
+    eng = pg.Engine(cfg, folded, 0)
+    want = [eng.infer(*[t.to(d) for t in s], None, None, 7 + i, want_aux=False)[0].cpu() for i, s in enumerate(segs)]
+    sched = pg.SegmentScheduler(cfg, folded, 0, lanes=2)
+    got = sched.decode([[t.to(d) for t in s] for s in segs], seeds=[7, 8, 9])
+    torch.cuda.synchronize()
+    for g, w in zip(got, want):
+        assert torch.equal(g.cpu(), w)
+    host_out = [torch.empty(1, T * cfg.upp).pin_memory() for T in frames]
+    got_h = sched.decode([[t.pin_memory() for t in s] for s in segs], seeds=[7, 8, 9], host_out=host_out)
+    for g, w in zip(got_h, want):
+        assert torch.equal(g, w)
+    assert sched.launch_count() > 300
