@@ -249,7 +249,7 @@ def run_ours(args):
 
     if rank == 0:
         tf_peak, hbm_peak, peak_src = peaks()
-        umma_ms, umma_fl, umma_n = prof["conv_umma"]
+        umma_ms, umma_fl, umma_n = prof["conv_planes"]
         achieved = umma_fl / (umma_ms * 1e-3) / 1e12 if umma_ms > 0 else 0.0
         roofline = {
             "bound": "tensor", "kernel": "conv_planes_kernel (tcgen05/TMEM implicit-GEMM conv over channel planes: ResBlocks, ups, conv_pre)",
@@ -286,7 +286,7 @@ def run_ours(args):
             with open(os.path.join(ROOT, "gpurun_out", args.table), "w") as f:
                 f.write("class,Cin,N,K,dil,launches,ms_total,ms_per_launch,tflops,share_of_step\n")
                 for cls, cin, n, k, dil, cnt, ms, fl in sorted(table, key=lambda r: -r[6]):
-                    f.write(f"{'tcgen05' if cls == 0 else 'cuda-core'},{int(cin)},{int(n)},{int(k)},{int(dil)},{int(cnt)},"
+                    f.write(f"{('planes-tcgen05', 'cuda-core', 'nlc-tcgen05-split')[int(cls)]},{int(cin)},{int(n)},{int(k)},{int(dil)},{int(cnt)},"
                             f"{ms:.3f},{ms / cnt:.4f},{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.1f},{ms / seq_ms:.4f}\n")
         if world == 1 and not args.no_cpu:
             frames = 500

@@ -85,6 +85,7 @@ typedef struct pg_config {
 #define PG_FLAG_FORCE_SIMT 1   /* run every conv on the CUDA-core fp32 kernels (validation aid) */
 #define PG_FLAG_KEEP_TAPS 2    /* keep copies of intermediates for pg_debug_fetch */
 #define PG_FLAG_PROFILE 4      /* CUDA events around every conv launch (pg_profile_read) */
+#define PG_FLAG_NO_PAIR_FUSION 32 /* run every ResBlock conv as its own kernel (validation twin of the fused pair kernel) */
 #define PG_FLAG_LEGACY_DECODER 16 /* decoder on the time-major tcgen05 kernel (A/B comparison aid) */
 #define PG_FLAG_F16_LATENTS 8  /* TextEncoder / flow GEMMs with single-pass f16 tensor-core operands (default: fp32-accurate) */
 
@@ -165,8 +166,9 @@ int64_t pg_debug_fetch(pg_handle h, void* stream, const char* tap, float* dst_de
 int64_t pg_launch_count(pg_handle h);
 
 /* PG_FLAG_PROFILE: device time, algorithmic FLOPs (2*B*L*Cin*Cout*K) and launch count of the
- * conv launches since the previous read, per kernel class: [0] tcgen05 implicit-GEMM conv,
- * [1] CUDA-core conv.  Each array has 2 entries.  Synchronises on the recorded events. */
+ * conv launches since the previous read, per kernel class: [0] tcgen05 channel-plane conv (decoder),
+ * [1] CUDA-core conv, [2] tcgen05 time-major conv (TextEncoder / flow GEMMs, split precision).
+ * Each array has 3 entries.  Synchronises on the recorded events. */
 int pg_profile_read(pg_handle h, double* ms_out, double* flops_out, int64_t* launches_out);
 
 /* PG_FLAG_PROFILE: the same records aggregated per layer shape since the previous call (the

@@ -20,6 +20,7 @@ PG_FLAG_KEEP_TAPS = 2
 PG_FLAG_PROFILE = 4
 PG_FLAG_F16_LATENTS = 8
 PG_FLAG_LEGACY_DECODER = 16
+PG_FLAG_NO_PAIR_FUSION = 32
 PG_F32 = 0
 
 

@@ -425,7 +425,7 @@ int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_d
   if (prof) {
     rec.e0 = take_event(h);
     rec.e1 = take_event(h);
-    rec.cls = umma ? 0 : 1;
+    rec.cls = umma ? 2 : 1;
     rec.flops = 2.0 * a.B * a.L_out * (double)a.Cin * a.Cout * a.K;
     rec.shape[0] = a.Cin; rec.shape[1] = a.Cout; rec.shape[2] = a.K; rec.shape[3] = a.dil; rec.shape[4] = a.L_out;
     cudaEventRecord(rec.e0, s);
@@ -690,6 +690,32 @@ int run_plane_conv(pg_handle h, cudaStream_t s, PlaneConvArgs a, const ConvW& w)
   return PG_OK;
 }
 
+// fused conv1 -> lrelu -> conv2 -> +residual of one ResBlock pair; returns PG_ERR_UNSUPPORTED (without
+// setting an error) when the shape does not fit the fused kernel so the caller can run the two convs
+int run_pair_conv(pg_handle h, cudaStream_t s, PairConvArgs a, const ConvW& w1, const ConvW& w2) {
+  if (h->cfg.flags & PG_FLAG_NO_PAIR_FUSION) return PG_ERR_UNSUPPORTED;
+  a.w1 = w1.w16; a.w2 = w2.w16; a.bias1 = w1.bias; a.bias2 = w2.bias;
+  a.C = w1.Cin; a.K = w1.K;
+  if (w1.Cin != w1.Cout || w2.Cin != w2.Cout || w1.Cin != w2.Cin || w1.K != w2.K) return PG_ERR_UNSUPPORTED;
+  if (!pair_conv_supported(a)) return PG_ERR_UNSUPPORTED;
+  const bool prof = (h->cfg.flags & PG_FLAG_PROFILE) != 0;
+  pg_handle_s::ProfRec rec;
+  if (prof) {
+    rec.e0 = take_event(h);
+    rec.e1 = take_event(h);
+    rec.cls = 0;
+    rec.flops = 2.0 * 2.0 * a.B * a.L * (double)a.C * a.C * a.K;
+    rec.shape[0] = a.C; rec.shape[1] = -a.C; rec.shape[2] = a.K; rec.shape[3] = a.dil; rec.shape[4] = a.L;
+    cudaEventRecord(rec.e0, s);
+  }
+  PG_LAUNCH(h, launch_pair_planes(a, s));
+  if (prof) {
+    cudaEventRecord(rec.e1, s);
+    h->prof.push_back(rec);
+  }
+  return PG_OK;
+}
+
 // ---- GeneratorNSF.forward (nsf.py:120-144) on the channel-plane layout ------------------
 // Conv inputs live in HBM as f16 planes in L-form (already leaky-ReLU'd with the slope the next
 // conv applies, 0.1); residuals are recovered from them in the epilogue.  The LAST stage keeps
@@ -753,6 +779,21 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
         for (int d = 0; d < nd; ++d) {
           const int dil = c.resblock_dilations[j][d];
           const bool last = d == nd - 1;
+          __half* dst = last ? acc : (xc == xa ? xb : xa);
+          const float o_scale = last ? 1.f / nk : 1.f;
+          const __half* o_accin = last && j > 0 ? acc : nullptr;
+          const float o_slope = last && j < nk - 1 ? 1.f : SL;   // the finished mean is stored for ups[i+1]
+          {
+            PairConvArgs pa;
+            pa.x = xc; pa.B = B; pa.L = (int)L; pa.dil = dil; pa.res_inv = INV;
+            pa.out16 = dst; pa.out16_slope = o_slope; pa.out_scale = o_scale; pa.accin16 = o_accin;
+            const int rc = run_pair_conv(h, s, pa, S.c1[j * nd + d], S.c2[j * nd + d]);
+            if (rc == PG_OK) {
+              xc = dst;
+              continue;
+            }
+            if (rc != PG_ERR_UNSUPPORTED) return rc;
+          }
           PlaneConvArgs a1;
           a1.x = xc; a1.B = B; a1.L = (int)L; a1.dil = dil; a1.pad = (ksz * dil - dil) / 2;
           a1.out16 = tmp; a1.out16_slope = SL;
@@ -760,15 +801,7 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
           PlaneConvArgs a2;
           a2.x = tmp; a2.B = B; a2.L = (int)L; a2.pad = (ksz - 1) / 2;
           a2.res16 = xc; a2.res_inv = INV;
-          __half* dst = last ? acc : (xc == xa ? xb : xa);
-          a2.out16 = dst;
-          if (last) {
-            a2.out_scale = 1.f / nk;
-            a2.accin16 = j > 0 ? acc : nullptr;
-            a2.out16_slope = j == nk - 1 ? SL : 1.f;   // the finished mean is stored for ups[i+1]
-          } else {
-            a2.out16_slope = SL;
-          }
+          a2.out16 = dst; a2.out_scale = o_scale; a2.accin16 = o_accin; a2.out16_slope = o_slope;
           PG_TRY(run_plane_conv(h, s, a2, S.c2[j * nd + d]));
           xc = dst;
         }
@@ -797,6 +830,29 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
         for (int d = 0; d < nd; ++d) {
           const int dil = c.resblock_dilations[j][d];
           const bool last = d == nd - 1;
+          {
+            PairConvArgs pa;
+            pa.x = xc; pa.B = B; pa.L = (int)L; pa.dil = dil; pa.res32 = rc; pa.res_inv = INV;
+            if (last) {
+              pa.out_scale = 1.f / nk;
+              pa.accin32 = j > 0 ? acc : nullptr;
+              pa.out32 = acc;
+            } else {
+              const bool to_b = xc == aa;
+              pa.out32 = to_b ? rb : ra;
+              pa.out16 = to_b ? ab : aa;
+              pa.out16_slope = SL;
+            }
+            const int prc = run_pair_conv(h, s, pa, S.c1[j * nd + d], S.c2[j * nd + d]);
+            if (prc == PG_OK) {
+              if (!last) {
+                xc = pa.out16;
+                rc = pa.out32;
+              }
+              continue;
+            }
+            if (prc != PG_ERR_UNSUPPORTED) return prc;
+          }
           PlaneConvArgs a1;
           a1.x = xc; a1.B = B; a1.L = (int)L; a1.dil = dil; a1.pad = (ksz * dil - dil) / 2;
           a1.out16 = tmp; a1.out16_slope = SL;
@@ -1232,7 +1288,7 @@ int64_t pg_launch_count(pg_handle h) { return h ? h->launches : 0; }
 int pg_profile_read(pg_handle h, double* ms_out, double* flops_out, int64_t* launches_out) {
   if (!h || !ms_out || !flops_out || !launches_out) return fail(PG_ERR_INVALID, "null argument");
   Guard g(h->device);
-  for (int c = 0; c < 2; ++c) {
+  for (int c = 0; c < 3; ++c) {
     ms_out[c] = 0.0;
     flops_out[c] = 0.0;
     launches_out[c] = 0;

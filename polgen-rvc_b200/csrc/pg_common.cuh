@@ -80,6 +80,22 @@ bool plane_conv_supported(const PlaneConvArgs& a);
 int plane_pick_nt(int n);
 cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s);
 
+// Fused ResBlock pair (pg_pair_planes.cu), C in {32, 64}:
+//   tmp = lrelu(conv_dil(x; w1) + bias1, 0.1) (zero outside [0, L));  v = conv_1(tmp; w2) + bias2 + residual
+//   residual = raw(x) (x is L-form: min(x, x*res_inv)) or the fp32 stream res32
+//   v = out_scale * v + accin ; out32 = v ; out16 = lrelu(v, out16_slope)
+struct PairConvArgs {
+  const __half* x = nullptr; int B = 0, L = 0, C = 0, K = 1, dil = 1;
+  const void* w1 = nullptr; const void* w2 = nullptr;      // [K][C][C] f16 each
+  const float* bias1 = nullptr; const float* bias2 = nullptr;
+  const float* res32 = nullptr; float res_inv = 1.f;
+  const __half* accin16 = nullptr; const float* accin32 = nullptr;
+  __half* out16 = nullptr; float out16_slope = 1.f; float* out32 = nullptr;
+  float out_scale = 1.f;
+};
+bool pair_conv_supported(const PairConvArgs& a);
+cudaError_t launch_pair_planes(const PairConvArgs& a, cudaStream_t s);
+
 // time-major [B][L][x_ld] (channels x_coff..x_coff+C) -> planes f16, rows >= lens[b] zeroed when lens,
 // stored as lrelu(x, slope)
 cudaError_t launch_nlc_to_planes(const void* x, DType dt, int x_ld, int x_coff, __half* y, int B, int L,

@@ -1,0 +1,553 @@
+// Fused ResBlock pair on channel planes (sm_100a): one dilated conv, leaky-ReLU, one plain conv and
+// the residual add of reference rvc/lib/algorithm/residuals.py:47-52
+//     xt = c1(lrelu(x)) ; xt = c2(lrelu(xt)) ; x = xt + x
+// in ONE kernel for the narrow decoder stages (C = 32 / 64), where the unfused layers are HBM-bound
+// (arithmetic intensity 32-350 flop/B against a ridge of 218).  The intermediate never leaves the SM
+// and the residual is read from the input window that is already in shared memory:
+// HBM traffic per pair drops from 5 tensor passes to 2.
+//
+// Per tile of MT*128 intermediate rows (MO = MT*128 - (K-1) output rows, halo recomputed):
+//   loader warp      bulk-copies the input window (MT*128 + (K-1)*dil rows of every 8-channel plane)
+//   MMA lane         GEMM 1: acc1[rows][C] = sum_tap W1[tap] * A[row + tap*dil]      (tcgen05, TMEM)
+//   8 warps  (E1)    acc1 -> +bias1 -> leaky-ReLU -> zero outside [0, L) -> f16 planes in SHARED memory
+//   MMA lane         GEMM 2: acc2[rows][C] = sum_tap W2[tap] * tmp[row + tap]
+//   8 warps  (E2)    acc2 -> +bias2 + residual (window rows in shared memory, or the fp32 stream through a
+//                    bulk-copy ring) -> scale / accumulate -> L-form f16 and/or fp32 planes in HBM
+// Both weight sets stay resident in shared memory (TMA, 128B/64B swizzle); accumulators and the
+// intermediate are double-buffered so GEMM 1 of tile i+1 overlaps E1 of tile i and GEMM 2 / E2 of i-1.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "pg_common.cuh"
+#include "pg_umma.cuh"
+
+namespace pg {
+
+namespace {
+
+using namespace umma;
+
+constexpr int BM = 128;
+constexpr int LOAD_WARP = 0, TMA_WARP = 1, MMA_WARP = 2, RES_WARP = 3, E1_WARP0 = 4, E1_WARPS = 8, E2_WARP0 = 12,
+              E2_WARPS = 8;
+constexpr int NTHREADS = (E2_WARP0 + E2_WARPS) * 32;
+constexpr int ECOLS = 16;   // accumulator columns per epilogue item
+
+struct PairParams {
+  const __half* x; int L, B, K, dil;
+  const float* bias1; const float* bias2;
+  const float* res32; float res_inv;
+  const __half* accin16; const float* accin32;
+  __half* out16; float out16_slope; float* out32; float out_scale;
+  int MO, n_row_tiles, total_tiles, h1, h2;
+  int plane_bytes, a_slots, a_slot_bytes;
+  int tmp_plane_bytes, tmp_bytes;
+  int w_tile_bytes;
+  int r_slots, r_slot_bytes;
+  int tmem_cols;
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 q;
+  __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  return q;
+}
+
+template <int MT, int C>
+__global__ void __launch_bounds__(NTHREADS, 1)
+pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_constant__ CUtensorMap wmap2,
+                   const PairParams p) {
+  constexpr int PLANES = C / 8;
+  constexpr int KC16 = C / 16;                 // one K chunk = all C input channels
+  constexpr int NCB = C / ECOLS, ITEMS = MT * NCB;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w1 = smem;                                              // [K] tiles, GEMM 1
+  uint8_t* w2 = w1 + (size_t)p.K * p.w_tile_bytes;                 // [K] tiles, GEMM 2
+  uint8_t* a_ring = w2 + (size_t)p.K * p.w_tile_bytes;
+  uint8_t* tmp = a_ring + (size_t)p.a_slots * p.a_slot_bytes;      // [2] intermediate planes
+  uint8_t* r_ring = tmp + 2 * (size_t)p.tmp_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(r_ring + (size_t)p.r_slots * p.r_slot_bytes);
+  uint64_t* a_full = bars;                    // [a_slots]
+  uint64_t* a_empty = a_full + p.a_slots;     // [a_slots]  GEMM 1 commit + every E2 warp
+  uint64_t* acc1_full = a_empty + p.a_slots;  // [2]
+  uint64_t* acc1_empty = acc1_full + 2;       // [2]  E1 warps
+  uint64_t* tmp_full = acc1_empty + 2;        // [2]  E1 warps
+  uint64_t* tmp_empty = tmp_full + 2;         // [2]  GEMM 2 commit
+  uint64_t* acc2_full = tmp_empty + 2;        // [2]
+  uint64_t* acc2_empty = acc2_full + 2;       // [2]  E2 warps
+  uint64_t* w_ready = acc2_empty + 2;
+  uint64_t* r_full = w_ready + 1;             // [r_slots]
+  uint64_t* r_empty = r_full + p.r_slots;     // [r_slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_empty + p.r_slots);
+  float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [2][C]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < p.a_slots; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1 + E2_WARPS);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc1_full[s], 1);
+      mbar_init(&acc1_empty[s], E1_WARPS);
+      mbar_init(&tmp_full[s], E1_WARPS);
+      mbar_init(&tmp_empty[s], 1);
+      mbar_init(&acc2_full[s], 1);
+      mbar_init(&acc2_empty[s], E2_WARPS);
+    }
+    mbar_init(w_ready, 1);
+    for (int s = 0; s < p.r_slots; ++s) {
+      mbar_init(&r_full[s], 1);
+      mbar_init(&r_empty[s], 4 * NCB);      // every (quarter warp, item) that reads the 128-row slot
+    }
+    fence_barrier_init();
+  }
+  if (tid < 2 * C) bias_s[tid] = tid < C ? p.bias1[tid] : p.bias2[tid - C];
+  if (warp == MMA_WARP) tcgen05_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == TMA_WARP && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap2) : "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int rows = BM * MT + (p.K - 1) * p.dil;        // input window rows
+  const uint32_t acc1_col = 0u, acc2_col = 2u * MT * C;  // TMEM columns of the two accumulator pairs
+
+  if (warp == LOAD_WARP) {
+    // ===== input window loader (bulk copies + zero fill outside [0, L)) =====
+    uint32_t cnt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++cnt) {
+      const int rt = tile % p.n_row_tiles, b = tile / p.n_row_tiles;
+      const int tstart = rt * p.MO - p.h2 - p.h1;
+      const int lo = min(max(-tstart, 0), rows);
+      const int hi = min(max(p.L - tstart, lo), rows);
+      const int nz = lo + (rows - hi);
+      const __half* xb = p.x + (size_t)b * PLANES * p.L * 8;
+      const uint32_t slot = cnt % (uint32_t)p.a_slots;
+      mbar_wait(&a_empty[slot], ((cnt / (uint32_t)p.a_slots) & 1u) ^ 1u);
+      uint8_t* dst = a_ring + (size_t)slot * p.a_slot_bytes;
+      if (nz > 0) {
+        for (int i = lane; i < PLANES * nz; i += 32) {
+          const int pl = i / nz, z = i - pl * nz;
+          const int r = z < lo ? z : hi + (z - lo);
+          *reinterpret_cast<uint4*>(dst + (size_t)pl * p.plane_bytes + (size_t)r * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      const uint32_t bytes = (uint32_t)(hi - lo) * 16u;
+      if (lane == 0) mbar_expect_tx(&a_full[slot], bytes * (uint32_t)PLANES);
+      __syncwarp();
+      if (bytes && lane < PLANES)
+        bulk_g2s(dst + (size_t)lane * p.plane_bytes + (size_t)lo * 16,
+                 xb + ((size_t)lane * p.L + (tstart + lo)) * 8, bytes, &a_full[slot]);
+    }
+  } else if (warp == TMA_WARP) {
+    // ===== both weight sets, once =====
+    if (elect_one()) {
+      mbar_expect_tx(w_ready, (uint32_t)(2 * p.K * p.w_tile_bytes));
+      for (int tap = 0; tap < p.K; ++tap) {
+        tma_load_2d(w1 + (size_t)tap * p.w_tile_bytes, &wmap1, w_ready, 0, tap * C);
+        tma_load_2d(w2 + (size_t)tap * p.w_tile_bytes, &wmap2, w_ready, 0, tap * C);
+      }
+    }
+    __syncwarp();
+  } else if (warp == MMA_WARP) {
+    // ===== MMA issuer (one elected lane): GEMM 1 of tile i, then GEMM 2 of tile i-1 =====
+    if (elect_one()) {
+      constexpr uint32_t w_layout = C == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
+      constexpr uint32_t w_sbo = 8u * C * 2u;
+      const uint64_t adesc0 = make_desc(0u, (uint32_t)p.plane_bytes, 128u, LAYOUT_NONE);
+      const uint64_t tdesc0 = make_desc(0u, (uint32_t)p.tmp_plane_bytes, 128u, LAYOUT_NONE);
+      const uint64_t bdesc0 = make_desc(0u, 0u, w_sbo, w_layout);
+      const uint32_t a_hi = (uint32_t)(adesc0 >> 32), t_hi = (uint32_t)(tdesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)adesc0, t_lo0 = (uint32_t)tdesc0, b_lo0 = (uint32_t)bdesc0;
+      const uint32_t plane2 = 2u * ((uint32_t)p.plane_bytes >> 4), tplane2 = 2u * ((uint32_t)p.tmp_plane_bytes >> 4);
+      const uint32_t w1_units = smem_u32(w1) >> 4, w2_units = smem_u32(w2) >> 4, wt_units = (uint32_t)p.w_tile_bytes >> 4;
+      const uint32_t a_units0 = smem_u32(a_ring) >> 4, slot_units = (uint32_t)p.a_slot_bytes >> 4;
+      const uint32_t tmp_units0 = smem_u32(tmp) >> 4, tmp_units = (uint32_t)p.tmp_bytes >> 4;
+      const uint32_t idesc = p.idesc;
+      mbar_wait(w_ready, 0);
+      tcgen05_fence_after();
+      const int n_my = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      for (int it = 0; it <= n_my; ++it) {
+        if (it < n_my) {   // GEMM 1 (dilated conv) of tile it
+          const uint32_t slot = (uint32_t)it % (uint32_t)p.a_slots, b = (uint32_t)it & 1u;
+          mbar_wait(&a_full[slot], ((uint32_t)it / (uint32_t)p.a_slots) & 1u);
+          mbar_wait(&acc1_empty[b], (((uint32_t)it >> 1) & 1u) ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t d_base = tmem_base + acc1_col + b * (uint32_t)(MT * C);
+          const uint32_t a_base = a_lo0 + a_units0 + slot * slot_units;
+#pragma unroll 1
+          for (int tap = 0; tap < p.K; ++tap) {
+            const uint32_t a_lo = a_base + (uint32_t)(tap * p.dil);
+            const uint32_t w_lo = b_lo0 + w1_units + (uint32_t)tap * wt_units;
+#pragma unroll
+            for (int k16 = 0; k16 < KC16; ++k16)
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                umma_f16_lh(d_base + (uint32_t)(m * C), a_lo + (uint32_t)k16 * plane2 + (uint32_t)(m * BM), a_hi,
+                            w_lo + 2u * (uint32_t)k16, b_hi, idesc, (uint32_t)(tap | k16));
+          }
+          tcgen05_commit(&acc1_full[b]);
+          tcgen05_commit(&a_empty[slot]);
+        }
+        if (it >= 1) {     // GEMM 2 (plain conv over the shared-memory intermediate) of tile it-1
+          const uint32_t j = (uint32_t)(it - 1), b = j & 1u;
+          mbar_wait(&tmp_full[b], (j >> 1) & 1u);
+          mbar_wait(&acc2_empty[b], ((j >> 1) & 1u) ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t d_base = tmem_base + acc2_col + b * (uint32_t)(MT * C);
+          const uint32_t t_base = t_lo0 + tmp_units0 + b * tmp_units;
+#pragma unroll 1
+          for (int tap = 0; tap < p.K; ++tap) {
+            const uint32_t t_lo = t_base + (uint32_t)tap;
+            const uint32_t w_lo = b_lo0 + w2_units + (uint32_t)tap * wt_units;
+#pragma unroll
+            for (int k16 = 0; k16 < KC16; ++k16)
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                umma_f16_lh(d_base + (uint32_t)(m * C), t_lo + (uint32_t)k16 * tplane2 + (uint32_t)(m * BM), t_hi,
+                            w_lo + 2u * (uint32_t)k16, b_hi, idesc, (uint32_t)(tap | k16));
+          }
+          tcgen05_commit(&acc2_full[b]);
+          tcgen05_commit(&tmp_empty[b]);
+        }
+      }
+    }
+  } else if (warp == RES_WARP && p.r_slots > 0) {
+    // ===== fp32 residual stream: one 128-row x C slot per row tile m =====
+    const int pl = lane & 7, sub = lane >> 3;
+    const int batch = min(min(MT, p.r_slots), 4);
+    uint32_t s_cnt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, s_cnt += (uint32_t)MT) {
+      const int rt = tile % p.n_row_tiles, b = tile / p.n_row_tiles;
+      const int o0 = rt * p.MO;
+      for (int base = 0; base < MT; base += batch) {
+        const int m = base + sub;
+        const bool mine = sub < batch && m < MT && pl < PLANES;
+        const uint32_t sidx = s_cnt + (uint32_t)m;
+        const uint32_t slot = sidx % (uint32_t)p.r_slots;
+        const int row0 = o0 + m * BM;
+        const int nrows = min(BM, p.L - row0);
+        const uint32_t bytes = nrows > 0 ? (uint32_t)nrows * 32u : 0u;
+        if (mine) mbar_wait(&r_empty[slot], ((sidx / (uint32_t)p.r_slots) & 1u) ^ 1u);
+        __syncwarp();
+        if (mine && pl == 0) mbar_expect_tx(&r_full[slot], (uint32_t)PLANES * bytes);
+        __syncwarp();
+        if (mine && bytes)
+          bulk_g2s(r_ring + (size_t)slot * p.r_slot_bytes + (size_t)pl * (BM * 32),
+                   reinterpret_cast<const char*>(p.res32) + (((size_t)b * PLANES + pl) * p.L + row0) * 32, bytes,
+                   &r_full[slot]);
+      }
+    }
+  } else if (warp >= E1_WARP0 && warp < E2_WARP0) {
+    // ===== E1: acc1 -> lrelu(acc + bias1) -> f16 planes of the intermediate, in shared memory =====
+    const int quarter = warp & 3, grp = (warp - E1_WARP0) >> 2;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc1_col;
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+      const int rt = tile % p.n_row_tiles;
+      const int t_first = rt * p.MO - p.h2;            // time of intermediate row 0
+      const uint32_t b = j & 1u;
+      mbar_wait(&acc1_full[b], (j >> 1) & 1u);
+      mbar_wait(&tmp_empty[b], ((j >> 1) & 1u) ^ 1u);
+      tcgen05_fence_after();
+      uint8_t* tb = tmp + (size_t)b * p.tmp_bytes;
+#pragma unroll 1
+      for (int it = grp; it < ITEMS; it += E1_WARPS / 4) {
+        const int m = it / NCB, cb = it - m * NCB;
+        const int r = m * BM + quarter * 32 + lane;
+        const int t = t_first + r;
+        const bool live = t >= 0 && t < p.L;
+        uint32_t acc[ECOLS];
+        tmem_ld16(lane_taddr + b * (uint32_t)(MT * C) + (uint32_t)(m * C + cb * ECOLS), acc);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float a = __uint_as_float(acc[jj * 8 + i]) + bias_s[cb * ECOLS + jj * 8 + i];
+            v[i] = live ? fmaxf(a, a * 0.1f) : 0.f;
+          }
+          *reinterpret_cast<uint4*>(tb + (size_t)(cb * 2 + jj) * p.tmp_plane_bytes + (size_t)r * 16) = pack8(v);
+        }
+      }
+      fence_proxy_async_smem();      // intermediate rows -> visible to the tensor core
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tmp_full[b]);
+        mbar_arrive(&acc1_empty[b]);
+      }
+    }
+  } else if (warp >= E2_WARP0) {
+    // ===== E2: acc2 -> + bias2 + residual -> scale / accumulate -> HBM =====
+    const int quarter = warp & 3, grp = (warp - E2_WARP0) >> 2;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc2_col;
+    const float* bias2 = bias_s + C;
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+      const int rt = tile % p.n_row_tiles, bb = tile / p.n_row_tiles;
+      const int o0 = rt * p.MO;
+      const uint32_t b = j & 1u, slot = j % (uint32_t)p.a_slots;
+      const size_t plane_base = (size_t)bb * PLANES * p.L;
+      // the accumulate input of this warp's items is fetched BEFORE waiting for the accumulator, so its
+      // HBM latency hides behind GEMM 2 (registers: IPW items x 2 chunks, x2 for fp32)
+      constexpr int IPW = ITEMS / (E2_WARPS / 4);
+      constexpr bool PRE32 = IPW * 4 <= 8;
+      uint4 pre[8];
+      const bool pre16 = p.accin16 != nullptr, pre32 = PRE32 && p.accin32 != nullptr;
+      if (pre16 || pre32) {
+#pragma unroll
+        for (int ii = 0; ii < IPW; ++ii) {
+          const int it = grp + ii * (E2_WARPS / 4);
+          const int m = it / NCB, cb = it - m * NCB;
+          const int o = m * BM + quarter * 32 + lane;
+          const int t = o0 + o;
+          if (o < p.MO && t < p.L) {
+            const size_t off = plane_base + (size_t)(cb * 2) * p.L + t;
+            if (pre16) {
+              pre[2 * ii] = *(reinterpret_cast<const uint4*>(p.accin16) + off);
+              pre[2 * ii + 1] = *(reinterpret_cast<const uint4*>(p.accin16) + off + p.L);
+            } else if (PRE32) {
+              pre[(4 * ii) & 7] = *(reinterpret_cast<const uint4*>(p.accin32) + off * 2);
+              pre[(4 * ii + 1) & 7] = *(reinterpret_cast<const uint4*>(p.accin32) + off * 2 + 1);
+              pre[(4 * ii + 2) & 7] = *(reinterpret_cast<const uint4*>(p.accin32) + (off + p.L) * 2);
+              pre[(4 * ii + 3) & 7] = *(reinterpret_cast<const uint4*>(p.accin32) + (off + p.L) * 2 + 1);
+            }
+          }
+        }
+      }
+      mbar_wait(&acc2_full[b], (j >> 1) & 1u);
+      mbar_wait(&a_full[slot], (j / (uint32_t)p.a_slots) & 1u);   // residual rows of the window (already landed)
+      tcgen05_fence_after();
+      const uint8_t* aw = a_ring + (size_t)slot * p.a_slot_bytes;
+#pragma unroll
+      for (int ii = 0; ii < IPW; ++ii) {
+        const int it = grp + ii * (E2_WARPS / 4);
+        const int m = it / NCB, cb = it - m * NCB;
+        const int o = m * BM + quarter * 32 + lane;
+        const int t = o0 + o;
+        const bool ok = o < p.MO && t < p.L;
+        uint4 rq[4];
+        if (p.r_slots > 0) {
+          const uint32_t sidx = j * (uint32_t)MT + (uint32_t)m;
+          const uint32_t rslot = sidx % (uint32_t)p.r_slots;
+          mbar_wait(&r_full[rslot], (sidx / (uint32_t)p.r_slots) & 1u);
+          const uint8_t* rs = r_ring + (size_t)rslot * p.r_slot_bytes + (size_t)(cb * 2) * (BM * 32) +
+                              (size_t)(quarter * 32 + lane) * 32;
+          rq[0] = *reinterpret_cast<const uint4*>(rs);
+          rq[1] = *reinterpret_cast<const uint4*>(rs + 16);
+          rq[2] = *reinterpret_cast<const uint4*>(rs + BM * 32);
+          rq[3] = *reinterpret_cast<const uint4*>(rs + BM * 32 + 16);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&r_empty[rslot]);
+        } else {
+          const uint8_t* ar = aw + (size_t)(cb * 2) * p.plane_bytes + (size_t)(o + p.h2 + p.h1) * 16;
+          rq[0] = *reinterpret_cast<const uint4*>(ar);
+          rq[1] = *reinterpret_cast<const uint4*>(ar + p.plane_bytes);
+        }
+        uint32_t acc[ECOLS];
+        tmem_ld16(lane_taddr + b * (uint32_t)(MT * C) + (uint32_t)(m * C + cb * ECOLS), acc);
+        if (ok) {
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const size_t off = plane_base + (size_t)(cb * 2 + jj) * p.L + t;   // 8-element units
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[jj * 8 + i]) + bias2[cb * ECOLS + jj * 8 + i];
+            if (p.r_slots > 0) {
+              const uint4 q0 = rq[2 * jj], q1 = rq[2 * jj + 1];
+              v[0] += __uint_as_float(q0.x); v[1] += __uint_as_float(q0.y);
+              v[2] += __uint_as_float(q0.z); v[3] += __uint_as_float(q0.w);
+              v[4] += __uint_as_float(q1.x); v[5] += __uint_as_float(q1.y);
+              v[6] += __uint_as_float(q1.z); v[7] += __uint_as_float(q1.w);
+            } else {
+              float rr[8];
+              unpack8(rq[jj], rr);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += fminf(rr[i], rr[i] * p.res_inv);
+            }
+            if (p.out_scale != 1.f) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= p.out_scale;
+            }
+            if (pre16) {
+              float a[8];
+              unpack8(pre[2 * ii + jj], a);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += a[i];
+            }
+            if (p.accin32) {
+              uint4 a0, a1;
+              if (PRE32) {
+                a0 = pre[(4 * ii + 2 * jj) & 7];
+                a1 = pre[(4 * ii + 2 * jj + 1) & 7];
+              } else {
+                a0 = *(reinterpret_cast<const uint4*>(p.accin32) + off * 2);
+                a1 = *(reinterpret_cast<const uint4*>(p.accin32) + off * 2 + 1);
+              }
+              v[0] += __uint_as_float(a0.x); v[1] += __uint_as_float(a0.y);
+              v[2] += __uint_as_float(a0.z); v[3] += __uint_as_float(a0.w);
+              v[4] += __uint_as_float(a1.x); v[5] += __uint_as_float(a1.y);
+              v[6] += __uint_as_float(a1.z); v[7] += __uint_as_float(a1.w);
+            }
+            if (p.out32) {
+              float4* o4 = reinterpret_cast<float4*>(p.out32) + off * 2;
+              o4[0] = make_float4(v[0], v[1], v[2], v[3]);
+              o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            if (p.out16) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * p.out16_slope);   // slope <= 1
+              *(reinterpret_cast<uint4*>(p.out16) + off) = pack8(v);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&acc2_empty[b]);
+        mbar_arrive(&a_empty[slot]);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tcgen05_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+struct PairPlan {
+  int MT, a_slots, a_slot_bytes, plane_bytes, tmp_plane_bytes, tmp_bytes, w_tile_bytes, r_slots, r_slot_bytes,
+      tmem_cols;
+  size_t smem;
+};
+
+bool make_pair_plan(const PairConvArgs& a, PairPlan* out) {
+  if (a.C != 32 && a.C != 64) return false;
+  if (a.K < 1 || a.K > 16 || !(a.K & 1) || a.dil < 1) return false;
+  const int planes = a.C / 8;
+  const int w_tile = a.C * a.C * 2;
+  const size_t fixed = 1024 + 1024 + 8 * (size_t)a.C;   // alignment slack, barriers, two bias vectors
+  const size_t budget = (size_t)227 * 1024;
+  const size_t w_all = 2 * (size_t)a.K * w_tile;
+  static const int forced_mt = [] { const char* e = getenv("PG_PAIR_MT"); return e ? atoi(e) : 0; }();
+  // pass 0 insists on rings deep enough to hide the HBM latency (3 input windows in flight and, for
+  // the fp32 residual stream, two tiles of residual slots); pass 1 takes whatever fits
+  for (int pass = 0; pass < 2; ++pass)
+  for (int MT : {4, 2, 1}) {
+    if (forced_mt && MT != forced_mt) continue;
+    if (4 * MT * a.C > 512) continue;
+    const int MO = BM * MT - (a.K - 1);
+    if (MO < 64) continue;
+    const int rows = BM * MT + (a.K - 1) * a.dil;
+    const int plane_bytes = 16 * ((rows + 7) & ~7);
+    const int a_slot = (planes * plane_bytes + 127) & ~127;
+    const int tmp_plane = 16 * (BM * MT + 16);
+    const int tmp_bytes = (planes * tmp_plane + 127) & ~127;
+    const int r_slot = a.res32 ? BM * planes * 32 : 0;
+    int r_slots = a.res32 ? 2 : 0;
+    size_t need = fixed + w_all + 2 * (size_t)a_slot + 2 * (size_t)tmp_bytes + (size_t)r_slots * r_slot;
+    if (need > budget) continue;
+    size_t left = budget - need;
+    int a_slots = 2;
+    auto grow = [&](int* v, int cap, size_t unit) {
+      while (*v < cap && left >= unit) {
+        ++*v;
+        left -= unit;
+      }
+    };
+    grow(&a_slots, 3, a_slot);
+    if (a.res32) grow(&r_slots, 2 * MT, r_slot);
+    grow(&a_slots, 4, a_slot);
+    if (a.res32) grow(&r_slots, 3 * MT, r_slot);
+    if (pass == 0 && (a_slots < 3 || (a.res32 && r_slots < 2 * MT))) continue;
+    int tm = 32;
+    while (tm < 4 * MT * a.C) tm <<= 1;
+    *out = PairPlan{MT, a_slots, a_slot, plane_bytes, tmp_plane, tmp_bytes, w_tile, r_slots, r_slot, tm,
+                    fixed + w_all + (size_t)a_slots * a_slot + 2 * (size_t)tmp_bytes + (size_t)r_slots * r_slot};
+    return true;
+  }
+  return false;
+}
+
+template <int MT, int C>
+cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_t s) {
+  CUtensorMap m1, m2;
+  const int kc = C == 64 ? 64 : 32;
+  if (!get_weight_map(a.w1, C, C, a.K, kc, C, &m1) || !get_weight_map(a.w2, C, C, a.K, kc, C, &m2))
+    return cudaErrorNotSupported;
+  PairParams p;
+  p.x = a.x; p.L = a.L; p.B = a.B; p.K = a.K; p.dil = a.dil;
+  p.bias1 = a.bias1; p.bias2 = a.bias2; p.res32 = a.res32; p.res_inv = a.res_inv;
+  p.accin16 = a.accin16; p.accin32 = a.accin32;
+  p.out16 = a.out16; p.out16_slope = a.out16_slope; p.out32 = a.out32; p.out_scale = a.out_scale;
+  p.MO = BM * MT - (a.K - 1);
+  p.n_row_tiles = (a.L + p.MO - 1) / p.MO;
+  p.total_tiles = p.n_row_tiles * a.B;
+  p.h1 = (a.K - 1) * a.dil / 2; p.h2 = (a.K - 1) / 2;
+  p.plane_bytes = pl.plane_bytes; p.a_slots = pl.a_slots; p.a_slot_bytes = pl.a_slot_bytes;
+  p.tmp_plane_bytes = pl.tmp_plane_bytes; p.tmp_bytes = pl.tmp_bytes; p.w_tile_bytes = pl.w_tile_bytes;
+  p.r_slots = pl.r_slots; p.r_slot_bytes = pl.r_slot_bytes; p.tmem_cols = pl.tmem_cols;
+  p.idesc = make_idesc(BM, C);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(pair_planes_kernel<MT, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  int grid = device_sm_count();
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  pair_planes_kernel<MT, C><<<grid, NTHREADS, pl.smem, s>>>(m1, m2, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool pair_conv_supported(const PairConvArgs& a) {
+  if (!a.x || !a.w1 || !a.w2 || !a.bias1 || !a.bias2 || (!a.out16 && !a.out32)) return false;
+  if (a.L <= 0 || a.B <= 0 || a.res_inv < 1.f || a.out16_slope > 1.f) return false;
+  PairPlan pl;
+  return make_pair_plan(a, &pl);
+}
+
+cudaError_t launch_pair_planes(const PairConvArgs& a, cudaStream_t s) {
+  PairPlan pl;
+  if (!pair_conv_supported(a) || !make_pair_plan(a, &pl)) return cudaErrorInvalidValue;
+  if (a.C == 32) {
+    switch (pl.MT) {
+      case 4: return launch_pair_t<4, 32>(a, pl, s);
+      case 2: return launch_pair_t<2, 32>(a, pl, s);
+      case 1: return launch_pair_t<1, 32>(a, pl, s);
+    }
+  } else {
+    switch (pl.MT) {
+      case 2: return launch_pair_t<2, 64>(a, pl, s);
+      case 1: return launch_pair_t<1, 64>(a, pl, s);
+    }
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace pg

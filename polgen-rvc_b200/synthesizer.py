@@ -113,9 +113,10 @@ class Engine:
 
     def profile_read(self):
         """PG_FLAG_PROFILE: {class: (ms, flops, launches)} of the conv launches since the last read."""
-        ms, fl, n = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_int64 * 2)()
+        ms, fl, n = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_int64 * 3)()
         _lib.check(self.lib.pg_profile_read(self._h, ms, fl, n), "pg_profile_read")
-        return {"conv_umma": (ms[0], fl[0], int(n[0])), "conv_simt": (ms[1], fl[1], int(n[1]))}
+        return {"conv_planes": (ms[0], fl[0], int(n[0])), "conv_simt": (ms[1], fl[1], int(n[1])),
+                "conv_umma": (ms[2], fl[2], int(n[2]))}
 
     def profile_table(self, max_rows: int = 256):
         """Per-shape rows (cls, Cin, N, K, dil, launches, ms, flops) of the records profile_read() consumed."""
