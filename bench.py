@@ -105,6 +105,12 @@ def cpu_reference_rate(cfg, frames, steps, warmup, seed=0):
     import torch
     import polgen_rvc_b200 as pg
     from oracle import rvc_oracle as orc
+    # all the host cores this process may use (torchrun pins OMP_NUM_THREADS=1 for N>1 ranks)
+    try:
+        n_threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n_threads = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n_threads))
     sd = orc.fold_weight_norm(pg.synth_weights(cfg, seed=seed))
     phone, lengths, pitch, f0, sid = pg.synth_inputs(cfg, 1, frames, seed=seed)
     eps_zp, eps_src = pg.synth_noise(cfg, 1, frames, seed=seed)
