@@ -74,15 +74,15 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
 }
 
 struct AttnSmem {
-  __half k[2][2][AK][KP];    // [buffer][hi/lo][key][dim]
-  __half v[2][2][AD][VP];    // [buffer][hi/lo][dim][key]
+  __half k[1][2][AK][KP];    // [buffer][hi/lo][key][dim]  (single buffer: two CTAs per SM overlap instead)
+  __half v[1][2][AD][VP];    // [buffer][hi/lo][dim][key]
   float rl[AQ][RP];          // rel-key logits q_i . Ek[r]
   float sb[AQ][RP];          // band scores (raw, masked) for the rel-value term
   float ev[RP][AD];          // rel-value table
   float m[AQ], inv_l[AQ];
 };
 
-__global__ void __launch_bounds__(ATT_THREADS) rel_attention_mma_kernel(
+__global__ void __launch_bounds__(ATT_THREADS, 2) rel_attention_mma_kernel(
     const __half* __restrict__ qh, const __half* __restrict__ ql, const __half* __restrict__ kh,
     const __half* __restrict__ kl, const __half* __restrict__ vth, const __half* __restrict__ vtl,
     const float* __restrict__ qkv, const float* __restrict__ rel_k, const float* __restrict__ rel_v,
@@ -163,13 +163,9 @@ __global__ void __launch_bounds__(ATT_THREADS) rel_attention_mma_kernel(
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
   for (int kb = 0; kb < nblk; ++kb) {
-    const int buf = kb & 1, k0 = kb * AK;
-    if (kb + 1 < nblk) {
-      load_block(kb + 1, buf ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
+    const int buf = 0, k0 = kb * AK;
+    if (kb > 0) load_block(kb, 0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     // ---- S = Q K^T (3-term split)
