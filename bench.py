@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -258,7 +258,7 @@ def run_ours(args):
         umma_ms, umma_fl, umma_n = prof["conv_planes"]
         achieved = umma_fl / (umma_ms * 1e-3) / 1e12 if umma_ms > 0 else 0.0
         roofline = {
-            "bound": "tensor", "kernel": "conv_planes_kernel (tcgen05/TMEM implicit-GEMM conv over channel planes: ResBlocks, ups, conv_pre)",
+            "bound": "tensor", "kernel": "decoder tcgen05/TMEM implicit-GEMM convs over channel planes: conv_planes_kernel (ResBlock convs, ups, conv_pre) + pair_planes_kernel (fused ResBlock pairs, C=32/64)",
             "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
             "peak_source": peak_src, "traffic": None,
             "launches": umma_n, "avg_launch_ms": umma_ms / max(umma_n, 1),

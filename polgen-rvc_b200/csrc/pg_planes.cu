@@ -90,10 +90,7 @@ __global__ void planes_to_nlc_kernel(const TIn* __restrict__ x, TOut* __restrict
   store8(y + ((size_t)id.b * L + id.t) * C + id.pl * 8, v);
 }
 
-// nsf.py:131  x = x + noise_convs[i](har_source), then the L-form copy the next conv reads.
-// Thread mapping: the 8-channel plane index is the FASTEST thread coordinate, so the lanes of a warp
-// share (or nearly share) the time row: the source sample of a tap is one broadcast load and the tap's
-// weights [C] are one coalesced load; the 16 B plane accesses of a row land in C/8 different planes.
+// nsf.py:131  x = x + noise_convs[i](har_source), then the L-form copy the next conv reads
 template <typename T>
 __global__ void __launch_bounds__(256) noise_inject_planes_kernel(
     T* __restrict__ x, __half* __restrict__ a16, const float* __restrict__ src, const float* __restrict__ wn,
@@ -101,18 +98,16 @@ __global__ void __launch_bounds__(256) noise_inject_planes_kernel(
   const int CP = C / 8;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * CP * L) return;
-  const int pl = (int)(i % CP);
-  const size_t rr = i / CP;
-  const int t = (int)(rr % L), b = (int)(rr / L);
-  const int c0 = pl * 8;
-  const size_t e = (((size_t)b * CP + pl) * L + t) * 8;   // element offset in the plane tensor
+  const Idx id = split(i, L, CP);
+  const int c0 = id.pl * 8;
   float acc[8];
   load8(bn + c0, acc);
-  const float* sp = src + (size_t)b * Lsrc;
-  const int s0 = t * stride - pad;
-  const int j_lo = max(0, -s0), j_hi = min(k, Lsrc - s0);
-  for (int j = j_lo; j < j_hi; ++j) {
-    const float sv = __ldg(sp + s0 + j);
+  const float* sp = src + (size_t)id.b * Lsrc;
+  const int s0 = id.t * stride - pad;
+  for (int j = 0; j < k; ++j) {
+    const int n = s0 + j;
+    if (n < 0 || n >= Lsrc) continue;
+    const float sv = sp[n];
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(wn + (size_t)j * C + c0));
     const float4 w1 = __ldg(reinterpret_cast<const float4*>(wn + (size_t)j * C + c0 + 4));
     acc[0] = fmaf(w0.x, sv, acc[0]); acc[1] = fmaf(w0.y, sv, acc[1]);
@@ -121,13 +116,13 @@ __global__ void __launch_bounds__(256) noise_inject_planes_kernel(
     acc[6] = fmaf(w1.z, sv, acc[6]); acc[7] = fmaf(w1.w, sv, acc[7]);
   }
   float v[8];
-  load8(x + e, v);
+  load8(x + i * 8, v);
 #pragma unroll
   for (int q = 0; q < 8; ++q) v[q] += acc[q];
-  if (sizeof(T) == 4) store8(x + e, v);   // fp32 residual stream keeps the raw value
+  if (sizeof(T) == 4) store8(x + i * 8, v);   // fp32 residual stream keeps the raw value
 #pragma unroll
   for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * slope;
-  store8(a16 + e, v);
+  store8(a16 + i * 8, v);
 }
 
 // nsf.py:142-143  wave = tanh(conv_post(leaky_relu(x)))  (Cout = 1, no bias); one thread per sample
