@@ -379,6 +379,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
           bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
         }
         uint4 rcur[2];
+        int ring_slot = 0;
         if (EPI == EPI_C2) {
           const uint32_t sidx = (t_cnt * (uint32_t)MT + (uint32_t)m) * (uint32_t)(p.NT / p.res_cols) + (uint32_t)(c0 / p.res_cols);
           const uint32_t slot = sidx % (uint32_t)p.r_slots;
@@ -386,11 +387,16 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
           const uint8_t* rs = r_ring + (size_t)slot * p.r_slot_bytes + (size_t)((c0 % p.res_cols) >> 3) * (BM * 16) + rrow16;
           rcur[0] = *reinterpret_cast<const uint4*>(rs);
           rcur[1] = *reinterpret_cast<const uint4*>(rs + BM * 16);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&r_empty[slot]);
+          ring_slot = (int)slot;
         }
         uint32_t acc[EPI_COLS];
         tmem_ld16(lane_taddr + accb * (uint32_t)(MT * p.NT) + (uint32_t)(m * p.NT + c0), acc);
+        if (EPI == EPI_C2) {   // release the slot only after the loads have landed (see mbar_arrive_dep)
+          uint32_t dep = rcur[0].x ^ rcur[0].w ^ rcur[1].x ^ rcur[1].w;
+          asm volatile("" : "+r"(dep));
+          __syncwarp();
+          if (lane == 0) mbar_arrive_dep(&r_empty[ring_slot], dep);
+        }
         if (q < p.L) {
           uint4* dst = out_b + (size_t)(c0 >> 3) * p.L + q;
 #pragma unroll
@@ -501,8 +507,13 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
 #pragma unroll
             for (int j = 0; j < NCH; ++j) rcur[j] = *reinterpret_cast<const uint4*>(rs + j * (BM * 16) + rrow * 16);
           }
+          // release the slot with an arrive that is data-dependent on the loaded registers: the refill is an
+          // async-proxy write and a plain arrive does not wait for this warp's outstanding shared loads
+          uint32_t dep = rcur[0].x ^ rcur[0].w ^ rcur[1].x ^ rcur[1].w;
+          if (p.res32) dep ^= rcur[2].x ^ rcur[2].w ^ rcur[3].x ^ rcur[3].w;
+          asm volatile("" : "+r"(dep));
           __syncwarp();
-          if (lane == 0 && !freerun) mbar_arrive(&r_empty[slot]);
+          if (lane == 0 && !freerun) mbar_arrive_dep(&r_empty[slot], dep);
         }
         uint32_t acc[EPI_COLS];
 #pragma unroll

@@ -49,6 +49,8 @@ struct PairParams {
   int r_slots, r_slot_bytes;
   int tmem_cols;
   uint32_t idesc;
+  int no_ring;  // PG_PAIR_NORING (debug): fp32 residual read straight from global memory in E2
+  int no_pre;   // PG_PAIR_NOPRE (debug): accumulate input loaded at use instead of prefetched
 };
 
 __device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
@@ -233,7 +235,7 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
         }
       }
     }
-  } else if (warp == RES_WARP && p.r_slots > 0) {
+  } else if (warp == RES_WARP && p.r_slots > 0 && !p.no_ring) {
     // ===== fp32 residual stream: one 128-row x C slot per row tile m =====
     const int pl = lane & 7, sub = lane >> 3;
     const int batch = min(min(MT, p.r_slots), 4);
@@ -315,7 +317,7 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
       constexpr int IPW = ITEMS / (E2_WARPS / 4);
       constexpr bool PRE32 = IPW * 4 <= 8;
       uint4 pre[8];
-      const bool pre16 = p.accin16 != nullptr, pre32 = PRE32 && p.accin32 != nullptr;
+      const bool pre16 = p.accin16 != nullptr && !p.no_pre, pre32 = PRE32 && p.accin32 != nullptr && !p.no_pre;
       if (pre16 || pre32) {
 #pragma unroll
         for (int ii = 0; ii < IPW; ++ii) {
@@ -349,7 +351,14 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
         const int t = o0 + o;
         const bool ok = o < p.MO && t < p.L;
         uint4 rq[4];
-        if (p.r_slots > 0) {
+        int ring_slot = -1;
+        if (p.r_slots > 0 && p.no_ring) {
+          if (ok) {
+            const uint4* g0 = reinterpret_cast<const uint4*>(p.res32) + (plane_base + (size_t)(cb * 2) * p.L + t) * 2;
+            const uint4* g1 = reinterpret_cast<const uint4*>(p.res32) + (plane_base + (size_t)(cb * 2 + 1) * p.L + t) * 2;
+            rq[0] = g0[0]; rq[1] = g0[1]; rq[2] = g1[0]; rq[3] = g1[1];
+          }
+        } else if (p.r_slots > 0) {
           const uint32_t sidx = j * (uint32_t)MT + (uint32_t)m;
           const uint32_t rslot = sidx % (uint32_t)p.r_slots;
           mbar_wait(&r_full[rslot], (sidx / (uint32_t)p.r_slots) & 1u);
@@ -359,8 +368,7 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
           rq[1] = *reinterpret_cast<const uint4*>(rs + 16);
           rq[2] = *reinterpret_cast<const uint4*>(rs + BM * 32);
           rq[3] = *reinterpret_cast<const uint4*>(rs + BM * 32 + 16);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&r_empty[rslot]);
+          ring_slot = (int)rslot;   // released below, once the loads have landed in registers
         } else {
           const uint8_t* ar = aw + (size_t)(cb * 2) * p.plane_bytes + (size_t)(o + p.h2 + p.h1) * 16;
           rq[0] = *reinterpret_cast<const uint4*>(ar);
@@ -368,6 +376,15 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
         }
         uint32_t acc[ECOLS];
         tmem_ld16(lane_taddr + b * (uint32_t)(MT * C) + (uint32_t)(m * C + cb * ECOLS), acc);
+        if (ring_slot >= 0) {
+          // The slot may be refilled (async proxy) as soon as r_empty completes, and an mbarrier arrive
+          // does not wait for this warp's outstanding shared-memory LOADS: make the arrive data-dependent
+          // on every loaded register so the scoreboard orders it after the loads.
+          uint32_t dep = rq[0].x ^ rq[1].x ^ rq[2].x ^ rq[3].x ^ rq[0].w ^ rq[1].w ^ rq[2].w ^ rq[3].w;
+          asm volatile("" : "+r"(dep));
+          __syncwarp();
+          if (lane == 0) mbar_arrive_dep(&r_empty[ring_slot], dep);
+        }
         if (ok) {
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
@@ -391,15 +408,15 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] *= p.out_scale;
             }
-            if (pre16) {
+            if (p.accin16) {
               float a[8];
-              unpack8(pre[2 * ii + jj], a);
+              unpack8(pre16 ? pre[2 * ii + jj] : *(reinterpret_cast<const uint4*>(p.accin16) + off), a);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] += a[i];
             }
             if (p.accin32) {
               uint4 a0, a1;
-              if (PRE32) {
+              if (PRE32 && pre32) {
                 a0 = pre[(4 * ii + 2 * jj) & 7];
                 a1 = pre[(4 * ii + 2 * jj + 1) & 7];
               } else {
@@ -510,6 +527,11 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
   p.tmp_plane_bytes = pl.tmp_plane_bytes; p.tmp_bytes = pl.tmp_bytes; p.w_tile_bytes = pl.w_tile_bytes;
   p.r_slots = pl.r_slots; p.r_slot_bytes = pl.r_slot_bytes; p.tmem_cols = pl.tmem_cols;
   p.idesc = make_idesc(BM, C);
+  static const int no_pre = [] { const char* e = getenv("PG_PAIR_NOPRE"); return e ? atoi(e) : 0; }();
+  p.no_pre = no_pre;
+  static const int no_ring = [] { const char* e = getenv("PG_PAIR_NORING"); return e ? atoi(e) : 0; }();
+  p.no_ring = no_ring;
+
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(pair_planes_kernel<MT, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -519,7 +541,10 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
   }
   int grid = device_sm_count();
   if (grid > p.total_tiles) grid = p.total_tiles;
+  static const int dbg_sync = [] { const char* e = getenv("PG_PAIR_SYNC"); return e ? atoi(e) : 0; }();
+  if (dbg_sync & 1) cudaStreamSynchronize(s);
   pair_planes_kernel<MT, C><<<grid, NTHREADS, pl.smem, s>>>(m1, m2, p);
+  if (dbg_sync & 2) cudaStreamSynchronize(s);
   return cudaGetLastError();
 }
 

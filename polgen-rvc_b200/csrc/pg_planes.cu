@@ -125,6 +125,92 @@ __global__ void __launch_bounds__(256) noise_inject_planes_kernel(
   store8(a16 + i * 8, v);
 }
 
+
+// Tiled form for the strided stages (k = 2*stride taps, f16 stream): one block = 32 time rows x all C
+// channels of one batch row.  The source window, the [k][C] weights and the x tile are staged in shared
+// memory with coalesced loads; a lane owns one 8-channel chunk (weights: two conflict-free 16 B reads per
+// tap, source sample: a broadcast) and CP/8 rows, so every weight read feeds 8*CP/8 FMAs.
+constexpr int NRB = 32;   // rows per block
+template <int CP>
+__global__ void __launch_bounds__(256) noise_inject_tiled_kernel(
+    __half* __restrict__ x, const float* __restrict__ src, const float* __restrict__ wn,
+    const float* __restrict__ bn, int L, int Lsrc, int k, int stride, int pad, float slope) {
+  constexpr int C = CP * 8;
+  constexpr int NR = CP / 8;              // rows per thread
+  constexpr int XP = NRB * 16 + 16;       // x-tile plane pitch in bytes (bank-staggered)
+  extern __shared__ __align__(16) uint8_t nsm[];
+  float* ws = reinterpret_cast<float*>(nsm);                    // [k][C]
+  float* ss = ws + (size_t)k * C;                               // [(NRB-1)*stride + k]
+  uint8_t* xs = reinterpret_cast<uint8_t*>(ss + (((NRB - 1) * stride + k + 3) & ~3));   // [CP][NRB] x 16 B
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, t0 = blockIdx.x * NRB;
+  for (int i = tid; i < k * C; i += 256) ws[i] = wn[i];
+  const int win = (NRB - 1) * stride + k, s_first = t0 * stride - pad;
+  const float* sp = src + (size_t)b * Lsrc;
+  for (int i = tid; i < win; i += 256) {
+    const int n = s_first + i;
+    ss[i] = (n >= 0 && n < Lsrc) ? sp[n] : 0.f;
+  }
+  __half* xb = x + (size_t)b * CP * L * 8;
+  for (int i = tid; i < CP * NRB; i += 256) {
+    const int pl = i / NRB, r = i - pl * NRB;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (t0 + r < L) v = *reinterpret_cast<const uint4*>(xb + ((size_t)pl * L + t0 + r) * 8);
+    *reinterpret_cast<uint4*>(xs + pl * XP + r * 16) = v;
+  }
+  __syncthreads();
+  const int chunk = lane % CP, rg = lane / CP;
+  const int r0 = warp * (NRB / 8) + rg * NR;
+  float acc[NR][8];
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr) load8(bn + chunk * 8, acc[rr]);
+  for (int j = 0; j < k; ++j) {
+    float w[8];
+    load8(ws + (size_t)j * C + chunk * 8, w);
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr) {
+      const float sv = ss[(r0 + rr) * stride + j];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[rr][q] = fmaf(w[q], sv, acc[rr][q]);
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr) {
+    uint8_t* cell = xs + chunk * XP + (r0 + rr) * 16;
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(cell), v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float a = v[q] + acc[rr][q];
+      v[q] = a > 0.f ? a : a * slope;
+    }
+    *reinterpret_cast<uint4*>(cell) = pack8(v);
+  }
+  __syncthreads();
+  for (int i = tid; i < CP * NRB; i += 256) {
+    const int pl = i / NRB, r = i - pl * NRB;
+    if (t0 + r < L)
+      *reinterpret_cast<uint4*>(xb + ((size_t)pl * L + t0 + r) * 8) = *reinterpret_cast<const uint4*>(xs + pl * XP + r * 16);
+  }
+}
+
+template <int CP>
+cudaError_t launch_noise_tiled(__half* x, const float* src, const float* wn, const float* bn, int B, int L,
+                               int Lsrc, int k, int stride, int pad, float slope, cudaStream_t s) {
+  const size_t smem = sizeof(float) * ((size_t)k * CP * 8 + (((NRB - 1) * stride + k + 3) & ~3)) +
+                      (size_t)CP * (NRB * 16 + 16);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(noise_inject_tiled_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  dim3 grid((L + NRB - 1) / NRB, B);
+  noise_inject_tiled_kernel<CP><<<grid, 256, smem, s>>>(x, src, wn, bn, L, Lsrc, k, stride, pad, slope);
+  return cudaGetLastError();
+}
+
 // nsf.py:142-143  wave = tanh(conv_post(leaky_relu(x)))  (Cout = 1, no bias); one thread per sample
 template <typename T, int K>
 __global__ void __launch_bounds__(256) conv_post_planes_kernel(const T* __restrict__ x,
@@ -198,6 +284,17 @@ cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, const flo
                                        const float* bn, int B, int L, int C, int Lsrc, int k, int stride,
                                        int pad, float slope, cudaStream_t s) {
   if (C % 8) return cudaErrorInvalidValue;
+  if (dt == DT_F16 && a16 == x && k > 1) {   // strided stages of the f16 stream: shared-memory tiled kernel
+    const size_t smem_need = 4 * ((size_t)k * C + (NRB - 1) * stride + k + 4) + (size_t)(C / 8) * (NRB * 16 + 16);
+    if (smem_need <= 200 * 1024) {
+      switch (C / 8) {
+        case 32: return launch_noise_tiled<32>(reinterpret_cast<__half*>(x), src, wn, bn, B, L, Lsrc, k, stride, pad, slope, s);
+        case 16: return launch_noise_tiled<16>(reinterpret_cast<__half*>(x), src, wn, bn, B, L, Lsrc, k, stride, pad, slope, s);
+        case 8: return launch_noise_tiled<8>(reinterpret_cast<__half*>(x), src, wn, bn, B, L, Lsrc, k, stride, pad, slope, s);
+        default: break;
+      }
+    }
+  }
   const size_t n = (size_t)B * (C / 8) * L;
   if (dt == DT_F32)
     noise_inject_planes_kernel<float><<<blocks_for(n), 256, 0, s>>>(reinterpret_cast<float*>(x), a16, src, wn, bn,

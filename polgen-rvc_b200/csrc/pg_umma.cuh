@@ -23,6 +23,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive that is data-dependent on `dep` (a value derived from registers loaded from the buffer being
+// released): the arrive cannot issue before those loads have written their registers
+__device__ __forceinline__ void mbar_arrive_dep(uint64_t* bar, uint32_t dep) {
+  asm volatile(
+      "{\n\t.reg .b32 t;\n\t"
+      "and.b32 t, %1, 0;\n\t"
+      "add.u32 t, t, %0;\n\t"
+      "mbarrier.arrive.shared::cta.b64 _, [t];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(dep)
+      : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
