@@ -419,6 +419,7 @@ int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_d
     a.w16s = w.w16s;
   }
   a.tapmask = w.tapmask;
+  a.out_f32 = out_dt == DT_F32 ? 1 : 0;
   const bool umma = !force_simt && w.w16 && umma_conv_supported(a);
   const bool prof = (h->cfg.flags & PG_FLAG_PROFILE) != 0;
   pg_handle_s::ProfRec rec;

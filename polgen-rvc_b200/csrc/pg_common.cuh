@@ -34,6 +34,7 @@ struct ConvArgs {
   const void* w16 = nullptr;         // UMMA: [K][Cout][Cin] f16 (K-major tiles)
   const void* w16s = nullptr;        // UMMA split mode: [2][K][Cout][Cin] f16, hi then lo (w = hi + lo)
   int split = 0;                     // two-term f16 operands, 3 MMAs per product (fp32-class accuracy)
+  int out_f32 = 0;                   // set by the launcher: f32 outputs need the wider epilogue staging
   const float* bias = nullptr;       // [Cout]
   const float* bbias = nullptr; int bbias_ld = 0;   // [B][bbias_ld]
   float in_slope = 1.f; int in_mask = 0;

@@ -409,7 +409,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
     constexpr int RV = VecIO<TOut>::RAW;   // uint4 per 8 output channels
     constexpr int BV = 4 * RV;             // uint4 per 32-column block of one row
     constexpr bool STAGED = RV == 1;
-    constexpr int EP = 80;                 // staging row pitch in bytes
+    constexpr int EP = STAGED ? 80 : 144;  // staging row pitch in bytes (f16: 64 B rows, f32: 128 B rows; bank-staggered)
     const int quarter = warp & 3, half = warp >> 2;
     const int n_blocks = p.NT / 32;        // 32-column blocks in the tile
     uint8_t* stg = epi_stage + (size_t)warp * (32 * EP);
@@ -541,8 +541,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
               for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
               *reinterpret_cast<uint4*>(stg + lane * EP + q8 * 16) = q;
             } else {
-              if (row_ok && !(p.debug & 2)) VecIO<TOut>::store8(yrow + c, v);
+              // f32 outputs: stage the row's 32 B so the block leaves as full 128 B rows (below)
+              *reinterpret_cast<float4*>(stg + lane * EP + q8 * 32) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(stg + lane * EP + q8 * 32 + 16) = make_float4(v[4], v[5], v[6], v[7]);
             }
+          }
+          if constexpr (!STAGED) {
+            __syncwarp();
+            if (!(p.debug & 2)) {
+              TOut* yb = reinterpret_cast<TOut*>(p.y) + ((size_t)tc.b * p.L + wrow0) * p.y_ld + p.y_coff + n0 + c0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int id = i * 32 + lane, r = id >> 3, c16 = id & 7;
+                if (wrow0 + r < p.L)
+                  *reinterpret_cast<float4*>(yb + (size_t)r * p.y_ld + c16 * 4) =
+                      *reinterpret_cast<const float4*>(stg + r * EP + c16 * 16);
+              }
+            }
+            __syncwarp();   // staging is rewritten by the next block
           }
           if constexpr (STAGED) {
             __syncwarp();
@@ -692,7 +708,7 @@ bool make_plan_nt(const ConvArgs& a, int NT, Plan* out) {
   const int n_groups = (planes + PG - 1) / PG;
   const int stage_bytes = NT * KC * 2 * (a.split ? 2 : 1);
   static const int forced_mt = env_int("PG_UMMA_MT"), no_resident = env_int("PG_UMMA_NORESIDENT");
-  const size_t fixed = 1024 + 1024 + EPI_WARPS * 32 * 80 + 256;   // align slack, barriers, epilogue staging
+  const size_t fixed = 1024 + 1024 + EPI_WARPS * 32 * (a.out_f32 ? 144 : 80) + 256;   // align slack, barriers, epilogue staging
   const size_t budget = (size_t)226 * 1024;
   const int n_chunks = a.Cin / KC;
   const size_t w_all = (size_t)n_chunks * a.K * stage_bytes;
@@ -840,7 +856,9 @@ bool umma_conv_supported(const ConvArgs& a) {
   return make_plan(a, &pl);
 }
 
-cudaError_t launch_conv_umma(const ConvArgs& a, DType in_dt, DType out_dt, cudaStream_t s) {
+cudaError_t launch_conv_umma(const ConvArgs& a_in, DType in_dt, DType out_dt, cudaStream_t s) {
+  ConvArgs a = a_in;
+  a.out_f32 = out_dt == DT_F32 ? 1 : 0;
   Plan pl;
   if (!umma_conv_supported(a) || !make_plan(a, &pl)) return cudaErrorInvalidValue;
   if (in_dt == DT_F16 && out_dt == DT_F16) return launch_mt<__half, __half>(a, pl, s);
