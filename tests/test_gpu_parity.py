@@ -372,3 +372,23 @@ def test_repeatable_across_interleaved_calls():
         eng.infer(*one, None, None, 2 + trial, want_aux=False)
         again, _ = eng.infer(*one, None, None, 1, want_aux=False)
         assert torch.equal(again, ref), trial
+
+
+@pytest.mark.parametrize("name", ["v2-40k", "v2-32k", "v1-40k"])
+def test_other_configs_medium_clip_vs_oracle_and_unfused(name):
+    """The remaining BASELINE configs (different upsample rates / kernel sizes, 256-dim features) on an
+    odd 2.57 s clip: waveform parity against the CPU oracle at the BASELINE tolerance, and the fused
+    decoder path against its kernel-per-conv twin."""
+    import polgen_rvc_b200 as pg
+    from polgen_rvc_b200 import _lib
+    from oracle import rvc_oracle as orc
+    cfg = pg.CONFIGS[name]
+    sd = pg.synth_weights(cfg, seed=17)
+    inputs = pg.synth_inputs(cfg, 1, 257, seed=17)
+    noise = pg.synth_noise(cfg, 1, 257, seed=17)
+    o, *_ = orc.infer(sd, cfg, *inputs, *noise)
+    wave, _ = _run(_engine(cfg, sd), inputs, noise)
+    assert snr_db(wave, o[:, 0]) >= WAVE_SNR_DB
+    assert (wave - o[:, 0]).abs().max().item() <= WAVE_MAXABS
+    twin, _ = _run(_engine(cfg, sd, _lib.PG_FLAG_NO_PAIR_FUSION), inputs, noise)
+    assert snr_db(wave, twin) >= 90.0
