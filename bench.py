@@ -60,9 +60,11 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        if os.environ.get("PG_BENCH_SAMPLER_MS", "50") == "0":
+            return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("PG_BENCH_SAMPLER_MS", "50"),
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -164,6 +166,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # the sampler process lives for the whole run: nvidia-smi attaching to / detaching from the driver
+    # stalls CUDA calls of this process for tens to hundreds of ms, so neither may fall near a timed region
+    sampler = ClockSampler(local)
+    sampler.start()
+
     cfg = pg.CONFIGS[args.config]
     seg_frames = clip_segments(cfg, seed=rank)
     sd = pg.synth_weights(cfg, seed=0)
@@ -173,17 +180,18 @@ def run_ours(args):
     # a profiled single engine for the per-kernel roofline pass (sequential, so CUDA-event durations
     # of one kernel are not inflated by another lane's kernels sharing the SMs)
     eng = pg.Engine(cfg, folded, local, _lib.PG_FLAG_PROFILE)
-    segs_dev, segs_host, waves_host = [], [], []
+    segs_dev, segs_host, waves_host, waves_dev = [], [], [], []
     for i, T in enumerate(seg_frames):
         inp = pg.synth_inputs(cfg, 1, T, seed=100 * rank + i)
         segs_host.append([t.pin_memory() for t in inp])
         segs_dev.append([t.to(dev) for t in inp])
         waves_host.append(torch.empty(1, T * cfg.upp, dtype=torch.float32).pin_memory())
+        waves_dev.append(torch.empty(1, T * cfg.upp, dtype=torch.float32, device=dev))
     audio_s = sum(seg_frames) / 100.0
     flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step_device():
-        return sched.decode(segs_dev)
+        return sched.decode(segs_dev, out=waves_dev)
 
     def barrier():
         if world > 1:
@@ -191,27 +199,37 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)        # also warms the fill kernel (lazy module load would land in step 1)
         step_device()
     torch.cuda.synchronize()
 
-    # ---- timed region: K steps, device time per step via CUDA events, L2 flushed between steps
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
+    # ---- timed region: K steps back to back (a stream of clips: the scheduler's lanes run on from one
+    # step into the next, so the encoder phase of one clip overlaps the decoder phase of another);
+    # device time by CUDA events around the K steps, L2 flushed once per step
     barrier()
     t_wall0 = time.time()
-    evs = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t_cpu0 = time.perf_counter()
+    marks, host_marks = [], []
     for _ in range(args.steps):
         flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step_device()
-        e1.record()
-        evs.append((e0, e1))
+        sched.decode(segs_dev, out=waves_dev, join=not args.pipelined)
+        if os.environ.get("PG_BENCH_TRACE"):
+            sched.join()
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
+            host_marks.append(round((time.perf_counter() - t_cpu0) * 1e3, 2))
+    sched.join()
+    e1.record()
+    host_enqueue_ms = (time.perf_counter() - t_cpu0) * 1e3 / args.steps
+    if marks:
+        torch.cuda.synchronize()
+        print("device ms at end of each step:", [round(e0.elapsed_time(m), 2) for m in marks],
+              "\nhost ms when each step was enqueued:", host_marks, file=sys.stderr)
     barrier()
     t_wall1 = time.time()
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    clocks = sampler.stop(t_wall0, t_wall1)
+    dev_ms = e0.elapsed_time(e1)
     per_step_launches = sched.launch_count()
 
     # ---- roofline pass: the same segments, sequentially on the profiled engine (L2 flushed per step)
@@ -239,14 +257,21 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    trace = []
     for _ in range(args.steps):
-        sched.decode(segs_host, host_out=waves_host)
+        t_s = time.perf_counter()
+        sched.decode(segs_host, host_out=waves_host, join=not args.pipelined)
+        trace.append(round((time.perf_counter() - t_s) * 1e3, 2))
+    sched.join(host_sync=True)
     e1.record()
+    if os.environ.get("PG_BENCH_TRACE"):
+        print("e2e host ms per step:", trace, file=sys.stderr)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     h2d = sum(sum(t.numel() * t.element_size() for t in s) for s in segs_host)
     d2h = sum(w.numel() * 4 for w in waves_host)
 
+    clocks = sampler.stop(t_wall0, t_wall1)
     t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -278,11 +303,13 @@ def run_ours(args):
                                    f"one clip per GPU per step",
                        "audio_s_per_step_per_gpu": audio_s, "l2": "flushed between steps (256 MiB write)",
                        "segment_lanes_per_gpu": args.lanes,
+                       "steps_pipelined": bool(args.pipelined),
                        "parallelism": f"segment-sharded x{world}, no collective"},
             "roofline": roofline,
             "e2e": {"value": total_audio / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": per_step_launches * args.steps,
+            "host_enqueue_ms_per_step": host_enqueue_ms,
             "clocks": clocks,
             "generator_tflops": cfg.generator_flops_per_frame() * 100 * total_audio / (dev_ms_max * 1e-3) / 1e12,
         }
@@ -314,6 +341,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="v2-48k", choices=["v2-48k", "v2-40k", "v2-32k", "v1-40k"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-pipelined", dest="pipelined", action="store_false",
+                    help="join the scheduler's lanes after every step instead of streaming clip after clip")
     ap.add_argument("--lanes", type=int, default=2, help="engines/streams per GPU the clip's segments are dealt over")
     ap.add_argument("--table", default="", help="write the per-layer-shape conv timing table to gpurun_out/<name>")
     args = ap.parse_args()

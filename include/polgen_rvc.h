@@ -87,6 +87,7 @@ typedef struct pg_config {
 #define PG_FLAG_PROFILE 4      /* CUDA events around every conv launch (pg_profile_read) */
 #define PG_FLAG_NO_PAIR_FUSION 32 /* run every ResBlock conv as its own kernel (validation twin of the fused pair kernel) */
 #define PG_FLAG_LEGACY_DECODER 16 /* decoder on the time-major tcgen05 kernel (A/B comparison aid) */
+#define PG_FLAG_NO_GRAPHS 64    /* launch every kernel of pg_infer directly (default: a CUDA graph per (B,T) is captured on the second call of a shape and replayed afterwards when the stream is capturable and the noise is device-drawn) */
 #define PG_FLAG_F16_LATENTS 8  /* TextEncoder / flow GEMMs with single-pass f16 tensor-core operands (default: fp32-accurate) */
 
 typedef struct pg_handle_s* pg_handle;
@@ -116,7 +117,13 @@ size_t pg_workspace_bytes(pg_handle h, int B, int T);
  * All rows of the batch share T; lengths[b] <= T mask the encoder/flow exactly
  * as sequence_mask does (commons.py:89-93).  eps_* == NULL draws the noise on
  * device from Philox(seed).  Enqueued on `stream` (a cudaStream_t); returns
- * without synchronising. */
+ * without synchronising.
+ * On a capturable stream (not the legacy default stream) with device-drawn noise the
+ * call is staged: inputs are copied into the handle's fixed buffers, the launch sequence
+ * runs as a CUDA graph per (B,T) (captured on the second call of a shape) and the
+ * waveform is copied out -- phone/lengths/pitch/f0/sid/wave may then also be PINNED HOST
+ * pointers (the copies are cudaMemcpyDefault on `stream`).  PG_FLAG_NO_GRAPHS, explicit
+ * eps_* or the legacy stream give direct launches on device pointers. */
 int pg_infer(pg_handle h, void* stream, int B, int T,
              const float* phone_dev, const int64_t* lengths_dev,
              const int64_t* pitch_dev, const float* f0_dev, const int64_t* sid_dev,
@@ -162,8 +169,12 @@ int pg_generator(pg_handle h, void* stream, int B, int T, const float* z_dev,
 int64_t pg_debug_fetch(pg_handle h, void* stream, const char* tap, float* dst_dev,
                        int64_t capacity, int64_t* shape_out);
 
-/* Statistics of the last call: number of kernels this library launched. */
+/* Statistics of the last call: number of kernels this library launched (for a replayed CUDA
+ * graph: the kernel nodes of the graph plus the seed store). */
 int64_t pg_launch_count(pg_handle h);
+
+/* Number of (B,T) shapes of pg_infer currently held as instantiated CUDA graphs. */
+int pg_graph_count(pg_handle h);
 
 /* PG_FLAG_PROFILE: device time, algorithmic FLOPs (2*B*L*Cin*Cout*K) and launch count of the
  * conv launches since the previous read, per kernel class: [0] tcgen05 channel-plane conv (decoder),

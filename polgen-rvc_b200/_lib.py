@@ -21,6 +21,7 @@ PG_FLAG_PROFILE = 4
 PG_FLAG_F16_LATENTS = 8
 PG_FLAG_LEGACY_DECODER = 16
 PG_FLAG_NO_PAIR_FUSION = 32
+PG_FLAG_NO_GRAPHS = 64
 PG_F32 = 0
 
 
@@ -56,6 +57,7 @@ SYMBOLS = {
     "pg_generator": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "pg_debug_fetch": (C.c_int64, [_P, _P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "pg_launch_count": (C.c_int64, [_P]),
+    "pg_graph_count": (C.c_int, [_P]),
     "pg_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pg_profile_table": (_I, [_P, C.POINTER(C.c_double), _I]),
     "pg_op_conv1d_f16": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _I,

@@ -106,6 +106,13 @@ struct pg_handle_s {
   // pinned/device staging for pg_infer_host
   DevBuf host_stage;
 
+  // CUDA graphs of pg_infer, one per (B, T): the ~60 launches per 100 frames of a segment are
+  // captured on the second call of a shape and replayed afterwards over the fixed staging
+  // buffers in `io` (inputs copied in, waveform copied out, Philox seed read from memory)
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int uses = 0; bool failed = false; };
+  std::map<std::pair<int, int>, GraphEntry> graphs;
+  DevBuf io;
+
   // PG_FLAG_PROFILE: CUDA events around every conv launch, per kernel class
   struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; int shape[5]; };
   std::map<std::vector<int>, std::vector<double>> prof_table;   // (cls,Cin,N,K,dil,MT..) -> {launches, ms, flops}
@@ -342,8 +349,17 @@ Ws plan_ws(const pg_config& c, int B, int T) {
   return w;
 }
 
+// captured graphs hold workspace / staging addresses: drop them when either buffer moves
+void invalidate_graphs(pg_handle h) {
+  for (auto& kv : h->graphs) {
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    kv.second.exec = nullptr;
+  }
+}
+
 int ensure_ws(pg_handle h, size_t bytes) {
   if (h->ws.bytes >= bytes) return PG_OK;
+  invalidate_graphs(h);
   if (h->ws.p) PG_CUDA_CHECK(cudaFree(h->ws.p));
   h->ws.p = nullptr;
   h->ws.bytes = 0;
@@ -1113,6 +1129,114 @@ static int prepare(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const
   return PG_OK;
 }
 
+// the launch sequence of Synthesizer.infer (synthesizers.py:162-188) on stream s
+static int infer_body(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const float* phone,
+                      const int64_t* lengths, const int64_t* pitch, const float* f0, const int64_t* sid,
+                      const float* eps_zp, const float* eps_src, uint64_t seed, const uint64_t* seed_dev,
+                      float* wave) {
+  const pg_config& c = h->cfg;
+  PG_TRY(prepare(h, s, w, B, T, lengths, pitch, sid));
+  PG_TRY(run_text_encoder(h, s, w, B, T, phone));
+  const int C = c.inter_channels;
+  float* z = at<float>(h, w.z);
+  PG_LAUNCH(h, launch_reparam(at<float>(h, w.stats), eps_zp, seed, seed_dev, at<int>(h, w.lens),
+                              at<float>(h, w.m_p), at<float>(h, w.logs_p), at<float>(h, w.z_p), z, B,
+                              T, C, s));
+  PG_TRY(run_flow(h, s, w, B, T, z));
+  float* source = at<float>(h, w.source);
+  PG_LAUNCH(h, launch_source(f0, eps_src, seed, seed_dev, h->src_w, h->src_b, at<double>(h, w.phase),
+                             source, nullptr, B, T, h->upp, c.sr, s));
+  ++h->launches;   // launch_source issues two kernels
+  PG_TRY(record_tap(h, s, "source", source, DT_F32, B, (int64_t)T * h->upp, 1));
+  PG_TRY(run_decoder(h, s, w, B, T, z, source, wave));
+  return PG_OK;
+}
+
+namespace {
+struct IoPtrs {
+  float* phone; int64_t* len; int64_t* pitch; float* f0; int64_t* sid; uint64_t* seed; float* wave;
+  size_t n_phone, n_len, n_pitch, n_f0, n_sid, n_wave, total;
+};
+IoPtrs io_layout(const pg_config& c, int upp, char* base, int B, int T) {
+  IoPtrs p;
+  const size_t BT = (size_t)B * T;
+  p.n_phone = BT * c.input_dim * sizeof(float);
+  p.n_len = B * sizeof(int64_t);
+  p.n_pitch = BT * sizeof(int64_t);
+  p.n_f0 = BT * sizeof(float);
+  p.n_sid = B * sizeof(int64_t);
+  p.n_wave = BT * upp * sizeof(float);
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  size_t off = 0;
+  auto take = [&](size_t n) { char* q = base + off; off += al(n); return q; };
+  p.phone = reinterpret_cast<float*>(take(p.n_phone));
+  p.len = reinterpret_cast<int64_t*>(take(p.n_len));
+  p.pitch = reinterpret_cast<int64_t*>(take(p.n_pitch));
+  p.f0 = reinterpret_cast<float*>(take(p.n_f0));
+  p.sid = reinterpret_cast<int64_t*>(take(p.n_sid));
+  p.seed = reinterpret_cast<uint64_t*>(take(sizeof(uint64_t)));
+  p.wave = reinterpret_cast<float*>(take(p.n_wave));
+  p.total = off;
+  return p;
+}
+}  // namespace
+
+// pg_infer over the handle's fixed staging buffers: inputs (device or pinned host memory) are copied
+// in, the waveform is copied out, and the launch sequence between them is a CUDA graph per (B, T) --
+// launched directly on the first call of a shape (lazy one-time setup is not capturable), captured on
+// the second and replayed afterwards.  A refused capture falls back to direct launches for good.
+static int infer_staged(pg_handle h, pg_handle_s::GraphEntry& ge, cudaStream_t s, const Ws& w, int B, int T,
+                        const float* phone, const int64_t* lengths, const int64_t* pitch, const float* f0,
+                        const int64_t* sid, uint64_t seed, float* wave) {
+  PG_TRY(ensure_ws(h, w.total));
+  const size_t need = io_layout(h->cfg, h->upp, nullptr, B, T).total;
+  if (h->io.bytes < need) {
+    invalidate_graphs(h);
+    if (h->io.p) PG_CUDA_CHECK(cudaFree(h->io.p));
+    h->io.p = nullptr;
+    h->io.bytes = 0;
+    PG_CUDA_CHECK(cudaMalloc(&h->io.p, need));
+    h->io.bytes = need;
+  }
+  const IoPtrs io = io_layout(h->cfg, h->upp, reinterpret_cast<char*>(h->io.p), B, T);
+  if (!ge.exec && !ge.failed && ge.uses >= 1) {
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      h->launches = 0;
+      const int rc = infer_body(h, s, w, B, T, io.phone, io.len, io.pitch, io.f0, io.sid, nullptr, nullptr,
+                                0, io.seed, io.wave);
+      cudaError_t e = cudaStreamEndCapture(s, &graph);
+      if (rc == PG_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&ge.exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (rc != PG_OK || e != cudaSuccess || !ge.exec) {
+        ge.exec = nullptr;
+        ge.failed = true;
+      }
+      ge.launches = h->launches;
+    } else {
+      ge.failed = true;
+    }
+    cudaGetLastError();
+  }
+  ++ge.uses;
+  PG_CUDA_CHECK(cudaMemcpyAsync(io.phone, phone, io.n_phone, cudaMemcpyDefault, s));
+  PG_CUDA_CHECK(cudaMemcpyAsync(io.len, lengths, io.n_len, cudaMemcpyDefault, s));
+  PG_CUDA_CHECK(cudaMemcpyAsync(io.pitch, pitch, io.n_pitch, cudaMemcpyDefault, s));
+  PG_CUDA_CHECK(cudaMemcpyAsync(io.f0, f0, io.n_f0, cudaMemcpyDefault, s));
+  PG_CUDA_CHECK(cudaMemcpyAsync(io.sid, sid, io.n_sid, cudaMemcpyDefault, s));
+  if (ge.exec) {
+    h->launches = ge.launches;
+    PG_LAUNCH(h, launch_set_seed(io.seed, seed, s));
+    PG_CUDA_CHECK(cudaGraphLaunch(ge.exec, s));
+  } else {
+    h->launches = 0;
+    PG_TRY(infer_body(h, s, w, B, T, io.phone, io.len, io.pitch, io.f0, io.sid, nullptr, nullptr, seed,
+                      nullptr, io.wave));
+  }
+  PG_CUDA_CHECK(cudaMemcpyAsync(wave, io.wave, io.n_wave, cudaMemcpyDefault, s));
+  return PG_OK;
+}
+
 int pg_infer(pg_handle h, void* stream, int B, int T, const float* phone, const int64_t* lengths,
              const int64_t* pitch, const float* f0, const int64_t* sid, const float* eps_zp,
              const float* eps_src, uint64_t seed, float* wave, float* aux) {
@@ -1124,29 +1248,32 @@ int pg_infer(pg_handle h, void* stream, int B, int T, const float* phone, const 
   const pg_config& c = h->cfg;
   const Ws w = plan_ws(c, B, T);
   h->launches = 0;
-  PG_TRY(prepare(h, s, w, B, T, lengths, pitch, sid));
-  PG_TRY(run_text_encoder(h, s, w, B, T, phone));
-  const int C = c.inter_channels;
-  float* z = at<float>(h, w.z);
-  PG_LAUNCH(h, launch_reparam(at<float>(h, w.stats), eps_zp, seed, at<int>(h, w.lens),
-                              at<float>(h, w.m_p), at<float>(h, w.logs_p), at<float>(h, w.z_p), z, B,
-                              T, C, s));
-  PG_TRY(run_flow(h, s, w, B, T, z));
-  float* source = at<float>(h, w.source);
-  PG_LAUNCH(h, launch_source(f0, eps_src, seed, h->src_w, h->src_b, at<double>(h, w.phase), source,
-                             nullptr, B, T, h->upp, c.sr, s));
-  ++h->launches;   // launch_source issues two kernels
-  PG_TRY(record_tap(h, s, "source", source, DT_F32, B, (int64_t)T * h->upp, 1));
-  PG_TRY(run_decoder(h, s, w, B, T, z, source, wave));
+  // graph replay: device-drawn noise only, a capturable (non-legacy) stream, no per-launch instrumentation
+  const bool graphable = !(c.flags & (PG_FLAG_PROFILE | PG_FLAG_KEEP_TAPS | PG_FLAG_NO_GRAPHS)) && !eps_zp &&
+                         !eps_src && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+  int rc;
+  if (graphable)
+    rc = infer_staged(h, h->graphs[std::make_pair(B, T)], s, w, B, T, phone, lengths, pitch, f0, sid, seed, wave);
+  else
+    rc = infer_body(h, s, w, B, T, phone, lengths, pitch, f0, sid, eps_zp, eps_src, seed, nullptr, wave);
+  if (rc != PG_OK) return rc;
   if (aux) {
+    const int C = c.inter_channels;
     const size_t n = (size_t)B * T * C * sizeof(float);
     char* a = reinterpret_cast<char*>(aux);
-    PG_CUDA_CHECK(cudaMemcpyAsync(a, z, n, cudaMemcpyDeviceToDevice, s));
+    PG_CUDA_CHECK(cudaMemcpyAsync(a, at<float>(h, w.z), n, cudaMemcpyDeviceToDevice, s));
     PG_CUDA_CHECK(cudaMemcpyAsync(a + n, at<float>(h, w.z_p), n, cudaMemcpyDeviceToDevice, s));
     PG_CUDA_CHECK(cudaMemcpyAsync(a + 2 * n, at<float>(h, w.m_p), n, cudaMemcpyDeviceToDevice, s));
     PG_CUDA_CHECK(cudaMemcpyAsync(a + 3 * n, at<float>(h, w.logs_p), n, cudaMemcpyDeviceToDevice, s));
   }
   return PG_OK;
+}
+
+int pg_graph_count(pg_handle h) {
+  if (!h) return 0;
+  int n = 0;
+  for (auto& kv : h->graphs) n += kv.second.exec != nullptr;
+  return n;
 }
 
 int pg_infer_host(pg_handle h, int B, int T, const float* phone, const int64_t* lengths,
@@ -1202,7 +1329,7 @@ int pg_text_encoder(pg_handle h, void* stream, int B, int T, const float* phone,
   PG_TRY(run_text_encoder(h, s, w, B, T, phone));
   // split stats with eps == 0: z_p/z are scratch
   PG_CUDA_CHECK(cudaMemsetAsync(at<float>(h, w.fa), 0, sizeof(float) * (size_t)B * T * h->cfg.inter_channels, s));
-  PG_LAUNCH(h, launch_reparam(at<float>(h, w.stats), at<float>(h, w.fa), 0, at<int>(h, w.lens), m_p,
+  PG_LAUNCH(h, launch_reparam(at<float>(h, w.stats), at<float>(h, w.fa), 0, nullptr, at<int>(h, w.lens), m_p,
                               logs_p, at<float>(h, w.z_p), at<float>(h, w.z), B, T,
                               h->cfg.inter_channels, s));
   return PG_OK;
@@ -1232,8 +1359,8 @@ int pg_source(pg_handle h, void* stream, int B, int T, const float* f0, const fl
   const Ws w = plan_ws(h->cfg, B, T);
   h->launches = 0;
   PG_TRY(ensure_ws(h, w.total));
-  PG_LAUNCH(h, launch_source(f0, eps_src, seed, h->src_w, h->src_b, at<double>(h, w.phase), source,
-                             sine, B, T, h->upp, h->cfg.sr, s));
+  PG_LAUNCH(h, launch_source(f0, eps_src, seed, nullptr, h->src_w, h->src_b, at<double>(h, w.phase),
+                             source, sine, B, T, h->upp, h->cfg.sr, s));
   ++h->launches;
   return PG_OK;
 }
@@ -1337,6 +1464,8 @@ int pg_destroy(pg_handle h) {
     if (kv.second.p) cudaFree(kv.second.p);
   if (h->ws.p) cudaFree(h->ws.p);
   if (h->host_stage.p) cudaFree(h->host_stage.p);
+  invalidate_graphs(h);
+  if (h->io.p) cudaFree(h->io.p);
   for (auto& r : h->prof) {
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);

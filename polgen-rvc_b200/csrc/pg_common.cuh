@@ -138,15 +138,16 @@ cudaError_t launch_rel_attention_mma(const float* qkv, const float* rel_k, const
                                      const int* lens, float* out, void* scratch, int B, int T, int H,
                                      int n_heads, int window, cudaStream_t s);
 // z_p = (m + exp(logs) * eps * 0.66666) * mask ; stats [B][T][2C] -> m, logs, z_p, z(copy)
-cudaError_t launch_reparam(const float* stats, const float* eps, uint64_t seed, const int* lens,
-                           float* m_p, float* logs_p, float* z_p, float* z, int B, int T, int C,
-                           cudaStream_t s);
+cudaError_t launch_reparam(const float* stats, const float* eps, uint64_t seed, const uint64_t* seed_dev,
+                           const int* lens, float* m_p, float* logs_p, float* z_p, float* z, int B,
+                           int T, int C, cudaStream_t s);
+cudaError_t launch_set_seed(uint64_t* dst, uint64_t seed, cudaStream_t s);
 // acts = tanh(a[:, :H]) * sigmoid(a[:, H:])
 cudaError_t launch_gate(const float* a, float* acts, int64_t rows, int H, cudaStream_t s);
 
 // harmonic source (pg_source.cu)
-cudaError_t launch_source(const float* f0, const float* eps, uint64_t seed, float lin_w, float lin_b,
-                          double* frame_phase, float* source, float* sine, int B, int T, int upp,
+cudaError_t launch_source(const float* f0, const float* eps, uint64_t seed, const uint64_t* seed_dev,
+                          float lin_w, float lin_b, double* frame_phase, float* source, float* sine, int B, int T, int upp,
                           int sr, cudaStream_t s);
 // x[b][t][c] += bn[c] + sum_j wn[c][j] * src[b][t*stride + j - pad]
 cudaError_t launch_noise_inject(void* x, DType dt, const float* src, const float* wn, const float* bn,

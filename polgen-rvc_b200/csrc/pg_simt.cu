@@ -477,7 +477,8 @@ cudaError_t launch_rel_attention(const float* qkv, const float* rel_k, const flo
 
 // synthesizers.py:174: z_p = (m_p + exp(logs_p) * randn * 0.66666) * x_mask
 __global__ void reparam_kernel(const float* __restrict__ stats, const float* __restrict__ eps,
-                               uint64_t seed, const int* __restrict__ lens, float* __restrict__ m_p,
+                               uint64_t seed, const uint64_t* __restrict__ seed_dev,
+                               const int* __restrict__ lens, float* __restrict__ m_p,
                                float* __restrict__ logs_p, float* __restrict__ z_p,
                                float* __restrict__ z, int B, int T, int C) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -492,7 +493,7 @@ __global__ void reparam_kernel(const float* __restrict__ stats, const float* __r
     e = eps[i];
   } else {
     curandStatePhilox4_32_10_t st;
-    curand_init(seed, i, 0, &st);
+    curand_init(seed_dev ? *seed_dev : seed, i, 0, &st);   // seed_dev: replayed CUDA graphs
     e = curand_normal(&st);
   }
   const float v = t < lens[b] ? m + __expf(lg) * e * 0.66666f : 0.f;
@@ -502,12 +503,20 @@ __global__ void reparam_kernel(const float* __restrict__ stats, const float* __r
   z[i] = v;
 }
 
-cudaError_t launch_reparam(const float* stats, const float* eps, uint64_t seed, const int* lens,
-                           float* m_p, float* logs_p, float* z_p, float* z, int B, int T, int C,
-                           cudaStream_t s) {
+cudaError_t launch_reparam(const float* stats, const float* eps, uint64_t seed, const uint64_t* seed_dev,
+                           const int* lens, float* m_p, float* logs_p, float* z_p, float* z, int B,
+                           int T, int C, cudaStream_t s) {
   const size_t total = (size_t)B * T * C;
-  reparam_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(stats, eps, seed, lens, m_p, logs_p,
-                                                                 z_p, z, B, T, C);
+  reparam_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(stats, eps, seed, seed_dev, lens, m_p,
+                                                                 logs_p, z_p, z, B, T, C);
+  return cudaGetLastError();
+}
+
+// per-call Philox seed of a replayed CUDA graph (the graph's kernels read it through seed_dev)
+__global__ void set_seed_kernel(uint64_t* dst, uint64_t seed) { *dst = seed; }
+
+cudaError_t launch_set_seed(uint64_t* dst, uint64_t seed, cudaStream_t s) {
+  set_seed_kernel<<<1, 1, 0, s>>>(dst, seed);
   return cudaGetLastError();
 }
 

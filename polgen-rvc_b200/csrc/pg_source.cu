@@ -62,11 +62,13 @@ __global__ void __launch_bounds__(256) frame_phase_kernel(const float* __restric
 }
 
 __global__ void source_kernel(const float* __restrict__ f0, const double* __restrict__ P,
-                              const float* __restrict__ eps, uint64_t seed, float lin_w, float lin_b,
+                              const float* __restrict__ eps, uint64_t seed,
+                              const uint64_t* __restrict__ seed_dev, float lin_w, float lin_b,
                               float* __restrict__ source, float* __restrict__ sine_out, int B, int T,
                               int upp, float sr) {
   const size_t L = (size_t)T * upp;
   const size_t total = (size_t)B * L;
+  if (seed_dev) seed = *seed_dev;   // replayed CUDA graphs read the per-call seed from memory
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const size_t b = i / L, n = i % L;
@@ -92,8 +94,8 @@ __global__ void source_kernel(const float* __restrict__ f0, const double* __rest
   }
 }
 
-cudaError_t launch_source(const float* f0, const float* eps, uint64_t seed, float lin_w, float lin_b,
-                          double* frame_phase, float* source, float* sine, int B, int T, int upp,
+cudaError_t launch_source(const float* f0, const float* eps, uint64_t seed, const uint64_t* seed_dev,
+                          float lin_w, float lin_b, double* frame_phase, float* source, float* sine, int B, int T, int upp,
                           int sr, cudaStream_t s) {
   frame_phase_kernel<<<B, 256, 0, s>>>(f0, frame_phase, T, upp, (float)sr);
   cudaError_t e = cudaGetLastError();
@@ -101,7 +103,7 @@ cudaError_t launch_source(const float* f0, const float* eps, uint64_t seed, floa
   const size_t total = (size_t)B * T * upp;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  source_kernel<<<(unsigned)blocks, 256, 0, s>>>(f0, frame_phase, eps, seed, lin_w, lin_b, source, sine,
+  source_kernel<<<(unsigned)blocks, 256, 0, s>>>(f0, frame_phase, eps, seed, seed_dev, lin_w, lin_b, source, sine,
                                                  B, T, upp, (float)sr);
   return cudaGetLastError();
 }

@@ -111,6 +111,10 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.pg_launch_count(self._h))
 
+    def graph_count(self) -> int:
+        """(B, T) shapes currently held as instantiated CUDA graphs (replayed from their 2nd call on)"""
+        return int(self.lib.pg_graph_count(self._h))
+
     def profile_read(self):
         """PG_FLAG_PROFILE: {class: (ms, flops, launches)} of the conv launches since the last read."""
         ms, fl, n = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_int64 * 3)()
@@ -127,11 +131,14 @@ class Engine:
         return [tuple(buf[8 * i + k] for k in range(8)) for i in range(n)]
 
     def infer(self, phone, lengths, pitch, f0, sid, eps_zp=None, eps_src=None, seed: int = 0,
-              want_aux: bool = True):
-        """Time-major tensors on this engine's GPU.  Returns (wave [B][L], aux [4][B][T][C] | None)."""
+              want_aux: bool = True, wave_out=None):
+        """Time-major tensors on this engine's GPU.  Returns (wave [B][L], aux [4][B][T][C] | None).
+        `wave_out` (optional) receives the waveform instead of a fresh tensor.  On a non-default
+        stream with device-drawn noise the call is staged (include/polgen_rvc.h: pg_infer), and the
+        inputs / `wave_out` may then be pinned CPU tensors."""
         B, T, _ = phone.shape
         dev = self._dev()
-        wave = torch.empty(B, T * self.cfg.upp, device=dev, dtype=torch.float32)
+        wave = wave_out if wave_out is not None else torch.empty(B, T * self.cfg.upp, device=dev, dtype=torch.float32)
         aux = torch.empty(4, B, T, self.cfg.inter_channels, device=dev, dtype=torch.float32) if want_aux else None
         _lib.check(self.lib.pg_infer(self._h, self._stream(), B, T, self._ptr(phone), self._ptr(lengths),
                                      self._ptr(pitch), self._ptr(f0), self._ptr(sid), self._ptr(eps_zp),
@@ -484,6 +491,8 @@ class SegmentScheduler:
         self.cfg = cfg
         self.device = int(device)
         self.engines = [Engine(cfg, weights, device, flags) for _ in range(max(1, lanes))]
+        # staged pg_infer (fixed I/O buffers + CUDA graph replay) accepts pinned host pointers
+        self._staged = not (flags & (_lib.PG_FLAG_NO_GRAPHS | _lib.PG_FLAG_PROFILE | _lib.PG_FLAG_KEEP_TAPS))
         with torch.cuda.device(self.device):
             self.streams = [torch.cuda.Stream(device=self.device) for _ in self.engines]
 
@@ -491,43 +500,62 @@ class SegmentScheduler:
         for e in self.engines:
             e.close()
 
-    def decode(self, segments, seeds=None, host_out=None):
+    def decode(self, segments, seeds=None, host_out=None, join=True, out=None):
         """segments: list of (phone, lengths, pitch, f0, sid) -- CUDA tensors, or pinned CPU tensors
-        (copied to the device on the lane's stream).  Returns the list of waveforms [B][T*upp]: CUDA
-        tensors, or the pinned CPU tensors of `host_out` filled by async D2H copies.  The caller's
-        current stream waits for every lane before this returns control to it (no host sync unless
-        host_out is given)."""
+        (copied to the device on the lane's stream).  Returns the list of waveforms [B][T*upp]: fresh
+        CUDA tensors, or the caller's buffers when given -- `host_out` (pinned CPU tensors, filled by
+        async D2H copies; the host is synchronised before returning) or `out` (preallocated CUDA
+        tensors: a steady stream of clips then makes no allocator calls at all).  The caller's current
+        stream waits for every lane before this returns control to it.  join=False (streaming use:
+        clip after clip) skips both joins, so the lanes run on into the next call and their phases
+        interleave freely; call join() before touching the results.  Inputs must then already be
+        complete on the device (or in pinned host memory)."""
         dev = torch.device("cuda", self.device)
         cur = torch.cuda.current_stream(self.device)
-        ev0 = torch.cuda.Event()
-        ev0.record(cur)
+        ev0 = None
+        if join:
+            ev0 = torch.cuda.Event()
+            ev0.record(cur)
+        dst = host_out if host_out is not None else out
         outs = [None] * len(segments)
         keep = []
         self.last_launches = 0
         for i, seg in enumerate(segments):
             lane = i % len(self.engines)
             st = self.streams[lane]
-            st.wait_event(ev0)
+            if ev0 is not None:
+                st.wait_event(ev0)
             with torch.cuda.stream(st):
-                args = [t if t.is_cuda else t.to(dev, non_blocking=True) for t in seg]
+                # pinned host tensors go straight to the library (its staged path copies them on the
+                # lane's stream); anything else pageable is first brought to the device by torch
+                args = [t.contiguous() if (t.is_cuda or (self._staged and t.is_pinned()))
+                        else t.to(dev, non_blocking=True) for t in seg]
                 keep.append(args)
                 seed = 0 if seeds is None else int(seeds[i])
-                wave, _ = self.engines[lane].infer(*args, None, None, seed, want_aux=False)
+                direct = dst is not None and dst[i].is_contiguous() and (
+                    dst[i].is_cuda or (self._staged and dst[i].is_pinned()))
+                wave, _ = self.engines[lane].infer(*args, None, None, seed, want_aux=False,
+                                                   wave_out=dst[i] if direct else None)
                 self.last_launches += self.engines[lane].launch_count()
-                if host_out is not None:
-                    host_out[i].copy_(wave, non_blocking=True)
-                    outs[i] = host_out[i]
-                else:
-                    outs[i] = wave
-                wave.record_stream(cur)
+                if dst is not None and not direct:
+                    dst[i].copy_(wave, non_blocking=True)
+                outs[i] = wave if dst is None else dst[i]
+                if dst is None:
+                    wave.record_stream(cur)
+        self._keep = getattr(self, "_keep", [])[-4 * len(self.engines):] + keep   # inputs stay alive
+        if join:
+            self.join(host_sync=host_out is not None)
+        return outs
+
+    def join(self, host_sync: bool = False):
+        """make the caller's current stream wait for every lane (and optionally the host too)"""
+        cur = torch.cuda.current_stream(self.device)
         for st in self.streams:
             ev = torch.cuda.Event()
             ev.record(st)
             cur.wait_event(ev)
-        if host_out is not None:
+        if host_sync:
             cur.synchronize()
-        self._keep = keep     # inputs stay alive until the next call
-        return outs
 
     def launch_count(self) -> int:
         """kernels launched by the last decode() call"""

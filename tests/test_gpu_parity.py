@@ -332,6 +332,52 @@ def test_segment_scheduler_matches_sequential():
     for g, w in zip(got_h, want):
         assert torch.equal(g, w)
     assert sched.launch_count() > 300
+    # caller-owned device buffers, streaming (join=False) over two clips, then one join
+    bufs = [torch.empty(1, T * cfg.upp, device=d) for T in frames]
+    for _ in range(2):
+        got_d = sched.decode([[t.to(d) for t in s] for s in segs], seeds=[7, 8, 9], out=bufs, join=False)
+    sched.join(host_sync=True)
+    assert all(g is b for g, b in zip(got_d, bufs))
+    for g, w in zip(got_d, want):
+        assert torch.equal(g.cpu(), w)
+    assert all(e.graph_count() >= 1 for e in sched.engines)
+
+
+def test_cuda_graph_replay_matches_direct_launches():
+    """pg_infer captures one CUDA graph per (B, T) on the second call of a shape (side stream, device
+    noise) and replays it afterwards: replays must be bit-identical to the directly launched twin
+    (PG_FLAG_NO_GRAPHS) for new inputs and new seeds, survive a workspace growth (graphs dropped and
+    re-captured) and leave explicit-noise / default-stream calls on the direct path."""
+    import polgen_rvc_b200 as pg
+    from polgen_rvc_b200 import _lib
+    cfg = pg.CONFIGS["v2-48k"]
+    sd = pg.synth_weights(cfg, seed=0)
+    folded = pg.fold_state_dict(sd)
+    d = _dev()
+    graphed = pg.Engine(cfg, folded, 0)
+    direct = pg.Engine(cfg, folded, 0, _lib.PG_FLAG_NO_GRAPHS)
+    st = torch.cuda.Stream()
+    calls = [(64, 1), (64, 2), (64, 3), (130, 4), (130, 5), (64, 6), (64, 7), (130, 8)]
+    for n, (T, seed) in enumerate(calls):
+        inp = [t.to(d) for t in pg.synth_inputs(cfg, 1, T, seed=50 + n)]
+        torch.cuda.synchronize()
+        with torch.cuda.stream(st):
+            a, aux_a = graphed.infer(*inp, None, None, seed, want_aux=True)
+            b, aux_b = direct.infer(*inp, None, None, seed, want_aux=True)
+        st.synchronize()
+        assert torch.equal(a, b), (T, seed)
+        assert all(torch.equal(x, y) for x, y in zip(aux_a, aux_b))
+    assert graphed.graph_count() == 2 and direct.graph_count() == 0
+    assert graphed.launch_count() > 150
+    # default (legacy) stream and explicit noise: direct launches, same numbers
+    inp = [t.to(d) for t in pg.synth_inputs(cfg, 1, 64, seed=60)]
+    w0 = graphed.infer(*inp, None, None, 11, want_aux=False)[0]
+    torch.cuda.synchronize()        # the two calls share the engine's workspace
+    with torch.cuda.stream(st):
+        w1 = graphed.infer(*inp, None, None, 11, want_aux=False)[0]
+    st.synchronize()
+    torch.cuda.synchronize()
+    assert torch.equal(w0, w1)
 
 
 def test_fused_pair_kernel_matches_unfused_path():
