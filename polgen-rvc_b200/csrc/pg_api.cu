@@ -492,7 +492,7 @@ int run_text_encoder(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, con
     } else {
       PG_LAUNCH(h, launch_rel_attention_mma(qkv, L.rel_k, L.rel_v, lens, att, at<char>(h, w.attn), B, T, H,
                                             c.n_heads, c.attn_window, s));
-      ++h->launches;   // prep + attention kernels
+      h->launches += 2;   // prep + split attention + merge kernels
     }
     a.x = att; a.x_ld = H; a.y = y; a.y_ld = H;
     PG_TRY(run_conv(h, s, a, L.o, DT_F32, DT_F32, true));

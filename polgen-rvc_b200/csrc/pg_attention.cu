@@ -9,6 +9,11 @@
 // two f16 terms (x = hi + lo) and each product is evaluated as hi*hi + hi*lo + lo*hi: ~2^-22
 // relative error, i.e. fp32-class results at tensor-core speed.
 // The relative-position terms are tiny (21 taps) and stay on CUDA cores in fp32.
+// A segment has only T/64 * heads query tiles (38 for a 12 s segment), far fewer than the 148 SMs,
+// and one warp's MMA chain over all T keys is latency-bound, so the key range is split over
+// `splits` CTAs per query tile (flash-decoding style): each writes its unnormalised partial output,
+// running max and sum plus its band scores, and attn_merge_kernel combines them, normalises and
+// adds the relative-value term.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -77,21 +82,20 @@ struct AttnSmem {
   __half k[1][2][AK][KP];    // [buffer][hi/lo][key][dim]  (single buffer: two CTAs per SM overlap instead)
   __half v[1][2][AD][VP];    // [buffer][hi/lo][dim][key]
   float rl[AQ][RP];          // rel-key logits q_i . Ek[r]
-  float sb[AQ][RP];          // band scores (raw, masked) for the rel-value term
-  float ev[RP][AD];          // rel-value table
-  float m[AQ], inv_l[AQ];
+  float qs[AQ][AD + 1];      // fp32 query rows / rel-key table staged for the rl prologue
+  float ek[RP][AD + 1];      //   (odd pitch: conflict-free for the row-per-thread reads)
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 2) rel_attention_mma_kernel(
     const __half* __restrict__ qh, const __half* __restrict__ ql, const __half* __restrict__ kh,
     const __half* __restrict__ kl, const __half* __restrict__ vth, const __half* __restrict__ vtl,
-    const float* __restrict__ qkv, const float* __restrict__ rel_k, const float* __restrict__ rel_v,
-    const int* __restrict__ lens, float* __restrict__ out, int T, int Tp, int H, int heads, int window,
-    float qscale) {
+    const float* __restrict__ qkv, const float* __restrict__ rel_k, const int* __restrict__ lens,
+    float* __restrict__ part_o, float* __restrict__ part_m, float* __restrict__ part_l,
+    float* __restrict__ band_s, int B, int T, int Tp, int H, int heads, int window, int splits, float qscale) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   AttnSmem& sm = *reinterpret_cast<AttnSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
+  const int b = blockIdx.z / splits, sp = blockIdx.z - b * splits, h = blockIdx.y, q0 = blockIdx.x * AQ;
   const int len = lens[b];
   const int R = 2 * window + 1;
   const size_t bh = (size_t)b * heads + h;
@@ -117,27 +121,40 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) rel_attention_mma_kernel(
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   const int nblk = Tp / AK;
-  load_block(0, 0);
+  const int kb_begin = (int)((long long)sp * nblk / splits), kb_end = (int)((long long)(sp + 1) * nblk / splits);
+  load_block(kb_begin, 0);
 
-  // ---- prologue: rel tables, rel-key logits (fp32), Q fragments
-  for (int i = tid; i < RP * AD; i += ATT_THREADS) {
-    const int r = i / AD;
-    sm.ev[r][i - r * AD] = r < R ? rel_v[i] : 0.f;
-  }
-  for (int i = tid; i < AQ * RP; i += ATT_THREADS) {
-    const int il = i / RP, r = i - il * RP;
-    sm.sb[il][r] = -INFINITY;
-    float s = 0.f;
-    const int qi = q0 + il;
-    if (r < R && qi < T) {
-      const float* qrow = qkv + ((size_t)b * T + qi) * 3 * H + h * AD;
-      const float* ek = rel_k + (size_t)r * AD;
-      for (int c = 0; c < AD; ++c) s = fmaf(qrow[c] * qscale, ek[c], s);
+  // ---- prologue: rel-key logits (fp32) if this CTA's keys touch the band of its queries, Q fragments
+  if (kb_begin * AK < q0 + AQ + window && kb_end * AK > q0 - window) {
+    for (int i = tid; i < AQ * (AD / 4); i += ATT_THREADS) {
+      const int il = i / (AD / 4), c4 = i - il * (AD / 4);
+      const int qi = q0 + il;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (qi < T) v = *reinterpret_cast<const float4*>(qkv + ((size_t)b * T + qi) * 3 * H + h * AD + c4 * 4);
+      sm.qs[il][c4 * 4 + 0] = v.x * qscale;
+      sm.qs[il][c4 * 4 + 1] = v.y * qscale;
+      sm.qs[il][c4 * 4 + 2] = v.z * qscale;
+      sm.qs[il][c4 * 4 + 3] = v.w * qscale;
     }
-    sm.rl[il][r] = s;
+    for (int i = tid; i < R * AD; i += ATT_THREADS) {
+      const int r = i / AD;
+      sm.ek[r][i - r * AD] = rel_k[i];
+    }
+    __syncthreads();
+    for (int i = tid; i < AQ * RP; i += ATT_THREADS) {
+      const int il = i / RP, r = i - il * RP;
+      float s = 0.f;
+      if (r < R) {
+#pragma unroll 8
+        for (int c = 0; c < AD; ++c) s = fmaf(sm.qs[il][c], sm.ek[r][c], s);
+      }
+      sm.rl[il][r] = s;
+    }
   }
   const int r0 = q0 + warp * 16;            // this warp's 16 query rows
   const int i0 = r0 + g, i1 = r0 + g + 8;   // this lane's two rows
+  float* band0 = band_s + (bh * Tp + i0) * RP;
+  float* band1 = band_s + (bh * Tp + i1) * RP;
   uint32_t aqh[6][4], aql[6][4];
   {
     const __half* qh_b = qh + bh * Tp * AD;
@@ -162,9 +179,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) rel_attention_mma_kernel(
     for (int e = 0; e < 4; ++e) o[n][e] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  for (int kb = 0; kb < nblk; ++kb) {
+  for (int kb = kb_begin; kb < kb_end; ++kb) {
     const int buf = 0, k0 = kb * AK;
-    if (kb > 0) load_block(kb, 0);
+    if (kb > kb_begin) load_block(kb, 0);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
@@ -210,7 +227,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) rel_attention_mma_kernel(
         if (inband) v += sm.rl[i - q0][rel];
         if (!(i < len && j < len)) v = -1e4f;
         if (j >= T) v = -INFINITY;
-        if (inband && j < T) sm.sb[i - q0][rel] = v;
+        if (inband && j < T) (e < 2 ? band0 : band1)[rel] = v;   // each (i, j) of the band has one owner CTA
         s[n][e] = v;
         if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
       }
@@ -284,42 +301,84 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) rel_attention_mma_kernel(
     __syncthreads();   // this buffer is refilled by the next iteration's prefetch
   }
 
-  // ---- epilogue: normalise, add the rel-value term
+  // ---- epilogue: this split's running max / sum and unnormalised output
+  const size_t rows = (size_t)B * heads * Tp;
+  const size_t row0 = (size_t)sp * rows + bh * Tp + i0, row1 = row0 + 8;
   if (t == 0) {
-    sm.m[i0 - q0] = m0;
-    sm.inv_l[i0 - q0] = 1.f / l0;
-    sm.m[i1 - q0] = m1;
-    sm.inv_l[i1 - q0] = 1.f / l1;
+    part_m[row0] = m0;
+    part_l[row0] = l0;
+    part_m[row1] = m1;
+    part_l[row1] = l1;
   }
-  __syncthreads();
-  for (int i = tid; i < AQ * RP; i += ATT_THREADS) {
-    const int il = i / RP, r = i - il * RP;
-    sm.sb[il][r] = r < R ? __expf(sm.sb[il][r] - sm.m[il]) * sm.inv_l[il] : 0.f;   // band probabilities
-  }
-  __syncthreads();
-  const float il0 = sm.inv_l[i0 - q0], il1 = sm.inv_l[i1 - q0];
 #pragma unroll
   for (int n = 0; n < 12; ++n) {
     const int c = n * 8 + 2 * t;
-    float v00 = o[n][0] * il0, v01 = o[n][1] * il0, v10 = o[n][2] * il1, v11 = o[n][3] * il1;
-    for (int r = 0; r < R; ++r) {
-      const float p0 = sm.sb[i0 - q0][r], p1 = sm.sb[i1 - q0][r];
-      const float e0 = sm.ev[r][c], e1 = sm.ev[r][c + 1];
-      v00 = fmaf(p0, e0, v00);
-      v01 = fmaf(p0, e1, v01);
-      v10 = fmaf(p1, e0, v10);
-      v11 = fmaf(p1, e1, v11);
-    }
-    if (i0 < T) *reinterpret_cast<float2*>(out + ((size_t)b * T + i0) * H + h * AD + c) = make_float2(v00, v01);
-    if (i1 < T) *reinterpret_cast<float2*>(out + ((size_t)b * T + i1) * H + h * AD + c) = make_float2(v10, v11);
+    *reinterpret_cast<float2*>(part_o + row0 * AD + c) = make_float2(o[n][0], o[n][1]);
+    *reinterpret_cast<float2*>(part_o + row1 * AD + c) = make_float2(o[n][2], o[n][3]);
   }
+}
+
+// out_i = (sum_s O_s e^{m_s-M}) / L + sum_r p_{i,i+r-w} Ev[r],  M = max_s m_s,  L = sum_s l_s e^{m_s-M}.
+// One warp per (b, head, query row); lanes cover the 96 channels three at a time.
+__global__ void attn_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_m,
+                                  const float* __restrict__ part_l, const float* __restrict__ band_s,
+                                  const float* __restrict__ rel_v, float* __restrict__ out, int B, int T,
+                                  int Tp, int H, int heads, int window, int splits) {
+  const int lane = threadIdx.x & 31;
+  const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= (size_t)B * heads * T) return;
+  const int i = (int)(gw % T);
+  const size_t bh = gw / T;
+  const int h = (int)(bh % heads), b = (int)(bh / heads);
+  const size_t rows = (size_t)B * heads * Tp, row = bh * Tp + i;
+  float M = -INFINITY;
+  for (int s = 0; s < splits; ++s) M = fmaxf(M, part_m[s * rows + row]);
+  float L = 0.f, acc[3] = {0.f, 0.f, 0.f};
+  for (int s = 0; s < splits; ++s) {
+    const float w = __expf(part_m[s * rows + row] - M);
+    L = fmaf(part_l[s * rows + row], w, L);
+    const float* po = part_o + (s * rows + row) * AD + lane;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc[k] = fmaf(po[32 * k], w, acc[k]);
+  }
+  const float inv_l = 1.f / L;
+  const int R = 2 * window + 1;
+  float p = 0.f;   // band probability of key j = i + lane - window
+  if (lane < R) {
+    const int j = i + lane - window;
+    if (j >= 0 && j < T) p = __expf(band_s[row * RP + lane] - M) * inv_l;
+  }
+  float v[3] = {acc[0] * inv_l, acc[1] * inv_l, acc[2] * inv_l};
+  for (int r = 0; r < R; ++r) {
+    const float pr = __shfl_sync(0xffffffffu, p, r);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = fmaf(pr, rel_v[r * AD + lane + 32 * k], v[k]);
+  }
+  float* dst = out + ((size_t)b * T + i) * H + h * AD + lane;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) dst[32 * k] = v[k];
+}
+
+// key-range splits per query tile: aim at ~2 CTAs per SM for one batch row, at least one key block
+// per split.  Independent of B so that a row's result does not depend on its batch neighbours.
+int attn_splits(int T, int heads) {
+  const int nblk = (T + AK - 1) / AK;
+  const int tiles = nblk * heads;
+  int ns = (2 * 148 + tiles - 1) / tiles;
+  if (ns > nblk) ns = nblk;
+  if (ns > 16) ns = 16;
+  return ns < 1 ? 1 : ns;
 }
 
 }  // namespace
 
 size_t rel_attention_scratch_bytes(int B, int T, int H) {
   const int Tp = (T + AK - 1) / AK * AK;
-  return (size_t)6 * B * H * Tp * sizeof(__half) + 256;
+  const int heads = H / AD > 0 ? H / AD : 1;
+  const size_t rows = (size_t)B * heads * Tp;
+  const size_t ns = (size_t)attn_splits(T, heads);
+  // q/k/v hi+lo (f16), then per split: partial output, max, sum (f32), then the band scores (f32)
+  return (size_t)6 * B * H * Tp * sizeof(__half) + (ns * rows * (AD + 2) + rows * RP) * sizeof(float) + 512;
 }
 
 cudaError_t launch_rel_attention_mma(const float* qkv, const float* rel_k, const float* rel_v, const int* lens,
@@ -330,6 +389,12 @@ cudaError_t launch_rel_attention_mma(const float* qkv, const float* rel_k, const
   const size_t n = (size_t)B * H * Tp;
   __half* base = reinterpret_cast<__half*>(scratch);
   __half *qh = base, *ql = base + n, *kh = base + 2 * n, *kl = base + 3 * n, *vth = base + 4 * n, *vtl = base + 5 * n;
+  const int ns = attn_splits(T, n_heads);
+  const size_t rows = (size_t)B * n_heads * Tp;
+  float* part_o = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + ((6 * n * sizeof(__half) + 255) & ~size_t(255)));
+  float* part_m = part_o + (size_t)ns * rows * AD;
+  float* part_l = part_m + (size_t)ns * rows;
+  float* band_s = part_l + (size_t)ns * rows;
   const float qscale = rsqrtf((float)AD);
   attn_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(qkv, qh, ql, kh, kl, vth, vtl, B, T, Tp, H, n_heads,
                                                                 qscale);
@@ -342,9 +407,15 @@ cudaError_t launch_rel_attention_mma(const float* qkv, const float* rel_k, const
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid(Tp / AQ, n_heads, B);
-  rel_attention_mma_kernel<<<grid, ATT_THREADS, sizeof(AttnSmem), s>>>(qh, ql, kh, kl, vth, vtl, qkv, rel_k, rel_v,
-                                                                       lens, out, T, Tp, H, n_heads, window, qscale);
+  dim3 grid(Tp / AQ, n_heads, B * ns);
+  rel_attention_mma_kernel<<<grid, ATT_THREADS, sizeof(AttnSmem), s>>>(qh, ql, kh, kl, vth, vtl, qkv, rel_k, lens,
+                                                                       part_o, part_m, part_l, band_s, B, T, Tp, H,
+                                                                       n_heads, window, ns, qscale);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const size_t warps = (size_t)B * n_heads * T;
+  attn_merge_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(part_o, part_m, part_l, band_s, rel_v, out, B, T, Tp,
+                                                               H, n_heads, window, ns);
   return cudaGetLastError();
 }
 
