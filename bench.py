@@ -48,6 +48,15 @@ def clip_segments(cfg, seed=0):
     return [c for _, c in seg.segment_frames(n, cuts, plan)]
 
 
+CPU_SAMPLE_FRAMES = 1000     # BASELINE.json's 10 s row: the CPU arms time one such segment per step
+
+
+def workload_name(config, seg_frames):
+    """the one workload both arms are quoted on (BASELINE.json configs[1])"""
+    return (f"RVC {config} synthesizer decode, {CLIP_SECONDS} s clip split into silence segments of "
+            f"{seg_frames} frames (incl. 1 s pad each side), B=1 per segment, one clip per GPU per step")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -133,14 +142,14 @@ def run_reference(args):
     import torch
     import polgen_rvc_b200 as pg
     cfg = pg.CONFIGS[args.config]
-    frames = 500     # bounded sample: one 5 s segment of the same config per step
+    frames = CPU_SAMPLE_FRAMES     # bounded sample: one 10 s segment of the same config per step
     rate, sec, threads = cpu_reference_rate(cfg, frames, args.steps, args.warmup)
     sample = f"one {frames / 100:.0f} s segment (T={frames}, B=1) of {args.config} per step, torch fp32 CPU"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"RVC {args.config} decode, 60 s clip split into silence segments (bounded CPU sample: {sample})"},
+        "config": {"workload": workload_name(args.config, clip_segments(cfg, seed=0)), "sample": sample},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -298,9 +307,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
-            "config": {"workload": f"RVC {args.config} synthesizer decode, {CLIP_SECONDS} s clip split into silence "
-                                   f"segments of {seg_frames} frames (incl. 1 s pad each side), B=1 per segment, "
-                                   f"one clip per GPU per step",
+            "config": {"workload": workload_name(args.config, seg_frames),
                        "audio_s_per_step_per_gpu": audio_s, "l2": "flushed between steps (256 MiB write)",
                        "segment_lanes_per_gpu": args.lanes,
                        "steps_pipelined": bool(args.pipelined),
@@ -322,11 +329,11 @@ def run_ours(args):
                     f.write(f"{('planes-tcgen05', 'cuda-core', 'nlc-tcgen05-split')[int(cls)]},{int(cin)},{int(n)},{int(k)},{int(dil)},{int(cnt)},"
                             f"{ms:.3f},{ms / cnt:.4f},{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.1f},{ms / seq_ms:.4f}\n")
         if world == 1 and not args.no_cpu:
-            frames = 500
-            rate, sec, threads = cpu_reference_rate(cfg, frames, 2, 1)
+            frames = CPU_SAMPLE_FRAMES
+            rate, sec, threads = cpu_reference_rate(cfg, frames, 6, 1)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"one {frames / 100:.0f} s segment (T={frames}, B=1) of {args.config}, "
-                                              f"oracle port of Synthesizer.infer, torch fp32, mean of 2 after 1 warm-up"}
+                                              f"oracle port of Synthesizer.infer, torch fp32, mean of 6 after 1 warm-up"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -141,3 +141,25 @@ def test_plan_shards_balanced_and_complete():
     assert abs(loads[0] - loads[1]) <= 3 and sum(loads) == 32
     batches = seg.batch_equal_lengths([0, 1, 2, 3, 4], [10, 20, 10, 10, 20], max_batch=2)
     assert sorted(map(tuple, batches)) == [(0, 2), (1, 4), (3,)]
+
+
+def test_bench_reference_arm_line_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the
+    same metric / unit / workload as our arm, kind "port", no GPU work."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "audio-s/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert "[3435, 2965]" in d["config"]["workload"] and "sample" in d["config"]
+    assert d["gpu_launches"] == 0
