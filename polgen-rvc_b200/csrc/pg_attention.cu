@@ -359,15 +359,23 @@ __global__ void attn_merge_kernel(const float* __restrict__ part_o, const float*
   for (int k = 0; k < 3; ++k) dst[32 * k] = v[k];
 }
 
-// key-range splits per query tile: aim at ~2 CTAs per SM for one batch row, at least one key block
-// per split.  Independent of B so that a row's result does not depend on its batch neighbours.
+// Key-range splits per query tile.  The grid is tiles*splits CTAs on 2*148 resident slots and a CTA's
+// time is ~(its key blocks + 1 for prologue/epilogue): pick the split count with the fewest
+// wave-steps, e.g. T = 3435 (108 tiles, 54 key blocks): 5 splits = 2 waves x 12 instead of 3 splits =
+// 2 waves x 19.  Depends on T only (not on B), so a row's result is independent of its batch.
 int attn_splits(int T, int heads) {
   const int nblk = (T + AK - 1) / AK;
-  const int tiles = nblk * heads;
-  int ns = (2 * 148 + tiles - 1) / tiles;
-  if (ns > nblk) ns = nblk;
-  if (ns > 16) ns = 16;
-  return ns < 1 ? 1 : ns;
+  const int tiles = nblk * heads, slots = 2 * 148;
+  int best = 1, best_cost = 1 << 30;
+  for (int ns = 1; ns <= 16 && ns <= nblk; ++ns) {
+    const int waves = (tiles * ns + slots - 1) / slots;
+    const int cost = waves * ((nblk + ns - 1) / ns + 1);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = ns;
+    }
+  }
+  return best;
 }
 
 }  // namespace
