@@ -48,6 +48,12 @@ def clip_segments(cfg, seed=0):
     return [c for _, c in seg.segment_frames(n, cuts, plan)]
 
 
+# DRAM traffic of the top-time decoder conv shape from one `ncu --set full` capture (bench.py cannot run
+# ncu on itself): C=128 k=11 conv1 at T=3435 (L = 412 200 rows), dram__bytes_read + dram__bytes_write.
+NCU_TRAFFIC = {"kernel": "conv_planes_kernel<2,4,1> C=128 k=11 dil=1, L=412200", "bytes_per_launch": 160.32e6,
+               "algorithmic_bytes_per_launch": 2 * 412200 * (128 + 128),
+               "source": "profiles/r01p_ncu_full_conv_planes_c128k11.txt (launch 0; kernel unchanged since)"}
+
 CPU_SAMPLE_FRAMES = 1000     # BASELINE.json's 10 s row: the CPU arms time one such segment per step
 
 
@@ -294,7 +300,7 @@ def run_ours(args):
         roofline = {
             "bound": "tensor", "kernel": "decoder tcgen05/TMEM implicit-GEMM convs over channel planes: conv_planes_kernel (ResBlock convs, ups, conv_pre) + pair_planes_kernel (fused ResBlock pairs, C=32/64)",
             "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-            "peak_source": peak_src, "traffic": None,
+            "peak_source": peak_src, "traffic": NCU_TRAFFIC["bytes_per_launch"], "traffic_detail": NCU_TRAFFIC,
             "launches": umma_n, "avg_launch_ms": umma_ms / max(umma_n, 1),
             "algorithmic_flops_per_launch": umma_fl / max(umma_n, 1),
             "share_of_step": umma_ms / seq_ms if seq_ms > 0 else None,

@@ -50,7 +50,6 @@ constexpr int EPI_COLS = 16;                // accumulator columns per epilogue 
 // epilogue specialisations: the two shapes that make up 5/6 of the ResBlock convs get straight-line code
 constexpr int EPI_GENERIC = 0, EPI_C1 = 1 /* y16 = lrelu(acc + bias) */, EPI_C2 = 2 /* y16 = lrelu(acc + bias + raw(res16)) */;
 constexpr int NTHREADS = (EPI_WARP0 + EPI_WARPS) * 32;
-constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GROUP_PLANES = 16;   // 128 channels per activation-ring slot
 
 struct PlaneParams {
