@@ -111,7 +111,13 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   return q;
 }
 
-template <int MT, int KC16, int EPI, bool DBG>
+// SWAP (C = 128 ResBlock shapes, MT == 2, NT == 128): the operands change roles -- the weight tile is
+// the M = 128 operand (rows = Cout) and the MT*128 = 256 time rows of the window are the N operand,
+// D[Cout][time].  One N = 256 MMA then reads 16 KB (weights) + 32 KB (window) of shared memory per 512
+// clk = 96 B/clk instead of the 128 B/clk of two N = 128 MMAs, which is what caps these layers at
+// ~60 % tensor-pipe duty.  TMEM lanes become channels, columns time, so the epilogue
+// transposes 8-lane x 8-(row pair) blocks with warp shuffles back into 16-byte plane rows.
+template <int MT, int KC16, int EPI, bool DBG, bool SWAP = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p) {
   const int dbg = DBG ? p.debug : 0;   // production instantiation: every debug switch folds away
@@ -294,11 +300,17 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
             const uint32_t a_lo = a_chunk + (uint32_t)(tap * p.dil);
 #pragma unroll
             for (int k16 = 0; k16 < KC16; ++k16) {
+              if (SWAP) {
+                if (do_mma)   // D[Cout 128][time MT*128] += W[Cout][16] * X[time][16]^T
+                  umma_f16_lh(d_base, w_lo + 2u * (uint32_t)k16, b_hi, a_lo + (uint32_t)k16 * plane2, a_hi, idesc,
+                              started | (uint32_t)k16);
+              } else {
 #pragma unroll
-              for (int m = 0; m < MT; ++m)
-                if (do_mma)
-                  umma_f16_lh(d_base + (uint32_t)m * nt, a_lo + (uint32_t)k16 * plane2 + (uint32_t)(m * BM), a_hi,
-                              w_lo + 2u * (uint32_t)k16, b_hi, idesc, started | (uint32_t)k16);
+                for (int m = 0; m < MT; ++m)
+                  if (do_mma)
+                    umma_f16_lh(d_base + (uint32_t)m * nt, a_lo + (uint32_t)k16 * plane2 + (uint32_t)(m * BM), a_hi,
+                                w_lo + 2u * (uint32_t)k16, b_hi, idesc, started | (uint32_t)k16);
+              }
             }
             started = 1;
             if (!p.resident) {
@@ -348,6 +360,97 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
                    &r_full[slot]);
         }
       }
+    }
+  } else if (warp >= EPI_WARP0 && EPI != EPI_GENERIC && SWAP) {
+    // ===== SWAP epilogue (EPI_C1 / EPI_C2, NT == Cout == 128): TMEM lane = channel, column = time row.
+    // Item = 16 time columns: tcgen05.ld -> + bias (per lane) -> 8x8 shuffle transpose inside each group of
+    // 8 lanes (= one 8-channel plane) -> lane i of the group owns rows 2i, 2i+1 of the block as two 16-byte
+    // plane rows -> (+ residual) -> leaky-ReLU -> store.
+    const int quarter = warp & 3, grp = (warp - EPI_WARP0) >> 2;
+    constexpr int ITEMS = MT * BM / EPI_COLS;
+    const int CP = p.Cout_real / 8;
+    const float slope = p.out16_slope, rinv = p.res_inv;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int j8 = lane >> 3, i8 = lane & 7;
+    const int plane = quarter * 4 + j8;
+    const float bias_c = bias_s[quarter * 32 + lane];
+    uint32_t t_cnt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t_cnt) {
+      const int rt = tile % p.n_row_tiles, b = tile / p.n_row_tiles;     // n_ntiles == 1
+      const uint32_t accb = t_cnt & 1u;
+      uint4* out_b = reinterpret_cast<uint4*>(p.out16) + ((size_t)b * CP + plane) * p.L;
+      mbar_wait(&acc_full[accb], (t_cnt >> 1) & 1u);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int it = grp; it < ITEMS; it += EPI_GROUPS) {
+        const int col0 = it * EPI_COLS;                  // time column inside the tile
+        const int m = col0 / BM;
+        const int row = rt * (BM * MT) + col0 + 2 * i8;  // first of this lane's two output rows
+        uint4 rcur[2];
+        int ring_slot = 0;
+        if (EPI == EPI_C2) {
+          // ring slot = (row tile m, 64-channel block): the four planes of a quarter share one slot
+          const uint32_t sidx = (t_cnt * (uint32_t)MT + (uint32_t)m) * (uint32_t)(p.NT / p.res_cols) +
+                                (uint32_t)((quarter * 32) / p.res_cols);
+          const uint32_t slot = sidx % (uint32_t)p.r_slots;
+          mbar_wait(&r_full[slot], (sidx / (uint32_t)p.r_slots) & 1u);
+          const uint8_t* rs = r_ring + (size_t)slot * p.r_slot_bytes +
+                              (size_t)(((quarter * 32) % p.res_cols) / 8 + j8) * (BM * 16) +
+                              (size_t)((col0 % BM) + 2 * i8) * 16;
+          rcur[0] = *reinterpret_cast<const uint4*>(rs);
+          rcur[1] = *reinterpret_cast<const uint4*>(rs + 16);
+          ring_slot = (int)slot;
+        }
+        uint32_t acc[EPI_COLS];
+        tmem_ld16(lane_taddr + accb * (uint32_t)(MT * BM) + (uint32_t)col0, acc);
+        if (EPI == EPI_C2) {   // release the slot only after the loads have landed (see mbar_arrive_dep)
+          uint32_t dep = rcur[0].x ^ rcur[0].w ^ rcur[1].x ^ rcur[1].w;
+          asm volatile("" : "+r"(dep));
+          __syncwarp();
+          if (lane == 0) mbar_arrive_dep(&r_empty[ring_slot], dep);
+        }
+        float a[EPI_COLS];
+#pragma unroll
+        for (int i = 0; i < EPI_COLS; ++i) a[i] = __uint_as_float(acc[i]) + bias_c;
+        // transpose: element e = (a[2e], a[2e+1]) = time pair e of this lane's channel; afterwards
+        // element k = time pair i8 of channel k of the plane
+#pragma unroll
+        for (int mask = 4; mask >= 1; mask >>= 1) {
+          const bool up = (i8 & mask) != 0;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (e & mask) continue;
+            const int f = e | mask;
+            const float s0 = up ? a[2 * e] : a[2 * f], s1 = up ? a[2 * e + 1] : a[2 * f + 1];
+            const float r0 = __shfl_xor_sync(0xffffffffu, s0, mask), r1 = __shfl_xor_sync(0xffffffffu, s1, mask);
+            if (up) {
+              a[2 * e] = r0;
+              a[2 * e + 1] = r1;
+            } else {
+              a[2 * f] = r0;
+              a[2 * f + 1] = r1;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = a[2 * k + j];
+          if (EPI == EPI_C2) {
+            float rr[8];
+            unpack8(rcur[j], rr);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += fminf(rr[k], rr[k] * rinv);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], v[k] * slope);
+          if (row + j < p.L) out_b[row + j] = pack8(v);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[accb]);
     }
   } else if (warp >= EPI_WARP0 && EPI != EPI_GENERIC) {
     // ===== specialised epilogue (EPI_C1 / EPI_C2): one Cout tile, row_mul == 1, bias in shared memory,
@@ -670,7 +773,7 @@ bool make_plan(const PlaneConvArgs& a, Plan* out) {
   return false;
 }
 
-template <int MT, int KC16, int EPI, bool DBG>
+template <int MT, int KC16, int EPI, bool DBG, bool SWAP = false>
 cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
   CUtensorMap wmap;
   if (!get_weight_map(a.w16, a.Cin, a.N, a.K, pl.KC, pl.NT, &wmap)) return cudaErrorNotSupported;
@@ -689,12 +792,12 @@ cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
   p.a_slots = pl.a_slots; p.a_slot_bytes = pl.a_slot_bytes; p.stages = pl.stages;
   p.stage_bytes = pl.stage_bytes; p.resident = pl.resident; p.tmem_cols = pl.tmem_cols;
   p.r_slots = pl.r_slots; p.r_slot_bytes = pl.r_slot_bytes; p.res_cols = pl.res_cols; p.bias_smem = pl.bias_smem;
-  p.idesc = make_idesc(BM, pl.NT);
+  p.idesc = SWAP ? make_idesc(pl.NT, BM * MT) : make_idesc(BM, pl.NT);
   static const int dbg = env_int("PG_PLANES_DEBUG", 0);
   p.debug = dbg;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_planes_kernel<MT, KC16, EPI, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_planes_kernel<MT, KC16, EPI, DBG, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return e;
     attr_done = true;
@@ -705,7 +808,7 @@ cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
     unsigned int zero = 0;
     cudaMemcpyToSymbol(g_ptrace_n, &zero, sizeof(zero));
   }
-  conv_planes_kernel<MT, KC16, EPI, DBG><<<grid, NTHREADS, pl.smem, s>>>(wmap, p);
+  conv_planes_kernel<MT, KC16, EPI, DBG, SWAP><<<grid, NTHREADS, pl.smem, s>>>(wmap, p);
   if (p.debug & 8) {
     cudaDeviceSynchronize();
     static unsigned long long host[4096];
@@ -750,6 +853,11 @@ cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s) {
   if (!dbg && pl.bias_smem && a.N == pl.NT && a.row_mul == 1 && !a.bbias && !a.res32 && !a.accin16 && !a.accin32 &&
       !a.out32 && a.out16 && a.out_scale == 1.f && a.out16_slope <= 1.f && a.res_inv >= 1.f)
     epi = a.res16 ? EPI_C2 : EPI_C1;
+  // operand-swapped variant for the C = 128 ResBlock convs (opt-in until validated on hardware)
+  static const bool swap_on = env_int("PG_PLANES_SWAP", 0) != 0;
+  if (swap_on && epi != EPI_GENERIC && pl.MT == 2 && pl.NT == 128 && pl.KC == 64 && pl.res_cols == 64 &&
+      a.Cout_real == 128)
+    return epi == EPI_C1 ? launch_t<2, 4, EPI_C1, false, true>(a, pl, s) : launch_t<2, 4, EPI_C2, false, true>(a, pl, s);
 #define PG_DISPATCH(MT_, KC16_)                                                        \
   return dbg ? launch_t<MT_, KC16_, EPI_GENERIC, true>(a, pl, s)                       \
              : (epi == EPI_C1 ? launch_t<MT_, KC16_, EPI_C1, false>(a, pl, s)          \
