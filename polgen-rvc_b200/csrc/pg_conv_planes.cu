@@ -855,7 +855,7 @@ cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s) {
     epi = a.res16 ? EPI_C2 : EPI_C1;
   // operand-swapped variant for the C = 128 ResBlock convs (opt-in until validated on hardware)
   static const bool swap_on = env_int("PG_PLANES_SWAP", 0) != 0;
-  if (swap_on && epi != EPI_GENERIC && pl.MT == 2 && pl.NT == 128 && pl.KC == 64 && pl.res_cols == 64 &&
+  if ((swap_on || a.swap) && epi != EPI_GENERIC && pl.MT == 2 && pl.NT == 128 && pl.KC == 64 && pl.res_cols == 64 &&
       a.Cout_real == 128)
     return epi == EPI_C1 ? launch_t<2, 4, EPI_C1, false, true>(a, pl, s) : launch_t<2, 4, EPI_C2, false, true>(a, pl, s);
 #define PG_DISPATCH(MT_, KC16_)                                                        \

@@ -380,6 +380,25 @@ def test_cuda_graph_replay_matches_direct_launches():
     assert torch.equal(w0, w1)
 
 
+def test_operand_swapped_conv_matches_default():
+    """PG_FLAG_PLANES_SWAP runs the C = 128 ResBlock convs with the MMA operands swapped (weights as the
+    M operand, 256 time rows as N, shuffle-transposed epilogue).  Same products, same fp32 accumulation:
+    the waveform must match the default path to rounding on a segment long enough for MT = 2 tiles."""
+    import polgen_rvc_b200 as pg
+    from polgen_rvc_b200 import _lib
+    cfg = pg.CONFIGS["v2-48k"]
+    sd = pg.synth_weights(cfg, seed=0)
+    folded = pg.fold_state_dict(sd)
+    d = _dev()
+    T = 1400
+    inp = [t.to(d) for t in pg.synth_inputs(cfg, 1, T, seed=1)]
+    a = pg.Engine(cfg, folded, 0).infer(*inp, None, None, 5, want_aux=False)[0]
+    b = pg.Engine(cfg, folded, 0, _lib.PG_FLAG_PLANES_SWAP).infer(*inp, None, None, 5, want_aux=False)[0]
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(b).all())
+    assert snr_db(a, b) >= 90.0
+
+
 def test_fused_pair_kernel_matches_unfused_path():
     """The fused ResBlock-pair kernel (conv1 -> lrelu -> conv2 -> +x in one launch, C = 32 / 64 stages)
     against its validation twin that runs the two convs as separate kernels: same operands, same
