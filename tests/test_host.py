@@ -163,3 +163,23 @@ def test_bench_reference_arm_line_contract():
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     assert "[3435, 2965]" in d["config"]["workload"] and "sample" in d["config"]
     assert d["gpu_launches"] == 0
+
+
+def test_plan_shards_properties_random():
+    """Randomised properties of the segment sharding (greedy longest-first): every segment on exactly
+    one rank, deterministic, and the classic LPT bound max_load <= mean_load + max_item."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(min_value=1, max_value=6000), min_size=0, max_size=64),
+           st.integers(min_value=1, max_value=8))
+    def check(lengths, world):
+        bins = seg.plan_shards(lengths, world)
+        assert len(bins) == world
+        assert sorted(i for b in bins for i in b) == list(range(len(lengths)))
+        assert bins == seg.plan_shards(list(lengths), world)
+        assert all(b == sorted(b) for b in bins)
+        if lengths:
+            loads = [sum(lengths[i] for i in b) for b in bins]
+            assert max(loads) <= sum(lengths) / world + max(lengths)
+    check()
