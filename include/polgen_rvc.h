@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 1
+#define PG_ABI_VERSION 2
 #define PG_MAX_UPS 8
 #define PG_MAX_RESBLOCK_KERNELS 4
 #define PG_MAX_DILATIONS 4
@@ -45,7 +45,7 @@ typedef enum pg_status {
   PG_ERR_UNSUPPORTED = -4
 } pg_status;
 
-typedef enum pg_dtype { PG_F32 = 0, PG_F16 = 1, PG_I64 = 2 } pg_dtype;
+typedef enum pg_dtype { PG_F32 = 0, PG_F16 = 1, PG_I64 = 2, PG_F64 = 3 } pg_dtype;
 
 /* Mirrors the reference constructor
  *   Synthesizer(spec_channels, segment_size, inter_channels, hidden_channels,
@@ -89,6 +89,7 @@ typedef struct pg_config {
 #define PG_FLAG_LEGACY_DECODER 16 /* decoder on the time-major tcgen05 kernel (A/B comparison aid) */
 #define PG_FLAG_NO_GRAPHS 64    /* launch every kernel of pg_infer directly (default: a CUDA graph per (B,T) is captured on the second call of a shape and replayed afterwards when the stream is capturable and the noise is device-drawn) */
 #define PG_FLAG_PLANES_SWAP 128  /* C=128 ResBlock convs with swapped MMA operands (weights = M, 256 time rows = N); opt-in, results identical */
+#define PG_FLAG_NO_PAD 256       /* do not pad T up to a launch-shape bucket (validation twin of the padded path) */
 #define PG_FLAG_F16_LATENTS 8  /* TextEncoder / flow GEMMs with single-pass f16 tensor-core operands (default: fp32-accurate) */
 
 typedef struct pg_handle_s* pg_handle;
@@ -119,17 +120,44 @@ size_t pg_workspace_bytes(pg_handle h, int B, int T);
  * as sequence_mask does (commons.py:89-93).  eps_* == NULL draws the noise on
  * device from Philox(seed).  Enqueued on `stream` (a cudaStream_t); returns
  * without synchronising.
- * On a capturable stream (not the legacy default stream) with device-drawn noise the
- * call is staged: inputs are copied into the handle's fixed buffers, the launch sequence
- * runs as a CUDA graph per (B,T) (captured on the second call of a shape) and the
- * waveform is copied out -- phone/lengths/pitch/f0/sid/wave may then also be PINNED HOST
- * pointers (the copies are cudaMemcpyDefault on `stream`).  PG_FLAG_NO_GRAPHS, explicit
- * eps_* or the legacy stream give direct launches on device pointers. */
+ * The call is staged: inputs are copied (cudaMemcpyDefault on `stream`, so device OR pinned
+ * host pointers work for phone/lengths/pitch/f0/sid/wave/aux) into handle-owned buffers whose
+ * frame count is padded up to a bucket (32 / 64 / 128 frames), the launch sequence runs over
+ * that padded shape with the true T as a hard end of every row (read from device memory, so
+ * the result does not depend on the padding), and the waveform is copied out.  On a
+ * capturable stream (not the legacy default stream) with device-drawn noise the launch
+ * sequence is a CUDA graph per (B, padded T): captured on the second call of a bucket,
+ * replayed afterwards for EVERY T inside it; at most pg_set_graph_cache() graphs are kept
+ * (LRU).  PG_FLAG_NO_GRAPHS, explicit eps_* or the legacy stream give direct launches.
+ * Row b of a batch draws its noise from Philox(seed + b*0x9E3779B97F4A7C15), indexed by
+ * (t, c) only: a row's result does not depend on the rest of the batch. */
 int pg_infer(pg_handle h, void* stream, int B, int T,
              const float* phone_dev, const int64_t* lengths_dev,
              const int64_t* pitch_dev, const float* f0_dev, const int64_t* sid_dev,
              const float* eps_zp_dev, const float* eps_src_dev, uint64_t seed,
              float* wave_dev, float* aux_dev);
+
+/* The silence-split segments of a clip as ONE call (rvc/infer/pipeline.py:381-447 runs them as a
+ * loop of B=1 infer calls).  Every segment is stand-alone: each layer of TextEncoder, flow AND
+ * decoder treats segs[b].T as the hard end of row b (zero padding there, exactly what a B=1 call of
+ * that length sees), so segs[b].wave equals pg_infer(B=1, T=segs[b].T) on that segment (same noise
+ * when eps_* are given; Philox row b as documented above otherwise).  Unlike a padded pg_infer batch
+ * -- which reproduces the reference's ragged-batch behaviour, where GeneratorNSF ignores the mask
+ *  -- rows of different lengths do not disturb each other, and decoder tiles past a
+ * row's end are skipped.  Pointers are device or pinned-host memory (copied on `stream`). */
+typedef struct pg_segment {
+  int32_t T;               /* frames */
+  int32_t trim;            /* samples dropped at BOTH ends on copy-out (t_pad_tgt, pipeline.py:397): wave gets T*upp - 2*trim */
+  int64_t sid;             /* speaker id */
+  const float* phone;      /* [T][input_dim] */
+  const int64_t* pitch;    /* [T] */
+  const float* f0;         /* [T] */
+  const float* eps_zp;     /* [T][inter]  nullable (all segments or none) */
+  const float* eps_src;    /* [T*upp]     nullable */
+  float* wave;             /* [T*upp - 2*trim] out */
+  float* aux;              /* nullable out: z, z_p, m_p, logs_p, each [T][inter] */
+} pg_segment;
+int pg_infer_segments(pg_handle h, void* stream, int n, const pg_segment* segs, uint64_t seed);
 
 /* Same call with HOST buffers (pinned recommended): copies the inputs to the
  * device, runs pg_infer, copies the waveform back and synchronises -- the
@@ -163,6 +191,35 @@ int pg_source(pg_handle h, void* stream, int B, int T, const float* f0_dev,
 int pg_generator(pg_handle h, void* stream, int B, int T, const float* z_dev,
                  const float* source_dev, const int64_t* sid_dev, float* wave_dev);
 
+/* ---- the glue on either side of infer in VC.vc / VC.pipeline ---- */
+
+/* Tail of VC.get_f0 (pipeline.py:186-201) + the casts of :379-380: f0 (Hz, already pitch-shifted;
+ * f64 as the reference's numpy array, or f32 widened) -> coarse pitch 1..255 on the mel scale
+ * (f0_min, f0_max = 50, 1100 in the reference) as i64, and pitchf = f0 as f32.  Bit-exact. */
+int pg_coarse_pitch(pg_handle h, void* stream, int64_t n, const void* f0_dev, int f0_dtype,
+                    double f0_min, double f0_max, int64_t* pitch_dev, float* pitchf_dev);
+
+/* VC.vc's feature glue (pipeline.py:252-270): feats [n_feat_frames][input_dim] (HuBERT output after the
+ * optional faiss mix) -> x2 nearest interpolate -> protect mix with feats0 (the pre-mix features;
+ * applied when feats0/pitchf are given and protect < 0.5) -> phone [p_len][input_dim], where
+ * p_len = min(n_audio_frames, 2*n_feat_frames) is returned in *p_len_out (pitch / pitchf are cut to
+ * it by the caller, :262-263).  Bit-exact in fp32. */
+int pg_prepare_features(pg_handle h, void* stream, int64_t n_feat_frames, int64_t n_audio_frames,
+                        const float* feats_dev, const float* feats0_dev, const float* pitchf_dev,
+                        float protect, float* phone_dev, int64_t* p_len_out);
+
+/* Tail of VC.pipeline (pipeline.py:449-460) on the concatenated, trimmed waveform `audio` [n] (see
+ * pg_segment.trim): optional AudioProcessor.change_rms (pipeline.py:31-61; librosa.feature.rms 0.10.2
+ * with center=True, zero padding; linear interpolate; applied when src_audio != NULL and
+ * rms_mix_rate != 1) against the 16 kHz source clip, then audio_max = max|x|/0.99, scale =
+ * 32768 (/ audio_max if > 1), int16 by truncation.  audio_out (nullable, device) receives the f32 audio
+ * after change_rms; pcm_out [n] may be device or pinned host memory.  The int16 step is bit-exact
+ * given the f32 audio; change_rms is f32 arithmetic (relative 1e-5).  The optional librosa.resample
+ * step (:454-455) is not included. */
+int pg_postprocess(pg_handle h, void* stream, const float* audio_dev, int64_t n,
+                   const float* src_audio_dev, int64_t n_src, int src_rate, int tgt_rate,
+                   float rms_mix_rate, float* audio_out_dev, int16_t* pcm_out);
+
 /* Copy an intermediate of the LAST pg_infer/pg_generator call to `dst_dev`
  * as f32 (parity tests tap the same points the oracle exposes: "enc.x0",
  * "enc.layer<i>", "flow.<f>", "dec.conv_pre", "dec.ups<i>", "dec.stage<i>").
@@ -174,8 +231,12 @@ int64_t pg_debug_fetch(pg_handle h, void* stream, const char* tap, float* dst_de
  * graph: the kernel nodes of the graph plus the seed store). */
 int64_t pg_launch_count(pg_handle h);
 
-/* Number of (B,T) shapes of pg_infer currently held as instantiated CUDA graphs. */
+/* Number of (B, padded T) shapes of pg_infer currently held as instantiated CUDA graphs. */
 int pg_graph_count(pg_handle h);
+/* Bound on that number (default 16, env PG_GRAPH_CACHE); least recently used graphs are dropped. */
+int pg_set_graph_cache(pg_handle h, int max_graphs);
+/* The padded frame count pg_infer runs a T-frame call at (the graph bucket of T). */
+int pg_padded_frames(pg_handle h, int T);
 
 /* PG_FLAG_PROFILE: device time, algorithmic FLOPs (2*B*L*Cin*Cout*K) and launch count of the
  * conv launches since the previous read, per kernel class: [0] tcgen05 channel-plane conv (decoder),
@@ -184,8 +245,9 @@ int pg_graph_count(pg_handle h);
 int pg_profile_read(pg_handle h, double* ms_out, double* flops_out, int64_t* launches_out);
 
 /* PG_FLAG_PROFILE: the same records aggregated per layer shape since the previous call (the
- * records pass through pg_profile_read first).  Each row is 8 doubles: class, Cin, N, K, dilation,
- * launches, ms, algorithmic FLOPs.  Returns the number of rows written (<= max_rows). */
+ * records pass through pg_profile_read first).  Each row is 9 doubles: class, Cin, N (negative:
+ * fused ResBlock pair), K, dilation, MT (128-row tiles per CTA tile the launch plan chose; 0 for
+ * classes 1/2), launches, ms, algorithmic FLOPs.  Returns the number of rows written (<= max_rows). */
 int pg_profile_table(pg_handle h, double* rows, int max_rows);
 
 /* Single-layer entry used by the op-level parity tests and micro-benchmarks:

@@ -16,3 +16,6 @@ from .synthesizer import (Engine, SegmentScheduler, Synthesizer, SynthesizerTrnM
 
 __all__ += ["Engine", "SegmentScheduler", "Synthesizer", "SynthesizerTrnMs256NSFsid", "SynthesizerTrnMs768NSFsid",
             "fold_state_dict"]
+from .pipeline import ClipConverter, coarse_pitch, postprocess, prepare_features
+
+__all__ += ["ClipConverter", "coarse_pitch", "postprocess", "prepare_features"]

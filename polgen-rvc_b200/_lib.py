@@ -23,7 +23,11 @@ PG_FLAG_LEGACY_DECODER = 16
 PG_FLAG_NO_PAIR_FUSION = 32
 PG_FLAG_NO_GRAPHS = 64
 PG_FLAG_PLANES_SWAP = 128
+PG_FLAG_NO_PAD = 256
 PG_F32 = 0
+PG_F64 = 3
+PG_ABI_VERSION = 2
+PROFILE_COLS = 9     # pg_profile_table row: class, Cin, N, K, dil, MT, launches, ms, flops
 
 
 class PgConfig(C.Structure):
@@ -41,6 +45,15 @@ class PgConfig(C.Structure):
     ]
 
 
+class PgSegment(C.Structure):
+    """pg_segment (include/polgen_rvc.h): one stand-alone segment of a pg_infer_segments call."""
+    _fields_ = [
+        ("T", C.c_int32), ("trim", C.c_int32), ("sid", C.c_int64),
+        ("phone", C.c_void_p), ("pitch", C.c_void_p), ("f0", C.c_void_p),
+        ("eps_zp", C.c_void_p), ("eps_src", C.c_void_p), ("wave", C.c_void_p), ("aux", C.c_void_p),
+    ]
+
+
 # every symbol include/polgen_rvc.h declares: name -> (restype, argtypes)
 _P, _I, _F = C.c_void_p, C.c_int, C.c_float
 SYMBOLS = {
@@ -51,7 +64,11 @@ SYMBOLS = {
     "pg_finalize": (_I, [_P]),
     "pg_workspace_bytes": (C.c_size_t, [_P, _I, _I]),
     "pg_infer": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, _P, _P]),
+    "pg_infer_segments": (_I, [_P, _P, _I, C.POINTER(PgSegment), C.c_uint64]),
     "pg_infer_host": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, C.c_uint64, _P]),
+    "pg_coarse_pitch": (_I, [_P, _P, C.c_int64, _P, _I, C.c_double, C.c_double, _P, _P]),
+    "pg_prepare_features": (_I, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, _F, _P, C.POINTER(C.c_int64)]),
+    "pg_postprocess": (_I, [_P, _P, _P, C.c_int64, _P, C.c_int64, _I, _I, _F, _P, _P]),
     "pg_text_encoder": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "pg_flow_reverse": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "pg_source": (_I, [_P, _P, _I, _I, _P, _P, C.c_uint64, _P, _P]),
@@ -59,6 +76,8 @@ SYMBOLS = {
     "pg_debug_fetch": (C.c_int64, [_P, _P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "pg_launch_count": (C.c_int64, [_P]),
     "pg_graph_count": (C.c_int, [_P]),
+    "pg_set_graph_cache": (_I, [_P, _I]),
+    "pg_padded_frames": (_I, [_P, _I]),
     "pg_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pg_profile_table": (_I, [_P, C.POINTER(C.c_double), _I]),
     "pg_op_conv1d_f16": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _I,

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpolgen_rvc.so")
-SOURCES = ["pg_api.cu", "pg_simt.cu", "pg_source.cu", "pg_conv_umma.cu", "pg_conv_planes.cu", "pg_planes.cu", "pg_attention.cu", "pg_pair_planes.cu"]
+SOURCES = ["pg_api.cu", "pg_simt.cu", "pg_source.cu", "pg_conv_umma.cu", "pg_conv_planes.cu", "pg_planes.cu", "pg_attention.cu", "pg_pair_planes.cu", "pg_pipeline.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -41,6 +41,7 @@ struct ConvW {
   float* bias = nullptr;   // [Cout]
   uint32_t* tapmask = nullptr;   // per Cout tile, taps with non-zero weights (polyphase upsampler)
   int Cin = 0, Cout = 0, K = 1;
+  double algo_taps = 0;    // taps the ALGORITHM multiplies per output column (polyphase ups: k/u, not the padded K)
 };
 
 struct EncLayerW {
@@ -109,12 +110,19 @@ struct pg_handle_s {
   // CUDA graphs of pg_infer, one per (B, T): the ~60 launches per 100 frames of a segment are
   // captured on the second call of a shape and replayed afterwards over the fixed staging
   // buffers in `io` (inputs copied in, waveform copied out, Philox seed read from memory)
-  struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int uses = 0; bool failed = false; };
-  std::map<std::pair<int, int>, GraphEntry> graphs;
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int uses = 0; bool failed = false;
+                      uint64_t last_use = 0; };
+  std::map<std::pair<int, int>, GraphEntry> graphs;   // key (B, padded T); at most graph_cap instantiated
+  uint64_t graph_clock = 0;
+  int graph_cap = 16;
   DevBuf io;
+  DevBuf io_eps;                // explicit-noise staging of pg_infer_segments
+  DevBuf post;                  // pg_postprocess scratch
+  bool planes_ok = true;        // every decoder stage fits the channel-plane kernels (else: time-major path)
+  cudaStream_t own_stream = nullptr;   // pg_infer_host and callers on the legacy default stream
 
   // PG_FLAG_PROFILE: CUDA events around every conv launch, per kernel class
-  struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; int shape[5]; };
+  struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; int shape[6]; };   // Cin, N, K, dil, L, MT
   std::map<std::vector<int>, std::vector<double>> prof_table;   // (cls,Cin,N,K,dil,MT..) -> {launches, ms, flops}
   std::vector<ProfRec> prof;       // records of the calls since the last pg_profile_read
   std::vector<cudaEvent_t> ev_pool;
@@ -270,6 +278,7 @@ int pack_conv_transpose(pg_handle h, const std::string& wname, const std::string
     for (int co = 0; co < Cout; ++co) b[r * Cout + co] = Bv->data[co];
   int rc = upload_conv(h, w, taps, Cin, N, &st->up);
   if (rc) return rc;
+  st->up.algo_taps = (double)k / u;   // 2*L_in*Cin*Cout*k FLOPs = 2*L_in*Cin*(u*Cout)*(k/u)
   rc = upload(h, b, &st->up.bias);
   if (rc) return rc;
   const int nt = plane_pick_nt(N);
@@ -301,7 +310,7 @@ struct Plan {
 struct Ws {
   // offsets into the workspace
   size_t lens, pitch, sid, x, y, qkv, att, ffn, stats, m_p, logs_p, z_p, z, fh, fa, facts, fskip,
-      gcond, dcond, source, phase, stage[5], zpl, h16[4], attn;
+      gcond, dcond, source, phase, stage[5], zpl, h16[4], attn, tlen;
   size_t stage_elems = 0;
   size_t total = 0;
 };
@@ -312,6 +321,7 @@ Ws plan_ws(const pg_config& c, int B, int T) {
   const size_t BT = (size_t)B * T;
   const int H = c.hidden_channels, F = c.filter_channels, C = c.inter_channels;
   w.lens = p.take(sizeof(int) * B);
+  w.tlen = p.take(sizeof(int) * B);
   w.pitch = p.take(sizeof(int) * BT);
   w.sid = p.take(sizeof(int) * B);
   w.x = p.take(sizeof(float) * BT * H);
@@ -351,10 +361,40 @@ Ws plan_ws(const pg_config& c, int B, int T) {
 
 // captured graphs hold workspace / staging addresses: drop them when either buffer moves
 void invalidate_graphs(pg_handle h) {
-  for (auto& kv : h->graphs) {
+  for (auto& kv : h->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    kv.second.exec = nullptr;
+  h->graphs.clear();     // also forgets `failed`: a shape may try to capture again
+}
+
+// keep at most graph_cap instantiated graphs: drop the least recently used
+void trim_graphs(pg_handle h) {
+  for (;;) {
+    int live = 0;
+    auto victim = h->graphs.end();
+    for (auto it = h->graphs.begin(); it != h->graphs.end(); ++it) {
+      if (!it->second.exec) continue;
+      ++live;
+      if (victim == h->graphs.end() || it->second.last_use < victim->second.last_use) victim = it;
+    }
+    if (live <= h->graph_cap || victim == h->graphs.end()) break;
+    cudaGraphExecDestroy(victim->second.exec);
+    h->graphs.erase(victim);
   }
+  // entries that never got a graph (one-off shapes) are only bookkeeping: bound them too
+  if (h->graphs.size() > 64 * (size_t)h->graph_cap) {
+    for (auto it = h->graphs.begin(); it != h->graphs.end();)
+      it = it->second.exec ? std::next(it) : h->graphs.erase(it);
+  }
+}
+
+// Frames are padded up to a bucket so that a stream of segments with arbitrary lengths maps onto a small
+// set of (B, Tp) launch shapes (one CUDA graph each); the true length is a hard end of the row that
+// every kernel reads from device memory (CallMeta / tlen), so results do not depend on the padding.
+int pad_frames(const pg_handle h, int T) {
+  if (!h->planes_ok || (h->cfg.flags & (PG_FLAG_FORCE_SIMT | PG_FLAG_LEGACY_DECODER | PG_FLAG_KEEP_TAPS | PG_FLAG_NO_PAD)))
+    return T;
+  const int q = T <= 512 ? 32 : (T <= 2048 ? 64 : 128);
+  return (T + q - 1) / q * q;
 }
 
 int ensure_ws(pg_handle h, size_t bytes) {
@@ -364,6 +404,7 @@ int ensure_ws(pg_handle h, size_t bytes) {
   h->ws.p = nullptr;
   h->ws.bytes = 0;
   PG_CUDA_CHECK(cudaMalloc(&h->ws.p, bytes));
+  PG_CUDA_CHECK(cudaMemset(h->ws.p, 0, bytes));   // rows past a hard end are never written: keep them finite
   h->ws.bytes = bytes;
   return PG_OK;
 }
@@ -445,6 +486,7 @@ int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_d
     rec.cls = umma ? 2 : 1;
     rec.flops = 2.0 * a.B * a.L_out * (double)a.Cin * a.Cout * a.K;
     rec.shape[0] = a.Cin; rec.shape[1] = a.Cout; rec.shape[2] = a.K; rec.shape[3] = a.dil; rec.shape[4] = a.L_out;
+    rec.shape[5] = 0;
     cudaEventRecord(rec.e0, s);
   }
   if (umma) {
@@ -696,8 +738,9 @@ int run_plane_conv(pg_handle h, cudaStream_t s, PlaneConvArgs a, const ConvW& w)
     rec.e0 = take_event(h);
     rec.e1 = take_event(h);
     rec.cls = 0;
-    rec.flops = 2.0 * a.B * a.L * (double)a.Cin * a.N * a.K;
+    rec.flops = 2.0 * a.B * a.L * (double)a.Cin * a.N * (w.algo_taps > 0 ? w.algo_taps : (double)a.K);
     rec.shape[0] = a.Cin; rec.shape[1] = a.N; rec.shape[2] = a.K; rec.shape[3] = a.dil; rec.shape[4] = a.L;
+    rec.shape[5] = plane_conv_mt(a);
     cudaEventRecord(rec.e0, s);
   }
   PG_LAUNCH(h, launch_conv_planes(a, s));
@@ -724,6 +767,7 @@ int run_pair_conv(pg_handle h, cudaStream_t s, PairConvArgs a, const ConvW& w1, 
     rec.cls = 0;
     rec.flops = 2.0 * 2.0 * a.B * a.L * (double)a.C * a.C * a.K;
     rec.shape[0] = a.C; rec.shape[1] = -a.C; rec.shape[2] = a.K; rec.shape[3] = a.dil; rec.shape[4] = a.L;
+    rec.shape[5] = pair_conv_mt(a);
     cudaEventRecord(rec.e0, s);
   }
   PG_LAUNCH(h, launch_pair_planes(a, s));
@@ -745,6 +789,7 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
   const int C0 = c.upsample_initial_channel;
   const float SL = 0.1f, INV = 10.f;
   float* dcond = at<float>(h, w.dcond);
+  const int* tlen = at<int>(h, w.tlen);   // hard end of every row, in frames (x L/T per stage)
   PG_LAUNCH(h, launch_cond_gemv(h->emb_g, at<int>(h, w.sid), h->dec_cond_w, h->dec_cond_b, dcond, B,
                                 c.gin_channels, C0, s));
   char* buf[5];
@@ -756,7 +801,7 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
   PG_LAUNCH(h, launch_nlc_to_planes(z, DT_F32, c.inter_channels, 0, zpl, B, T, c.inter_channels, lens, 1.f, s));
   {
     PlaneConvArgs a;
-    a.x = zpl; a.B = B; a.L = T; a.pad = 3;
+    a.x = zpl; a.B = B; a.L = T; a.pad = 3; a.tlen = tlen; a.len_mul = 1;
     a.bbias = dcond; a.bbias_ld = C0;
     a.out16 = reinterpret_cast<__half*>(buf[0]); a.out16_slope = SL;
     PG_TRY(run_plane_conv(h, s, a, h->conv_pre));
@@ -775,6 +820,7 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
       if (k != cur) fr[nf++] = k;
     const int64_t Lin = L;
     L *= S.u;
+    const int mul_in = (int)(Lin / T), mul = (int)(L / T);
     if (!wide) {
       __half* x0 = reinterpret_cast<__half*>(buf[fr[0]]);
       __half* xa = reinterpret_cast<__half*>(buf[fr[1]]);
@@ -784,6 +830,7 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
       {
         PlaneConvArgs a;
         a.x = reinterpret_cast<const __half*>(buf[cur]); a.B = B; a.L = (int)Lin; a.pad = S.up_pad;
+        a.tlen = tlen; a.len_mul = mul_in;
         a.Cout_real = C; a.row_mul = S.u;
         a.out16 = x0;   // raw
         PG_TRY(run_plane_conv(h, s, a, S.up));
@@ -803,7 +850,7 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
           const float o_slope = last && j < nk - 1 ? 1.f : SL;   // the finished mean is stored for ups[i+1]
           {
             PairConvArgs pa;
-            pa.x = xc; pa.B = B; pa.L = (int)L; pa.dil = dil; pa.res_inv = INV;
+            pa.x = xc; pa.B = B; pa.L = (int)L; pa.dil = dil; pa.res_inv = INV; pa.tlen = tlen; pa.len_mul = mul;
             pa.out16 = dst; pa.out16_slope = o_slope; pa.out_scale = o_scale; pa.accin16 = o_accin;
             const int rc = run_pair_conv(h, s, pa, S.c1[j * nd + d], S.c2[j * nd + d]);
             if (rc == PG_OK) {
@@ -814,10 +861,11 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
           }
           PlaneConvArgs a1;
           a1.x = xc; a1.B = B; a1.L = (int)L; a1.dil = dil; a1.pad = (ksz * dil - dil) / 2;
+          a1.tlen = tlen; a1.len_mul = mul;
           a1.out16 = tmp; a1.out16_slope = SL;
           PG_TRY(run_plane_conv(h, s, a1, S.c1[j * nd + d]));
           PlaneConvArgs a2;
-          a2.x = tmp; a2.B = B; a2.L = (int)L; a2.pad = (ksz - 1) / 2;
+          a2.x = tmp; a2.B = B; a2.L = (int)L; a2.pad = (ksz - 1) / 2; a2.tlen = tlen; a2.len_mul = mul;
           a2.res16 = xc; a2.res_inv = INV;
           a2.out16 = dst; a2.out_scale = o_scale; a2.accin16 = o_accin; a2.out16_slope = o_slope;
           PG_TRY(run_plane_conv(h, s, a2, S.c2[j * nd + d]));
@@ -834,6 +882,7 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
       {
         PlaneConvArgs a;
         a.x = reinterpret_cast<const __half*>(buf[cur]); a.B = B; a.L = (int)Lin; a.pad = S.up_pad;
+        a.tlen = tlen; a.len_mul = mul_in;
         a.Cout_real = C; a.row_mul = S.u;
         a.out32 = r0;
         PG_TRY(run_plane_conv(h, s, a, S.up));
@@ -851,6 +900,7 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
           {
             PairConvArgs pa;
             pa.x = xc; pa.B = B; pa.L = (int)L; pa.dil = dil; pa.res32 = rc; pa.res_inv = INV;
+            pa.tlen = tlen; pa.len_mul = mul;
             if (last) {
               pa.out_scale = 1.f / nk;
               pa.accin32 = j > 0 ? acc : nullptr;
@@ -873,10 +923,11 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
           }
           PlaneConvArgs a1;
           a1.x = xc; a1.B = B; a1.L = (int)L; a1.dil = dil; a1.pad = (ksz * dil - dil) / 2;
+          a1.tlen = tlen; a1.len_mul = mul;
           a1.out16 = tmp; a1.out16_slope = SL;
           PG_TRY(run_plane_conv(h, s, a1, S.c1[j * nd + d]));
           PlaneConvArgs a2;
-          a2.x = tmp; a2.B = B; a2.L = (int)L; a2.pad = (ksz - 1) / 2;
+          a2.x = tmp; a2.B = B; a2.L = (int)L; a2.pad = (ksz - 1) / 2; a2.tlen = tlen; a2.len_mul = mul;
           a2.res32 = rc;
           if (last) {
             a2.out_scale = 1.f / nk;
@@ -895,7 +946,7 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
       }
       PG_TRY(record_tap_planes(h, s, "dec.stage" + std::to_string(i), acc, DT_F32, 1.f, B, L, C));
       const int Cl = C;
-      PG_LAUNCH(h, launch_conv_post_planes(acc, DT_F32, h->conv_post_w, wave, B, (int)L, Cl, 7, 0.01f, s));
+      PG_LAUNCH(h, launch_conv_post_planes(acc, DT_F32, h->conv_post_w, wave, B, (int)L, Cl, 7, 0.01f, tlen, mul, s));
       return PG_OK;
     }
     // acc lives in buf[cur]: the next stage reads it
@@ -905,7 +956,7 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
 
 int run_decoder(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const float* z,
                 const float* source, float* wave) {
-  if (h->cfg.flags & (PG_FLAG_FORCE_SIMT | PG_FLAG_LEGACY_DECODER))
+  if (!h->planes_ok || (h->cfg.flags & (PG_FLAG_FORCE_SIMT | PG_FLAG_LEGACY_DECODER)))
     return run_generator(h, s, w, B, T, z, source, wave);
   return run_generator_planes(h, s, w, B, T, z, source, wave);
 }
@@ -1112,6 +1163,14 @@ int pg_finalize(pg_handle h) {
       for (int j = 0; j < 7; ++j) wp[(size_t)j * cin + ci] = W->data[(size_t)ci * 7 + j];
     PG_TRY(upload(h, wp, &h->conv_post_w));
   }
+  // every stage must fit the channel-plane kernels (C % 32 == 0, power of two); otherwise (upstream v1
+  // 32k/48k: five stages, C = 16 at the end) the whole decoder runs on the time-major tcgen05 / CUDA-core path
+  h->planes_ok = true;
+  for (const StageW& S : h->stages)
+    if (S.C % 32 || (S.C & (S.C - 1))) h->planes_ok = false;
+  if (h->stages.back().C % 8 || h->stages.back().C > 256)
+    return fail(PG_ERR_UNSUPPORTED, "last decoder stage width must be a multiple of 8 and <= 256 channels");
+  if (const char* e = getenv("PG_GRAPH_CACHE")) h->graph_cap = std::max(0, atoi(e));
   h->host.clear();
   h->finalized = true;
   return PG_OK;
@@ -1123,30 +1182,31 @@ size_t pg_workspace_bytes(pg_handle h, int B, int T) {
 }
 
 static int prepare(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const int64_t* lengths,
-                   const int64_t* pitch, const int64_t* sid) {
+                   const int64_t* pitch, const int64_t* sid, const CallMeta* meta = nullptr) {
   PG_TRY(ensure_ws(h, w.total));
-  PG_LAUNCH(h, launch_prepare_ints(lengths, pitch, sid, at<int>(h, w.lens), at<int>(h, w.pitch),
-                                   at<int>(h, w.sid), B, T, h->cfg.spk_embed_dim, s));
+  PG_LAUNCH(h, launch_prepare_ints(lengths, pitch, sid, meta, at<int>(h, w.lens), at<int>(h, w.tlen),
+                                   at<int>(h, w.pitch), at<int>(h, w.sid), B, T, h->cfg.spk_embed_dim, s));
   return PG_OK;
 }
 
-// the launch sequence of Synthesizer.infer (synthesizers.py:162-188) on stream s
+// the launch sequence of Synthesizer.infer (synthesizers.py:162-188) on stream s over [B][T] rows
+// (T = the padded frame count); the true length / raggedness / per-row seeds come from device memory
 static int infer_body(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const float* phone,
                       const int64_t* lengths, const int64_t* pitch, const float* f0, const int64_t* sid,
-                      const float* eps_zp, const float* eps_src, uint64_t seed, const uint64_t* seed_dev,
-                      float* wave) {
+                      const float* eps_zp, const float* eps_src, int eps_T, const CallMeta* meta,
+                      const uint64_t* seeds_dev, float* wave) {
   const pg_config& c = h->cfg;
-  PG_TRY(prepare(h, s, w, B, T, lengths, pitch, sid));
+  PG_TRY(prepare(h, s, w, B, T, lengths, pitch, sid, meta));
   PG_TRY(run_text_encoder(h, s, w, B, T, phone));
   const int C = c.inter_channels;
   float* z = at<float>(h, w.z);
-  PG_LAUNCH(h, launch_reparam(at<float>(h, w.stats), eps_zp, seed, seed_dev, at<int>(h, w.lens),
+  PG_LAUNCH(h, launch_reparam(at<float>(h, w.stats), eps_zp, eps_T, 0, seeds_dev, at<int>(h, w.lens),
                               at<float>(h, w.m_p), at<float>(h, w.logs_p), at<float>(h, w.z_p), z, B,
                               T, C, s));
   PG_TRY(run_flow(h, s, w, B, T, z));
   float* source = at<float>(h, w.source);
-  PG_LAUNCH(h, launch_source(f0, eps_src, seed, seed_dev, h->src_w, h->src_b, at<double>(h, w.phase),
-                             source, nullptr, B, T, h->upp, c.sr, s));
+  PG_LAUNCH(h, launch_source(f0, eps_src, eps_T, 0, seeds_dev, at<int>(h, w.tlen), h->src_w, h->src_b,
+                             at<double>(h, w.phase), source, nullptr, B, T, h->upp, c.sr, s));
   ++h->launches;   // launch_source issues two kernels
   PG_TRY(record_tap(h, s, "source", source, DT_F32, B, (int64_t)T * h->upp, 1));
   PG_TRY(run_decoder(h, s, w, B, T, z, source, wave));
@@ -1154,87 +1214,176 @@ static int infer_body(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, co
 }
 
 namespace {
+// handle-owned staging: inputs padded to [B][Tp] rows, per-call scalars, the waveform
 struct IoPtrs {
-  float* phone; int64_t* len; int64_t* pitch; float* f0; int64_t* sid; uint64_t* seed; float* wave;
-  size_t n_phone, n_len, n_pitch, n_f0, n_sid, n_wave, total;
+  float* phone; int64_t* len; int64_t* pitch; float* f0; int64_t* sid; uint64_t* seeds; CallMeta* meta; float* wave;
+  size_t total;
 };
-IoPtrs io_layout(const pg_config& c, int upp, char* base, int B, int T) {
+IoPtrs io_layout(const pg_config& c, int upp, char* base, int B, int Tp) {
   IoPtrs p;
-  const size_t BT = (size_t)B * T;
-  p.n_phone = BT * c.input_dim * sizeof(float);
-  p.n_len = B * sizeof(int64_t);
-  p.n_pitch = BT * sizeof(int64_t);
-  p.n_f0 = BT * sizeof(float);
-  p.n_sid = B * sizeof(int64_t);
-  p.n_wave = BT * upp * sizeof(float);
+  const size_t BT = (size_t)B * Tp;
   auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
   size_t off = 0;
   auto take = [&](size_t n) { char* q = base + off; off += al(n); return q; };
-  p.phone = reinterpret_cast<float*>(take(p.n_phone));
-  p.len = reinterpret_cast<int64_t*>(take(p.n_len));
-  p.pitch = reinterpret_cast<int64_t*>(take(p.n_pitch));
-  p.f0 = reinterpret_cast<float*>(take(p.n_f0));
-  p.sid = reinterpret_cast<int64_t*>(take(p.n_sid));
-  p.seed = reinterpret_cast<uint64_t*>(take(sizeof(uint64_t)));
-  p.wave = reinterpret_cast<float*>(take(p.n_wave));
+  p.phone = reinterpret_cast<float*>(take(BT * c.input_dim * sizeof(float)));
+  p.len = reinterpret_cast<int64_t*>(take(B * sizeof(int64_t)));
+  p.pitch = reinterpret_cast<int64_t*>(take(BT * sizeof(int64_t)));
+  p.f0 = reinterpret_cast<float*>(take(BT * sizeof(float)));
+  p.sid = reinterpret_cast<int64_t*>(take(B * sizeof(int64_t)));
+  p.seeds = reinterpret_cast<uint64_t*>(take(B * sizeof(uint64_t)));
+  p.meta = reinterpret_cast<CallMeta*>(take(sizeof(CallMeta)));
+  p.wave = reinterpret_cast<float*>(take(BT * upp * sizeof(float)));
   p.total = off;
   return p;
 }
+
+// rows of `row_bytes` from a dense [B][T] tensor into / out of the padded [B][Tp] staging
+cudaError_t copy_rows(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, int B,
+                      cudaStream_t s) {
+  if (B == 1 || (dst_pitch == row_bytes && src_pitch == row_bytes))
+    return cudaMemcpyAsync(dst, src, row_bytes * B, cudaMemcpyDefault, s);
+  return cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, B, cudaMemcpyDefault, s);
+}
 }  // namespace
 
-// pg_infer over the handle's fixed staging buffers: inputs (device or pinned host memory) are copied
-// in, the waveform is copied out, and the launch sequence between them is a CUDA graph per (B, T) --
-// launched directly on the first call of a shape (lazy one-time setup is not capturable), captured on
-// the second and replayed afterwards.  A refused capture falls back to direct launches for good.
-static int infer_staged(pg_handle h, pg_handle_s::GraphEntry& ge, cudaStream_t s, const Ws& w, int B, int T,
-                        const float* phone, const int64_t* lengths, const int64_t* pitch, const float* f0,
-                        const int64_t* sid, uint64_t seed, float* wave) {
+// One call's tensors: a dense [B][T] batch (pg_infer) or a list of stand-alone segments (pg_infer_segments)
+struct CallIo {
+  int B = 0, T = 0, ragged = 0;       // T = frames of the longest row
+  const float* phone = nullptr; const int64_t* lengths = nullptr; const int64_t* pitch = nullptr;
+  const float* f0 = nullptr; const int64_t* sid = nullptr;
+  const float* eps_zp = nullptr; const float* eps_src = nullptr;
+  float* wave = nullptr; float* aux = nullptr;
+  const pg_segment* segs = nullptr;   // ragged: per-row pointers, the dense ones above are unused
+};
+
+// pg_infer / pg_infer_segments: stage the inputs (device or pinned host memory) into the handle's padded
+// [B][Tp] buffers, run the launch sequence -- a CUDA graph per (B, Tp), captured on the second call of a
+// shape and replayed afterwards, when the stream is capturable and the noise is device-drawn -- and copy
+// the waveform (and latents) out.  A refused capture falls back to direct launches for that shape.
+static int infer_staged(pg_handle h, cudaStream_t s, const CallIo& io_in, uint64_t seed) {
+  const pg_config& c = h->cfg;
+  const int B = io_in.B, T = io_in.T;
+  const int Tp = pad_frames(h, T);
+  const Ws w = plan_ws(c, B, Tp);
   PG_TRY(ensure_ws(h, w.total));
-  const size_t need = io_layout(h->cfg, h->upp, nullptr, B, T).total;
+  const size_t need = io_layout(c, h->upp, nullptr, B, Tp).total;
   if (h->io.bytes < need) {
     invalidate_graphs(h);
     if (h->io.p) PG_CUDA_CHECK(cudaFree(h->io.p));
     h->io.p = nullptr;
     h->io.bytes = 0;
     PG_CUDA_CHECK(cudaMalloc(&h->io.p, need));
+    PG_CUDA_CHECK(cudaMemset(h->io.p, 0, need));   // padding rows are read (and masked): keep them finite
     h->io.bytes = need;
   }
-  const IoPtrs io = io_layout(h->cfg, h->upp, reinterpret_cast<char*>(h->io.p), B, T);
-  if (!ge.exec && !ge.failed && ge.uses >= 1) {
-    cudaGraph_t graph = nullptr;
-    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      h->launches = 0;
-      const int rc = infer_body(h, s, w, B, T, io.phone, io.len, io.pitch, io.f0, io.sid, nullptr, nullptr,
-                                0, io.seed, io.wave);
-      cudaError_t e = cudaStreamEndCapture(s, &graph);
-      if (rc == PG_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&ge.exec, graph, 0);
-      if (graph) cudaGraphDestroy(graph);
-      if (rc != PG_OK || e != cudaSuccess || !ge.exec) {
-        ge.exec = nullptr;
-        ge.failed = true;
-      }
-      ge.launches = h->launches;
-    } else {
-      ge.failed = true;
+  const IoPtrs io = io_layout(c, h->upp, reinterpret_cast<char*>(h->io.p), B, Tp);
+  const size_t D = c.input_dim, U = h->upp, C = c.inter_channels;
+  const float* eps_zp = io_in.eps_zp;
+  const float* eps_src = io_in.eps_src;
+  int eps_T = T;
+  if (io_in.segs && io_in.segs[0].eps_zp) {     // explicit noise per segment: staged into padded rows too
+    const size_t n_zp = (size_t)B * Tp * C * 4, n_src = (size_t)B * Tp * U * 4;
+    if (h->io_eps.bytes < n_zp + n_src) {
+      if (h->io_eps.p) PG_CUDA_CHECK(cudaFree(h->io_eps.p));
+      h->io_eps.p = nullptr;
+      h->io_eps.bytes = 0;
+      PG_CUDA_CHECK(cudaMalloc(&h->io_eps.p, n_zp + n_src));
+      h->io_eps.bytes = n_zp + n_src;
     }
-    cudaGetLastError();
+    float* ez = reinterpret_cast<float*>(h->io_eps.p);
+    float* es = reinterpret_cast<float*>(reinterpret_cast<char*>(h->io_eps.p) + n_zp);
+    for (int b = 0; b < B; ++b) {
+      const pg_segment& g = io_in.segs[b];
+      PG_CUDA_CHECK(cudaMemcpyAsync(ez + (size_t)b * Tp * C, g.eps_zp, (size_t)g.T * C * 4, cudaMemcpyDefault, s));
+      PG_CUDA_CHECK(cudaMemcpyAsync(es + (size_t)b * Tp * U, g.eps_src, (size_t)g.T * U * 4, cudaMemcpyDefault, s));
+    }
+    eps_zp = ez;
+    eps_src = es;
+    eps_T = Tp;
   }
-  ++ge.uses;
-  PG_CUDA_CHECK(cudaMemcpyAsync(io.phone, phone, io.n_phone, cudaMemcpyDefault, s));
-  PG_CUDA_CHECK(cudaMemcpyAsync(io.len, lengths, io.n_len, cudaMemcpyDefault, s));
-  PG_CUDA_CHECK(cudaMemcpyAsync(io.pitch, pitch, io.n_pitch, cudaMemcpyDefault, s));
-  PG_CUDA_CHECK(cudaMemcpyAsync(io.f0, f0, io.n_f0, cudaMemcpyDefault, s));
-  PG_CUDA_CHECK(cudaMemcpyAsync(io.sid, sid, io.n_sid, cudaMemcpyDefault, s));
-  if (ge.exec) {
-    h->launches = ge.launches;
-    PG_LAUNCH(h, launch_set_seed(io.seed, seed, s));
-    PG_CUDA_CHECK(cudaGraphLaunch(ge.exec, s));
+  const bool graphable = h->graph_cap > 0 && !(c.flags & (PG_FLAG_PROFILE | PG_FLAG_KEEP_TAPS | PG_FLAG_NO_GRAPHS)) &&
+                         !eps_zp && !eps_src && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+  pg_handle_s::GraphEntry* ge = nullptr;
+  if (graphable) {
+    ge = &h->graphs[std::make_pair(B, Tp)];
+    ge->last_use = ++h->graph_clock;
+    if (!ge->exec && !ge->failed && ge->uses >= 1) {
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        h->launches = 0;
+        const int rc = infer_body(h, s, w, B, Tp, io.phone, io.len, io.pitch, io.f0, io.sid, nullptr, nullptr, 0,
+                                  io.meta, io.seeds, io.wave);
+        cudaError_t e = cudaStreamEndCapture(s, &graph);
+        if (rc == PG_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&ge->exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != PG_OK || e != cudaSuccess || !ge->exec) {
+          ge->exec = nullptr;
+          ge->failed = true;
+        }
+        ge->launches = h->launches;
+      } else {
+        ge->failed = true;
+      }
+      cudaGetLastError();
+      trim_graphs(h);
+      ge = &h->graphs[std::make_pair(B, Tp)];
+    }
+    ++ge->uses;
+  }
+  h->launches = 0;
+  if (io_in.segs) {
+    for (int b = 0; b < B; ++b) {
+      const pg_segment& g = io_in.segs[b];
+      PG_CUDA_CHECK(cudaMemcpyAsync(io.phone + (size_t)b * Tp * D, g.phone, (size_t)g.T * D * 4, cudaMemcpyDefault, s));
+      PG_CUDA_CHECK(cudaMemcpyAsync(io.pitch + (size_t)b * Tp, g.pitch, (size_t)g.T * 8, cudaMemcpyDefault, s));
+      PG_CUDA_CHECK(cudaMemcpyAsync(io.f0 + (size_t)b * Tp, g.f0, (size_t)g.T * 4, cudaMemcpyDefault, s));
+    }
+    // lengths / speaker ids travel as kernel parameters (no pageable H2D copy: that would sync the stream)
+    for (int b0 = 0; b0 < B; b0 += RowScalars::N) {
+      RowScalars rs;
+      const int n = std::min(RowScalars::N, B - b0);
+      for (int i = 0; i < n; ++i) {
+        rs.len[i] = io_in.segs[b0 + i].T;
+        rs.sid[i] = (int)io_in.segs[b0 + i].sid;
+      }
+      PG_LAUNCH(h, launch_set_rows(io.len + b0, io.sid + b0, rs, n, s));
+    }
   } else {
-    h->launches = 0;
-    PG_TRY(infer_body(h, s, w, B, T, io.phone, io.len, io.pitch, io.f0, io.sid, nullptr, nullptr, seed,
-                      nullptr, io.wave));
+    PG_CUDA_CHECK(copy_rows(io.phone, (size_t)Tp * D * 4, io_in.phone, (size_t)T * D * 4, (size_t)T * D * 4, B, s));
+    PG_CUDA_CHECK(copy_rows(io.pitch, (size_t)Tp * 8, io_in.pitch, (size_t)T * 8, (size_t)T * 8, B, s));
+    PG_CUDA_CHECK(copy_rows(io.f0, (size_t)Tp * 4, io_in.f0, (size_t)T * 4, (size_t)T * 4, B, s));
+    PG_CUDA_CHECK(cudaMemcpyAsync(io.len, io_in.lengths, B * sizeof(int64_t), cudaMemcpyDefault, s));
+    PG_CUDA_CHECK(cudaMemcpyAsync(io.sid, io_in.sid, B * sizeof(int64_t), cudaMemcpyDefault, s));
   }
-  PG_CUDA_CHECK(cudaMemcpyAsync(wave, io.wave, io.n_wave, cudaMemcpyDefault, s));
+  PG_LAUNCH(h, launch_set_call(io.meta, io.seeds, B, T, io_in.ragged, seed, s));
+  if (ge && ge->exec) {
+    h->launches += ge->launches;
+    PG_CUDA_CHECK(cudaGraphLaunch(ge->exec, s));
+  } else {
+    PG_TRY(infer_body(h, s, w, B, Tp, io.phone, io.len, io.pitch, io.f0, io.sid, eps_zp, eps_src, eps_T, io.meta,
+                      io.seeds, io.wave));
+  }
+  const size_t offs[4] = {w.z, w.z_p, w.m_p, w.logs_p};
+  if (io_in.segs) {
+    for (int b = 0; b < B; ++b) {
+      const pg_segment& g = io_in.segs[b];
+      // t_pad_tgt of pipeline.py:397 is dropped here, so the caller's buffer can be the concatenated clip
+      PG_CUDA_CHECK(cudaMemcpyAsync(g.wave, io.wave + (size_t)b * Tp * U + g.trim, ((size_t)g.T * U - 2 * (size_t)g.trim) * 4,
+                                    cudaMemcpyDefault, s));
+      if (g.aux)
+        for (int i = 0; i < 4; ++i)
+          PG_CUDA_CHECK(cudaMemcpyAsync(g.aux + (size_t)i * g.T * C, at<float>(h, offs[i]) + (size_t)b * Tp * C,
+                                        (size_t)g.T * C * 4, cudaMemcpyDefault, s));
+    }
+  } else {
+    PG_CUDA_CHECK(copy_rows(io_in.wave, (size_t)T * U * 4, io.wave, (size_t)Tp * U * 4, (size_t)T * U * 4, B, s));
+    if (io_in.aux) {
+      const size_t n = (size_t)B * T * C;
+      for (int i = 0; i < 4; ++i)
+        PG_CUDA_CHECK(copy_rows(io_in.aux + i * n, (size_t)T * C * 4, at<float>(h, offs[i]), (size_t)Tp * C * 4,
+                                (size_t)T * C * 4, B, s));
+    }
+  }
   return PG_OK;
 }
 
@@ -1245,29 +1394,37 @@ int pg_infer(pg_handle h, void* stream, int B, int T, const float* phone, const 
   if (!phone || !lengths || !pitch || !f0 || !sid || !wave)
     return fail(PG_ERR_INVALID, "null tensor argument to pg_infer");
   Guard g(h->device);
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const pg_config& c = h->cfg;
-  const Ws w = plan_ws(c, B, T);
-  h->launches = 0;
-  // graph replay: device-drawn noise only, a capturable (non-legacy) stream, no per-launch instrumentation
-  const bool graphable = !(c.flags & (PG_FLAG_PROFILE | PG_FLAG_KEEP_TAPS | PG_FLAG_NO_GRAPHS)) && !eps_zp &&
-                         !eps_src && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
-  int rc;
-  if (graphable)
-    rc = infer_staged(h, h->graphs[std::make_pair(B, T)], s, w, B, T, phone, lengths, pitch, f0, sid, seed, wave);
-  else
-    rc = infer_body(h, s, w, B, T, phone, lengths, pitch, f0, sid, eps_zp, eps_src, seed, nullptr, wave);
-  if (rc != PG_OK) return rc;
-  if (aux) {
-    const int C = c.inter_channels;
-    const size_t n = (size_t)B * T * C * sizeof(float);
-    char* a = reinterpret_cast<char*>(aux);
-    PG_CUDA_CHECK(cudaMemcpyAsync(a, at<float>(h, w.z), n, cudaMemcpyDeviceToDevice, s));
-    PG_CUDA_CHECK(cudaMemcpyAsync(a + n, at<float>(h, w.z_p), n, cudaMemcpyDeviceToDevice, s));
-    PG_CUDA_CHECK(cudaMemcpyAsync(a + 2 * n, at<float>(h, w.m_p), n, cudaMemcpyDeviceToDevice, s));
-    PG_CUDA_CHECK(cudaMemcpyAsync(a + 3 * n, at<float>(h, w.logs_p), n, cudaMemcpyDeviceToDevice, s));
+  CallIo io;
+  io.B = B; io.T = T; io.phone = phone; io.lengths = lengths; io.pitch = pitch; io.f0 = f0; io.sid = sid;
+  io.eps_zp = eps_zp; io.eps_src = eps_src; io.wave = wave; io.aux = aux;
+  return infer_staged(h, reinterpret_cast<cudaStream_t>(stream), io, seed);
+}
+
+int pg_infer_segments(pg_handle h, void* stream, int n, const pg_segment* segs, uint64_t seed) {
+  if (!h) return fail(PG_ERR_INVALID, "null handle");
+  if (!segs || n <= 0) return fail(PG_ERR_INVALID, "empty segment list");
+  int T = 0;
+  bool any_eps = false, all_eps = true;
+  for (int b = 0; b < n; ++b) {
+    const pg_segment& g = segs[b];
+    if (g.T <= 0 || !g.phone || !g.pitch || !g.f0 || !g.wave)
+      return fail(PG_ERR_INVALID, "segment " + std::to_string(b) + ": null tensor or T <= 0");
+    if (g.trim < 0 || 2 * (int64_t)g.trim >= (int64_t)g.T * h->upp)
+      return fail(PG_ERR_INVALID, "segment " + std::to_string(b) + ": trim does not leave any samples");
+    const bool e = g.eps_zp && g.eps_src;
+    if (!e && (g.eps_zp || g.eps_src)) return fail(PG_ERR_INVALID, "eps_zp and eps_src must be given together");
+    any_eps |= e;
+    all_eps &= e;
+    T = std::max(T, (int)g.T);
   }
-  return PG_OK;
+  if (any_eps && !all_eps) return fail(PG_ERR_INVALID, "explicit noise must be given for all segments or none");
+  PG_TRY(check_ready(h, n, T));
+  if (!h->planes_ok || (h->cfg.flags & (PG_FLAG_FORCE_SIMT | PG_FLAG_LEGACY_DECODER)))
+    return fail(PG_ERR_UNSUPPORTED, "ragged segment batches need the channel-plane decoder");
+  Guard g(h->device);
+  CallIo io;
+  io.B = n; io.T = T; io.ragged = 1; io.segs = segs;
+  return infer_staged(h, reinterpret_cast<cudaStream_t>(stream), io, seed);
 }
 
 int pg_graph_count(pg_handle h) {
@@ -1277,44 +1434,103 @@ int pg_graph_count(pg_handle h) {
   return n;
 }
 
+int pg_set_graph_cache(pg_handle h, int max_graphs) {
+  if (!h || max_graphs < 0) return fail(PG_ERR_INVALID, "bad argument");
+  Guard g(h->device);
+  h->graph_cap = max_graphs;
+  trim_graphs(h);
+  return PG_OK;
+}
+
+int pg_padded_frames(pg_handle h, int T) { return (h && T > 0) ? pad_frames(h, T) : 0; }
+
+static int own_stream(pg_handle h, cudaStream_t* out) {
+  if (!h->own_stream) PG_CUDA_CHECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  *out = h->own_stream;
+  return PG_OK;
+}
+
 int pg_infer_host(pg_handle h, int B, int T, const float* phone, const int64_t* lengths,
                   const int64_t* pitch, const float* f0, const int64_t* sid, uint64_t seed,
                   float* wave) {
   PG_TRY(check_ready(h, B, T));
-  if (!phone || !lengths || !pitch || !f0 || !sid || !wave)
-    return fail(PG_ERR_INVALID, "null tensor argument to pg_infer_host");
   Guard g(h->device);
-  const pg_config& c = h->cfg;
-  const size_t BT = (size_t)B * T;
-  const size_t n_phone = BT * c.input_dim * sizeof(float), n_len = B * sizeof(int64_t),
-               n_pitch = BT * sizeof(int64_t), n_f0 = BT * sizeof(float), n_sid = B * sizeof(int64_t),
-               n_wave = BT * h->upp * sizeof(float);
-  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
-  const size_t total = al(n_phone) + al(n_len) + al(n_pitch) + al(n_f0) + al(n_sid) + al(n_wave);
-  if (h->host_stage.bytes < total) {
-    if (h->host_stage.p) PG_CUDA_CHECK(cudaFree(h->host_stage.p));
-    h->host_stage.p = nullptr;
-    h->host_stage.bytes = 0;
-    PG_CUDA_CHECK(cudaMalloc(&h->host_stage.p, total));
-    h->host_stage.bytes = total;
-  }
-  char* base = reinterpret_cast<char*>(h->host_stage.p);
-  float* d_phone = reinterpret_cast<float*>(base);
-  int64_t* d_len = reinterpret_cast<int64_t*>(base + al(n_phone));
-  int64_t* d_pitch = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(d_len) + al(n_len));
-  float* d_f0 = reinterpret_cast<float*>(reinterpret_cast<char*>(d_pitch) + al(n_pitch));
-  int64_t* d_sid = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(d_f0) + al(n_f0));
-  float* d_wave = reinterpret_cast<float*>(reinterpret_cast<char*>(d_sid) + al(n_sid));
-  cudaStream_t s = 0;
-  PG_CUDA_CHECK(cudaMemcpyAsync(d_phone, phone, n_phone, cudaMemcpyHostToDevice, s));
-  PG_CUDA_CHECK(cudaMemcpyAsync(d_len, lengths, n_len, cudaMemcpyHostToDevice, s));
-  PG_CUDA_CHECK(cudaMemcpyAsync(d_pitch, pitch, n_pitch, cudaMemcpyHostToDevice, s));
-  PG_CUDA_CHECK(cudaMemcpyAsync(d_f0, f0, n_f0, cudaMemcpyHostToDevice, s));
-  PG_CUDA_CHECK(cudaMemcpyAsync(d_sid, sid, n_sid, cudaMemcpyHostToDevice, s));
-  PG_TRY(pg_infer(h, s, B, T, d_phone, d_len, d_pitch, d_f0, d_sid, nullptr, nullptr, seed, d_wave,
-                  nullptr));
-  PG_CUDA_CHECK(cudaMemcpyAsync(wave, d_wave, n_wave, cudaMemcpyDeviceToHost, s));
+  cudaStream_t s = nullptr;
+  PG_TRY(own_stream(h, &s));
+  // the staged path copies straight from / to the host buffers on the handle's own stream
+  PG_TRY(pg_infer(h, s, B, T, phone, lengths, pitch, f0, sid, nullptr, nullptr, seed, wave, nullptr));
   PG_CUDA_CHECK(cudaStreamSynchronize(s));
+  return PG_OK;
+}
+
+// ---- pipeline glue ----
+int pg_coarse_pitch(pg_handle h, void* stream, int64_t n, const void* f0, int f0_dtype, double f0_min,
+                    double f0_max, int64_t* pitch, float* pitchf) {
+  if (!h || !f0 || !pitch || !pitchf || n < 0) return fail(PG_ERR_INVALID, "bad argument to pg_coarse_pitch");
+  if (f0_dtype != PG_F32 && f0_dtype != PG_F64) return fail(PG_ERR_UNSUPPORTED, "f0 must be f32 or f64");
+  if (!(f0_max > f0_min) || f0_min < 0) return fail(PG_ERR_INVALID, "need 0 <= f0_min < f0_max");
+  Guard g(h->device);
+  PG_CUDA_CHECK(launch_coarse_pitch(f0, f0_dtype == PG_F64, n, f0_min, f0_max, pitch, pitchf,
+                                    reinterpret_cast<cudaStream_t>(stream)));
+  return PG_OK;
+}
+
+int pg_prepare_features(pg_handle h, void* stream, int64_t n_feat_frames, int64_t n_audio_frames,
+                        const float* feats, const float* feats0, const float* pitchf, float protect,
+                        float* phone, int64_t* p_len_out) {
+  if (!h || !feats || !phone || n_feat_frames <= 0 || n_audio_frames <= 0)
+    return fail(PG_ERR_INVALID, "bad argument to pg_prepare_features");
+  // p_len = audio0.shape[0] // window, lowered to the interpolated feature length (pipeline.py:258-263)
+  const int64_t p_len = std::min(n_audio_frames, 2 * n_feat_frames);
+  if (p_len_out) *p_len_out = p_len;
+  Guard g(h->device);
+  PG_CUDA_CHECK(launch_prepare_features(feats, feats0, pitchf, protect, phone, p_len, h->cfg.input_dim,
+                                        reinterpret_cast<cudaStream_t>(stream)));
+  return PG_OK;
+}
+
+int pg_postprocess(pg_handle h, void* stream, const float* audio, int64_t n, const float* src_audio,
+                   int64_t n_src, int src_rate, int tgt_rate, float rms_mix_rate, float* audio_out,
+                   int16_t* pcm_out) {
+  if (!h || !audio || !pcm_out || n <= 0) return fail(PG_ERR_INVALID, "bad argument to pg_postprocess");
+  const bool rms = src_audio != nullptr && rms_mix_rate != 1.f;
+  if (rms && (n_src <= 0 || src_rate < 2 || tgt_rate < 2)) return fail(PG_ERR_INVALID, "bad source audio / rates");
+  Guard g(h->device);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int n1 = rms ? (int)(1 + n_src / (src_rate / 2)) : 0, n2 = rms ? (int)(1 + n / (tgt_rate / 2)) : 0;
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  const size_t o_max = 0, o_r1 = 256, o_r2 = o_r1 + al(4 * (size_t)n1), o_tmp = o_r2 + al(4 * (size_t)n2),
+               o_pcm = o_tmp + al(rms && !audio_out ? 4 * (size_t)n : 0), total = o_pcm + al(2 * (size_t)n);
+  if (h->post.bytes < total) {
+    if (h->post.p) {
+      PG_CUDA_CHECK(cudaStreamSynchronize(s));
+      PG_CUDA_CHECK(cudaFree(h->post.p));
+    }
+    h->post.p = nullptr;
+    h->post.bytes = 0;
+    PG_CUDA_CHECK(cudaMalloc(&h->post.p, total));
+    h->post.bytes = total;
+  }
+  char* base = reinterpret_cast<char*>(h->post.p);
+  unsigned int* max_bits = reinterpret_cast<unsigned int*>(base + o_max);
+  int16_t* pcm = reinterpret_cast<int16_t*>(base + o_pcm);
+  PG_CUDA_CHECK(cudaMemsetAsync(max_bits, 0, sizeof(unsigned int), s));
+  const float* x = audio;
+  if (rms) {
+    float* r1 = reinterpret_cast<float*>(base + o_r1);
+    float* r2 = reinterpret_cast<float*>(base + o_r2);
+    float* y = audio_out ? audio_out : reinterpret_cast<float*>(base + o_tmp);
+    PG_LAUNCH(h, launch_frame_rms(src_audio, n_src, src_rate, r1, n1, s));
+    PG_LAUNCH(h, launch_frame_rms(audio, n, tgt_rate, r2, n2, s));
+    PG_LAUNCH(h, launch_change_rms(audio, n, r1, n1, r2, n2, rms_mix_rate, y, max_bits, s));
+    x = y;
+  } else {
+    PG_LAUNCH(h, launch_absmax(audio, n, max_bits, s));
+    if (audio_out && audio_out != audio)
+      PG_CUDA_CHECK(cudaMemcpyAsync(audio_out, audio, 4 * (size_t)n, cudaMemcpyDefault, s));
+  }
+  PG_LAUNCH(h, launch_to_int16(x, n, max_bits, pcm, s));
+  PG_CUDA_CHECK(cudaMemcpyAsync(pcm_out, pcm, 2 * (size_t)n, cudaMemcpyDefault, s));
   return PG_OK;
 }
 
@@ -1330,7 +1546,7 @@ int pg_text_encoder(pg_handle h, void* stream, int B, int T, const float* phone,
   PG_TRY(run_text_encoder(h, s, w, B, T, phone));
   // split stats with eps == 0: z_p/z are scratch
   PG_CUDA_CHECK(cudaMemsetAsync(at<float>(h, w.fa), 0, sizeof(float) * (size_t)B * T * h->cfg.inter_channels, s));
-  PG_LAUNCH(h, launch_reparam(at<float>(h, w.stats), at<float>(h, w.fa), 0, nullptr, at<int>(h, w.lens), m_p,
+  PG_LAUNCH(h, launch_reparam(at<float>(h, w.stats), at<float>(h, w.fa), T, 0, nullptr, at<int>(h, w.lens), m_p,
                               logs_p, at<float>(h, w.z_p), at<float>(h, w.z), B, T,
                               h->cfg.inter_channels, s));
   return PG_OK;
@@ -1360,7 +1576,7 @@ int pg_source(pg_handle h, void* stream, int B, int T, const float* f0, const fl
   const Ws w = plan_ws(h->cfg, B, T);
   h->launches = 0;
   PG_TRY(ensure_ws(h, w.total));
-  PG_LAUNCH(h, launch_source(f0, eps_src, seed, nullptr, h->src_w, h->src_b, at<double>(h, w.phase),
+  PG_LAUNCH(h, launch_source(f0, eps_src, T, seed, nullptr, nullptr, h->src_w, h->src_b, at<double>(h, w.phase),
                              source, sine, B, T, h->upp, h->cfg.sr, s));
   ++h->launches;
   return PG_OK;
@@ -1380,8 +1596,8 @@ int pg_generator(pg_handle h, void* stream, int B, int T, const float* z, const 
   int64_t* d_len = reinterpret_cast<int64_t*>(at<char>(h, w.qkv));
   PG_CUDA_CHECK(cudaMemcpyAsync(d_len, full.data(), sizeof(int64_t) * B, cudaMemcpyHostToDevice, s));
   PG_CUDA_CHECK(cudaStreamSynchronize(s));
-  PG_LAUNCH(h, launch_prepare_ints(d_len, nullptr, sid, at<int>(h, w.lens), at<int>(h, w.pitch),
-                                   at<int>(h, w.sid), B, T, h->cfg.spk_embed_dim, s));
+  PG_LAUNCH(h, launch_prepare_ints(d_len, nullptr, sid, nullptr, at<int>(h, w.lens), at<int>(h, w.tlen),
+                                   at<int>(h, w.pitch), at<int>(h, w.sid), B, T, h->cfg.spk_embed_dim, s));
   PG_TRY(run_decoder(h, s, w, B, T, z, source, wave));
   return PG_OK;
 }
@@ -1429,7 +1645,7 @@ int pg_profile_read(pg_handle h, double* ms_out, double* flops_out, int64_t* lau
     ms_out[r.cls] += ms;
     flops_out[r.cls] += r.flops;
     launches_out[r.cls] += 1;
-    std::vector<double>& row = h->prof_table[{r.cls, r.shape[0], r.shape[1], r.shape[2], r.shape[3]}];
+    std::vector<double>& row = h->prof_table[{r.cls, r.shape[0], r.shape[1], r.shape[2], r.shape[3], r.shape[5]}];
     row.resize(3, 0.0);
     row[0] += 1;
     row[1] += ms;
@@ -1446,11 +1662,11 @@ int pg_profile_table(pg_handle h, double* rows, int max_rows) {
   int n = 0;
   for (auto& kv : h->prof_table) {
     if (n >= max_rows) break;
-    double* r = rows + (size_t)n * 8;
-    for (int i = 0; i < 5; ++i) r[i] = kv.first[i];
-    r[5] = kv.second[0];
-    r[6] = kv.second[1];
-    r[7] = kv.second[2];
+    double* r = rows + (size_t)n * 9;
+    for (int i = 0; i < 6; ++i) r[i] = kv.first[i];
+    r[6] = kv.second[0];
+    r[7] = kv.second[1];
+    r[8] = kv.second[2];
     ++n;
   }
   h->prof_table.clear();
@@ -1467,6 +1683,9 @@ int pg_destroy(pg_handle h) {
   if (h->host_stage.p) cudaFree(h->host_stage.p);
   invalidate_graphs(h);
   if (h->io.p) cudaFree(h->io.p);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->io_eps.p) cudaFree(h->io_eps.p);
+  if (h->post.p) cudaFree(h->post.p);
   for (auto& r : h->prof) {
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);

@@ -359,13 +359,13 @@ __global__ void attn_merge_kernel(const float* __restrict__ part_o, const float*
   for (int k = 0; k < 3; ++k) dst[32 * k] = v[k];
 }
 
-// Key-range splits per query tile.  The grid is tiles*splits CTAs on 2*148 resident slots and a CTA's
+// Key-range splits per query tile.  The grid is tiles*splits CTAs on 2 resident slots per SM and a CTA's
 // time is ~(its key blocks + 1 for prologue/epilogue): pick the split count with the fewest
 // wave-steps, e.g. T = 3435 (108 tiles, 54 key blocks): 5 splits = 2 waves x 12 instead of 3 splits =
 // 2 waves x 19.  Depends on T only (not on B), so a row's result is independent of its batch.
 int attn_splits(int T, int heads) {
   const int nblk = (T + AK - 1) / AK;
-  const int tiles = nblk * heads, slots = 2 * 148;
+  const int tiles = nblk * heads, slots = 2 * device_sm_count();
   int best = 1, best_cost = 1 << 30;
   for (int ns = 1; ns <= 16 && ns <= nblk; ++ns) {
     const int waves = (tiles * ns + slots - 1) / slots;
@@ -408,13 +408,9 @@ cudaError_t launch_rel_attention_mma(const float* qkv, const float* rel_k, const
                                                                 qscale);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  static bool attr_set = false;
-  if (!attr_set) {
-    e = cudaFuncSetAttribute(rel_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(AttnSmem));
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  e = ensure_dyn_smem(rel_attention_mma_kernel, once, (int)sizeof(AttnSmem));
+  if (e != cudaSuccess) return e;
   dim3 grid(Tp / AQ, n_heads, B * ns);
   rel_attention_mma_kernel<<<grid, ATT_THREADS, sizeof(AttnSmem), s>>>(qh, ql, kh, kl, vth, vtl, qkv, rel_k, lens,
                                                                        part_o, part_m, part_l, band_s, B, T, Tp, H,

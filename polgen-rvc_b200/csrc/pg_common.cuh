@@ -4,9 +4,36 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 
 namespace pg {
+
+// cudaFuncSetAttribute and the SM count are PER DEVICE: a process may own handles on several GPUs
+// (Synthesizer.to('cuda:1') after an engine on cuda:0), so one-time launcher setup is remembered per
+// (kernel instantiation, device).  Thread-safe: handles on different devices may run concurrently.
+constexpr int PG_MAX_DEVICES = 64;
+struct DeviceOnce {
+  std::atomic<int> bytes[PG_MAX_DEVICES] = {};
+};
+// opt in to `bytes` of dynamic shared memory for `kernel` on the current device (idempotent)
+template <class Kernel>
+inline cudaError_t ensure_dyn_smem(Kernel kernel, DeviceOnce& once, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool tracked = dev >= 0 && dev < PG_MAX_DEVICES;
+  if (tracked && once.bytes[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  if (tracked) {
+    int cur = once.bytes[dev].load(std::memory_order_relaxed);
+    while (cur < bytes && !once.bytes[dev].compare_exchange_weak(cur, bytes, std::memory_order_release)) {}
+  }
+  return cudaSuccess;
+}
+// SM count of the CURRENT device (cached per device)
+int device_sm_count();
 
 // thread-local error string behind pg_last_error()
 void set_error(const std::string& msg);
@@ -67,6 +94,8 @@ cudaError_t launch_conv_umma(const ConvArgs& a, DType in_dt, DType out_dt, cudaS
 struct PlaneConvArgs {
   const __half* x = nullptr; int B = 0, L = 0, Cin = 0;
   const int* lens = nullptr; int in_mask = 0;            // input rows >= lens[b] read as zero
+  const int* tlen = nullptr; int len_mul = 1;            // hard end of row b: input rows >= tlen[b]*len_mul read as
+                                                          // zero and tiles that start there are skipped
   const void* w16 = nullptr;                              // [K][N][Cin] f16
   int N = 0, K = 1, dil = 1, pad = 0;
   const float* bias = nullptr; const float* bbias = nullptr; int bbias_ld = 0;
@@ -79,6 +108,7 @@ struct PlaneConvArgs {
   int swap = 0;   // PG_FLAG_PLANES_SWAP: operand-swapped MMA where the shape qualifies (C = 128, MT = 2)
 };
 bool plane_conv_supported(const PlaneConvArgs& a);
+int plane_conv_mt(const PlaneConvArgs& a);   // 128-row tiles per CTA tile the launch plan picks (0: unsupported)
 int plane_pick_nt(int n);
 cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s);
 
@@ -88,6 +118,7 @@ cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s);
 //   v = out_scale * v + accin ; out32 = v ; out16 = lrelu(v, out16_slope)
 struct PairConvArgs {
   const __half* x = nullptr; int B = 0, L = 0, C = 0, K = 1, dil = 1;
+  const int* tlen = nullptr; int len_mul = 1;              // hard end of row b at tlen[b]*len_mul (zero beyond)
   const void* w1 = nullptr; const void* w2 = nullptr;      // [K][C][C] f16 each
   const float* bias1 = nullptr; const float* bias2 = nullptr;
   const float* res32 = nullptr; float res_inv = 1.f;
@@ -96,6 +127,7 @@ struct PairConvArgs {
   float out_scale = 1.f;
 };
 bool pair_conv_supported(const PairConvArgs& a);
+int pair_conv_mt(const PairConvArgs& a);
 cudaError_t launch_pair_planes(const PairConvArgs& a, cudaStream_t s);
 
 // time-major [B][L][x_ld] (channels x_coff..x_coff+C) -> planes f16, rows >= lens[b] zeroed when lens,
@@ -113,12 +145,30 @@ cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, const flo
                                        const float* bn, int B, int L, int C, int Lsrc, int k, int stride,
                                        int pad, float slope, cudaStream_t s);
 // wave = tanh(conv_post(lrelu(x, in_slope))) over planes (f16 or f32)
+// tlen (nullable): rows >= tlen[b]*len_mul read as zero (hard end of row b)
 cudaError_t launch_conv_post_planes(const void* x, DType dt, const float* w /*[K][C]*/, float* wave, int B,
-                                    int L, int C, int K, float in_slope, cudaStream_t s);
+                                    int L, int C, int K, float in_slope, const int* tlen, int len_mul,
+                                    cudaStream_t s);
 
+// Per-call scalars the kernels of a (possibly replayed) launch sequence read from DEVICE memory, so a
+// CUDA graph captured for a padded (B, Tp) bucket serves every true length inside the bucket:
+//   meta[0] = T_true (frames the caller passed), meta[1] = ragged (rows are stand-alone segments)
+//   seeds[b] = Philox seed of batch row b (row_seed(seed, b))
+struct CallMeta { int t_true; int ragged; };
+__host__ __device__ inline uint64_t row_seed(uint64_t seed, int b) {
+  return seed + (uint64_t)b * 0x9E3779B97F4A7C15ull;
+}
+cudaError_t launch_set_call(CallMeta* meta, uint64_t* seeds, int B, int t_true, int ragged, uint64_t seed,
+                            cudaStream_t s);
+// lengths / speaker ids of up to N rows passed BY VALUE (kernel parameters): written to the int64 arrays
+struct RowScalars { static constexpr int N = 128; int len[N]; int sid[N]; };
+cudaError_t launch_set_rows(int64_t* lengths, int64_t* sid, const RowScalars& rs, int n, cudaStream_t s);
+// lens32[b] = clamp(lengths[b], 0, T_true): the sequence_mask of the TextEncoder / flow (commons.py:89-93);
+// tlen32[b] = hard end of row b for the decoder (every layer zero-pads there): lens32[b] when ragged,
+// else T_true.  T is the row pitch of `pitch` (the padded frame count); meta == nullptr: T_true = T, dense.
 cudaError_t launch_prepare_ints(const int64_t* lengths, const int64_t* pitch, const int64_t* sid,
-                                int* lens32, int* pitch32, int* sid32, int B, int T, int n_spk,
-                                cudaStream_t s);
+                                const CallMeta* meta, int* lens32, int* tlen32, int* pitch32, int* sid32,
+                                int B, int T, int n_spk, cudaStream_t s);
 // y[b][n] = bias[n] + sum_k w[n][k] * emb[sid[b]][k]
 cudaError_t launch_cond_gemv(const float* emb, const int* sid, const float* w, const float* bias,
                              float* y, int B, int Kdim, int N, cudaStream_t s);
@@ -139,17 +189,20 @@ cudaError_t launch_rel_attention_mma(const float* qkv, const float* rel_k, const
                                      const int* lens, float* out, void* scratch, int B, int T, int H,
                                      int n_heads, int window, cudaStream_t s);
 // z_p = (m + exp(logs) * eps * 0.66666) * mask ; stats [B][T][2C] -> m, logs, z_p, z(copy)
-cudaError_t launch_reparam(const float* stats, const float* eps, uint64_t seed, const uint64_t* seed_dev,
-                           const int* lens, float* m_p, float* logs_p, float* z_p, float* z, int B,
-                           int T, int C, cudaStream_t s);
-cudaError_t launch_set_seed(uint64_t* dst, uint64_t seed, cudaStream_t s);
+// eps (nullable) is [B][eps_T][C] (rows >= eps_T draw 0); otherwise Philox(seeds[b] | row_seed(seed, b)),
+// subsequence t*C + c: a row's noise does not depend on the batch around it or on the padded T
+cudaError_t launch_reparam(const float* stats, const float* eps, int eps_T, uint64_t seed,
+                           const uint64_t* seeds_dev, const int* lens, float* m_p, float* logs_p, float* z_p,
+                           float* z, int B, int T, int C, cudaStream_t s);
 // acts = tanh(a[:, :H]) * sigmoid(a[:, H:])
 cudaError_t launch_gate(const float* a, float* acts, int64_t rows, int H, cudaStream_t s);
 
 // harmonic source (pg_source.cu)
-cudaError_t launch_source(const float* f0, const float* eps, uint64_t seed, const uint64_t* seed_dev,
-                          float lin_w, float lin_b, double* frame_phase, float* source, float* sine, int B, int T, int upp,
-                          int sr, cudaStream_t s);
+// eps (nullable) is [B][eps_T*upp]; tlen (nullable): samples >= tlen[b]*upp are written as 0 (hard end of
+// the row: the noise convs then see the zero padding a stand-alone run of that length would)
+cudaError_t launch_source(const float* f0, const float* eps, int eps_T, uint64_t seed, const uint64_t* seeds_dev,
+                          const int* tlen, float lin_w, float lin_b, double* frame_phase, float* source,
+                          float* sine, int B, int T, int upp, int sr, cudaStream_t s);
 // x[b][t][c] += bn[c] + sum_j wn[c][j] * src[b][t*stride + j - pad]
 cudaError_t launch_noise_inject(void* x, DType dt, const float* src, const float* wn, const float* bn,
                                 int B, int L, int C, int Lsrc, int k, int stride, int pad,
@@ -158,5 +211,16 @@ cudaError_t launch_noise_inject(void* x, DType dt, const float* src, const float
 cudaError_t launch_conv_post(const void* x, DType dt, const float* w /*[K][C]*/, float* wave, int B,
                              int L, int C, int K, float in_slope, cudaStream_t s);
 cudaError_t launch_cast_f16_to_f32(const __half* x, float* y, int64_t n, cudaStream_t s);
+
+// ---- pipeline glue around Synthesizer.infer (pg_pipeline.cu; rvc/infer/pipeline.py) ----
+cudaError_t launch_coarse_pitch(const void* f0, int is_f64, int64_t n, double f0_min, double f0_max, int64_t* pitch,
+                                float* pitchf, cudaStream_t s);
+cudaError_t launch_prepare_features(const float* feats, const float* feats0, const float* pitchf, float protect,
+                                    float* out, int64_t p_len, int D, cudaStream_t s);
+cudaError_t launch_frame_rms(const float* y, int64_t n, int rate, float* rms, int n_frames, cudaStream_t s);
+cudaError_t launch_change_rms(const float* x, int64_t n, const float* rms1, int n1, const float* rms2, int n2,
+                              float rate, float* out, unsigned int* max_bits, cudaStream_t s);
+cudaError_t launch_absmax(const float* x, int64_t n, unsigned int* max_bits, cudaStream_t s);
+cudaError_t launch_to_int16(const float* x, int64_t n, const unsigned int* max_bits, int16_t* pcm, cudaStream_t s);
 
 }  // namespace pg

@@ -55,6 +55,7 @@ constexpr int GROUP_PLANES = 16;   // 128 channels per activation-ring slot
 struct PlaneParams {
   const __half* x; int L;              // input planes [B][Cin/8][L][8]
   const int* lens; int in_mask;
+  const int* tlen; int len_mul;        // hard end of row b (tile rows): tlen[b]*len_mul, nullptr = L
   int B, Cin, K, dil, pad;
   const float* bias; const float* bbias; int bbias_ld;
   const uint32_t* tapmask;
@@ -92,6 +93,12 @@ __device__ __forceinline__ TileCoord decode_tile(int id, const PlaneParams& p) {
   c.rt = tmp % p.n_row_tiles;
   c.b = tmp / p.n_row_tiles;
   return c;
+}
+
+// hard end (in tile rows) of batch row b; tiles that start at or beyond it are skipped by EVERY role
+// (same test everywhere, so the per-role ring / accumulator counters stay in step)
+__device__ __forceinline__ int row_end(const PlaneParams& p, int b) {
+  return p.tlen ? min(p.L, p.tlen[b] * p.len_mul) : p.L;
 }
 
 __device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
@@ -183,9 +190,11 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
     uint32_t a_cnt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(tile, p);
+      const int t_end = row_end(p, tc.b);
+      if (tc.rt * (BM * MT) >= t_end) continue;            // dead tile (past the row's hard end)
       const int tstart = tc.rt * (BM * MT) - p.pad;        // time index of window row 0
       const int len = p.lens ? p.lens[tc.b] : p.L;
-      const int t_hi = p.in_mask ? min(p.L, len) : p.L;
+      const int t_hi = p.in_mask ? min(t_end, len) : t_end;
       const int lo = min(max(-tstart, 0), rows);           // rows [lo, hi) exist, the rest are zero
       const int hi = min(max(t_hi - tstart, lo), rows);
       const int nz = lo + (rows - hi);
@@ -230,6 +239,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(tile, p);
+        if (tc.rt * (BM * MT) >= row_end(p, tc.b)) continue;
         const uint32_t tapmask = p.tapmask ? p.tapmask[tc.ntile] : 0xFFFFFFFFu;
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
           for (int tap = 0; tap < p.K; ++tap) {
@@ -269,7 +279,11 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       mbar_wait(w_ready, 0);
       tcgen05_fence_after();
     }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t_cnt) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      {
+        const TileCoord tc = decode_tile(tile, p);
+        if (tc.rt * (BM * MT) >= row_end(p, tc.b)) continue;
+      }
       const uint32_t tapmask = p.tapmask ? p.tapmask[(tile % p.n_ntiles)] : 0xFFFFFFFFu;
       const uint32_t accb = t_cnt & 1u;
       if (!freerun) mbar_wait(&acc_empty[accb], ((t_cnt >> 1) & 1u) ^ 1u);
@@ -323,6 +337,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       }
       if (do_commit) tcgen05_commit(&acc_full[accb]);
       trace(dbg, 1, 3, (int)t_cnt);
+      ++t_cnt;
     }
     }
   } else if (warp == RES_WARP && p.r_slots > 0 && !(dbg & (64 | 16384))) {
@@ -336,9 +351,10 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
     const int sub = lane >> 3, pl = lane & 7;
     const int batch = min(min(per_tile, p.r_slots), 4);   // slots issued together (distinct ring entries)
     uint32_t s_cnt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, s_cnt += (uint32_t)per_tile) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(tile, p);
       const int t0 = tc.rt * (BM * MT), n0 = tc.ntile * p.NT;
+      if (t0 >= row_end(p, tc.b)) continue;
       const size_t plane0 = (size_t)tc.b * CP;
       for (int base = 0; base < per_tile; base += batch) {
         const int which = base + sub;
@@ -360,6 +376,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
                    &r_full[slot]);
         }
       }
+      s_cnt += (uint32_t)per_tile;
     }
   } else if (warp >= EPI_WARP0 && EPI != EPI_GENERIC && SWAP) {
     // ===== SWAP epilogue (EPI_C1 / EPI_C2, NT == Cout == 128): TMEM lane = channel, column = time row.
@@ -375,8 +392,9 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
     const int plane = quarter * 4 + j8;
     const float bias_c = bias_s[quarter * 32 + lane];
     uint32_t t_cnt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t_cnt) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int rt = tile % p.n_row_tiles, b = tile / p.n_row_tiles;     // n_ntiles == 1
+      if (rt * (BM * MT) >= row_end(p, b)) continue;
       const uint32_t accb = t_cnt & 1u;
       uint4* out_b = reinterpret_cast<uint4*>(p.out16) + ((size_t)b * CP + plane) * p.L;
       mbar_wait(&acc_full[accb], (t_cnt >> 1) & 1u);
@@ -451,6 +469,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[accb]);
+      ++t_cnt;
     }
   } else if (warp >= EPI_WARP0 && EPI != EPI_GENERIC) {
     // ===== specialised epilogue (EPI_C1 / EPI_C2): one Cout tile, row_mul == 1, bias in shared memory,
@@ -462,8 +481,9 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int rrow16 = (quarter * 32 + lane) * 16;
     uint32_t t_cnt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t_cnt) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int rt = tile % p.n_row_tiles, b = tile / p.n_row_tiles;     // n_ntiles == 1
+      if (rt * (BM * MT) >= row_end(p, b)) continue;
       const int qbase = rt * (BM * MT) + quarter * 32 + lane;
       const uint32_t accb = t_cnt & 1u;
       uint4* out_b = reinterpret_cast<uint4*>(p.out16) + (size_t)b * CP * p.L;
@@ -521,6 +541,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[accb]);
+      ++t_cnt;
     }
   } else if (warp >= EPI_WARP0 && !(dbg & 256)) {
     // ===== epilogue: quarter q = warp % 4 owns TMEM lanes 32q..32q+31 (one output row per lane);
@@ -532,9 +553,10 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
     constexpr int NCH = EPI_COLS / 8;                     // 8-channel chunks per item
     const bool io = !(dbg & (2 | 2048));
     uint32_t t_cnt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t_cnt) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(tile, p);
       const int t0 = tc.rt * (BM * MT);
+      if (t0 >= row_end(p, tc.b)) continue;
       const int n0 = tc.ntile * p.NT;
       const uint32_t accb = t_cnt & 1u;
       const float* bias = p.bias ? p.bias + n0 : nullptr;
@@ -680,6 +702,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[accb]);
       if (tid == EPI_WARP0 * 32) trace(dbg, 3, 2, (int)t_cnt);
+      ++t_cnt;
     }
   }
   tcgen05_fence_before();
@@ -779,6 +802,7 @@ cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
   if (!get_weight_map(a.w16, a.Cin, a.N, a.K, pl.KC, pl.NT, &wmap)) return cudaErrorNotSupported;
   PlaneParams p;
   p.x = a.x; p.L = a.L; p.lens = a.lens; p.in_mask = a.in_mask;
+  p.tlen = a.tlen; p.len_mul = a.len_mul;
   p.B = a.B; p.Cin = a.Cin; p.K = a.K; p.dil = a.dil; p.pad = a.pad;
   p.bias = a.bias; p.bbias = a.bbias; p.bbias_ld = a.bbias_ld; p.tapmask = a.tapmask;
   p.N = a.N; p.NT = pl.NT; p.n_ntiles = a.N / pl.NT;
@@ -795,13 +819,8 @@ cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
   p.idesc = SWAP ? make_idesc(pl.NT, BM * MT) : make_idesc(BM, pl.NT);
   static const int dbg = env_int("PG_PLANES_DEBUG", 0);
   p.debug = dbg;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_planes_kernel<MT, KC16, EPI, DBG, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static DeviceOnce once;
+  if (cudaError_t e = ensure_dyn_smem(conv_planes_kernel<MT, KC16, EPI, DBG, SWAP>, once, 227 * 1024)) return e;
   int grid = device_sm_count();
   if (grid > p.total_tiles) grid = p.total_tiles;
   if (p.debug & 8) {
@@ -842,6 +861,11 @@ bool plane_conv_supported(const PlaneConvArgs& a) {
   if (a.res16 && a.res32) return false;
   Plan pl;
   return make_plan(a, &pl);
+}
+
+int plane_conv_mt(const PlaneConvArgs& a) {
+  Plan pl;
+  return make_plan(a, &pl) ? pl.MT : 0;
 }
 
 cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s) {

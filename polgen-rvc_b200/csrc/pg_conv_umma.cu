@@ -674,13 +674,15 @@ int env_int(const char* name) {
 }
 
 int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v;
-  }();
-  return n;
+  static std::atomic<int> cache[PG_MAX_DEVICES] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool tracked = dev >= 0 && dev < PG_MAX_DEVICES;
+  int v = tracked ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (v > 0) return v;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 1;
+  if (tracked) cache[dev].store(v, std::memory_order_relaxed);
+  return v;
 }
 
 // Choose row-tile multiplicity, ring depths and CTAs per SM.  Narrow layers (little MMA work per
@@ -791,13 +793,8 @@ cudaError_t launch_t(const ConvArgs& a, const Plan& pl, cudaStream_t s) {
   static const int dbg = env_int("PG_UMMA_DEBUG"), norot = env_int("PG_UMMA_NOROTATE");
   p.debug = dbg;
   p.rotate = (!pl.resident && !norot) ? 1 : 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<MT, TIn, TOut>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static DeviceOnce once;
+  if (cudaError_t e = ensure_dyn_smem(conv_umma_kernel<MT, TIn, TOut>, once, 227 * 1024)) return e;
   int grid = num_sms() * pl.ctas_per_sm;
   if (grid > p.total_tiles) grid = p.total_tiles;
   if (p.debug & 8) {

@@ -38,6 +38,7 @@ constexpr int ECOLS = 16;   // accumulator columns per epilogue item
 
 struct PairParams {
   const __half* x; int L, B, K, dil;
+  const int* tlen; int len_mul;        // hard end of row b: tlen[b]*len_mul (nullptr = L)
   const float* bias1; const float* bias2;
   const float* res32; float res_inv;
   const __half* accin16; const float* accin32;
@@ -52,6 +53,11 @@ struct PairParams {
   int no_ring;  // PG_PAIR_NORING (debug): fp32 residual read straight from global memory in E2
   int no_pre;   // PG_PAIR_NOPRE (debug): accumulate input loaded at use instead of prefetched
 };
+
+// hard end of batch row b; tiles whose first output row lies at or beyond it are skipped by every role
+__device__ __forceinline__ int row_end(const PairParams& p, int b) {
+  return p.tlen ? min(p.L, p.tlen[b] * p.len_mul) : p.L;
+}
 
 __device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
   const __half2* h = reinterpret_cast<const __half2*>(&q);
@@ -136,11 +142,13 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
   if (warp == LOAD_WARP) {
     // ===== input window loader (bulk copies + zero fill outside [0, L)) =====
     uint32_t cnt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++cnt) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int rt = tile % p.n_row_tiles, b = tile / p.n_row_tiles;
+      const int t_end = row_end(p, b);
+      if (rt * p.MO >= t_end) continue;
       const int tstart = rt * p.MO - p.h2 - p.h1;
       const int lo = min(max(-tstart, 0), rows);
-      const int hi = min(max(p.L - tstart, lo), rows);
+      const int hi = min(max(t_end - tstart, lo), rows);
       const int nz = lo + (rows - hi);
       const __half* xb = p.x + (size_t)b * PLANES * p.L * 8;
       const uint32_t slot = cnt % (uint32_t)p.a_slots;
@@ -161,6 +169,7 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
       if (bytes && lane < PLANES)
         bulk_g2s(dst + (size_t)lane * p.plane_bytes + (size_t)lo * 16,
                  xb + ((size_t)lane * p.L + (tstart + lo)) * 8, bytes, &a_full[slot]);
+      ++cnt;
     }
   } else if (warp == TMA_WARP) {
     // ===== both weight sets, once =====
@@ -189,7 +198,9 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
       const uint32_t idesc = p.idesc;
       mbar_wait(w_ready, 0);
       tcgen05_fence_after();
-      const int n_my = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      int n_my = 0;     // live tiles of this CTA (dead ones are skipped by every role)
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+        n_my += (tile % p.n_row_tiles) * p.MO < row_end(p, tile / p.n_row_tiles) ? 1 : 0;
       for (int it = 0; it <= n_my; ++it) {
         if (it < n_my) {   // GEMM 1 (dilated conv) of tile it
           const uint32_t slot = (uint32_t)it % (uint32_t)p.a_slots, b = (uint32_t)it & 1u;
@@ -240,9 +251,10 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
     const int pl = lane & 7, sub = lane >> 3;
     const int batch = min(min(MT, p.r_slots), 4);
     uint32_t s_cnt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, s_cnt += (uint32_t)MT) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int rt = tile % p.n_row_tiles, b = tile / p.n_row_tiles;
       const int o0 = rt * p.MO;
+      if (o0 >= row_end(p, b)) continue;
       for (int base = 0; base < MT; base += batch) {
         const int m = base + sub;
         const bool mine = sub < batch && m < MT && pl < PLANES;
@@ -260,14 +272,17 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
                    reinterpret_cast<const char*>(p.res32) + (((size_t)b * PLANES + pl) * p.L + row0) * 32, bytes,
                    &r_full[slot]);
       }
+      s_cnt += (uint32_t)MT;
     }
   } else if (warp >= E1_WARP0 && warp < E2_WARP0) {
     // ===== E1: acc1 -> lrelu(acc + bias1) -> f16 planes of the intermediate, in shared memory =====
     const int quarter = warp & 3, grp = (warp - E1_WARP0) >> 2;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc1_col;
     uint32_t j = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int rt = tile % p.n_row_tiles;
+      const int t_end = row_end(p, tile / p.n_row_tiles);
+      if (rt * p.MO >= t_end) continue;
       const int t_first = rt * p.MO - p.h2;            // time of intermediate row 0
       const uint32_t b = j & 1u;
       mbar_wait(&acc1_full[b], (j >> 1) & 1u);
@@ -279,7 +294,7 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
         const int m = it / NCB, cb = it - m * NCB;
         const int r = m * BM + quarter * 32 + lane;
         const int t = t_first + r;
-        const bool live = t >= 0 && t < p.L;
+        const bool live = t >= 0 && t < t_end;
         uint32_t acc[ECOLS];
         tmem_ld16(lane_taddr + b * (uint32_t)(MT * C) + (uint32_t)(m * C + cb * ECOLS), acc);
 #pragma unroll
@@ -300,6 +315,7 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
         mbar_arrive(&tmp_full[b]);
         mbar_arrive(&acc1_empty[b]);
       }
+      ++j;
     }
   } else if (warp >= E2_WARP0) {
     // ===== E2: acc2 -> + bias2 + residual -> scale / accumulate -> HBM =====
@@ -307,9 +323,10 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc2_col;
     const float* bias2 = bias_s + C;
     uint32_t j = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int rt = tile % p.n_row_tiles, bb = tile / p.n_row_tiles;
       const int o0 = rt * p.MO;
+      if (o0 >= row_end(p, bb)) continue;
       const uint32_t b = j & 1u, slot = j % (uint32_t)p.a_slots;
       const size_t plane_base = (size_t)bb * PLANES * p.L;
       // the accumulate input of this warp's items is fetched BEFORE waiting for the accumulator, so its
@@ -447,6 +464,7 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
         mbar_arrive(&acc2_empty[b]);
         mbar_arrive(&a_empty[slot]);
       }
+      ++j;
     }
   }
   tcgen05_fence_before();
@@ -516,6 +534,7 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
     return cudaErrorNotSupported;
   PairParams p;
   p.x = a.x; p.L = a.L; p.B = a.B; p.K = a.K; p.dil = a.dil;
+  p.tlen = a.tlen; p.len_mul = a.len_mul;
   p.bias1 = a.bias1; p.bias2 = a.bias2; p.res32 = a.res32; p.res_inv = a.res_inv;
   p.accin16 = a.accin16; p.accin32 = a.accin32;
   p.out16 = a.out16; p.out16_slope = a.out16_slope; p.out32 = a.out32; p.out_scale = a.out_scale;
@@ -532,13 +551,8 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
   static const int no_ring = [] { const char* e = getenv("PG_PAIR_NORING"); return e ? atoi(e) : 0; }();
   p.no_ring = no_ring;
 
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(pair_planes_kernel<MT, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static DeviceOnce once;
+  if (cudaError_t e = ensure_dyn_smem(pair_planes_kernel<MT, C>, once, 227 * 1024)) return e;
   int grid = device_sm_count();
   if (grid > p.total_tiles) grid = p.total_tiles;
   static const int dbg_sync = [] { const char* e = getenv("PG_PAIR_SYNC"); return e ? atoi(e) : 0; }();
@@ -555,6 +569,11 @@ bool pair_conv_supported(const PairConvArgs& a) {
   if (a.L <= 0 || a.B <= 0 || a.res_inv < 1.f || a.out16_slope > 1.f) return false;
   PairPlan pl;
   return make_pair_plan(a, &pl);
+}
+
+int pair_conv_mt(const PairConvArgs& a) {
+  PairPlan pl;
+  return make_pair_plan(a, &pl) ? pl.MT : 0;
 }
 
 cudaError_t launch_pair_planes(const PairConvArgs& a, cudaStream_t s) {

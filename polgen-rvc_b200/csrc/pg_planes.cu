@@ -199,13 +199,9 @@ cudaError_t launch_noise_tiled(__half* x, const float* src, const float* wn, con
                                int Lsrc, int k, int stride, int pad, float slope, cudaStream_t s) {
   const size_t smem = sizeof(float) * ((size_t)k * CP * 8 + (((NRB - 1) * stride + k + 3) & ~3)) +
                       (size_t)CP * (NRB * 16 + 16);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(noise_inject_tiled_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static DeviceOnce once;
+  if (smem > 48 * 1024)
+    if (cudaError_t e = ensure_dyn_smem(noise_inject_tiled_kernel<CP>, once, (int)smem)) return e;
   dim3 grid((L + NRB - 1) / NRB, B);
   noise_inject_tiled_kernel<CP><<<grid, 256, smem, s>>>(x, src, wn, bn, L, Lsrc, k, stride, pad, slope);
   return cudaGetLastError();
@@ -216,13 +212,15 @@ template <typename T, int K>
 __global__ void __launch_bounds__(256) conv_post_planes_kernel(const T* __restrict__ x,
                                                                const float* __restrict__ w /*[K][C]*/,
                                                                float* __restrict__ wave, int L, int C,
-                                                               float in_slope) {
+                                                               float in_slope, const int* __restrict__ tlen,
+                                                               int len_mul) {
   extern __shared__ float ws[];
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= L) return;
+  const int t_hi = tlen ? min(L, tlen[b] * len_mul) : L;   // hard end of the row
   const int CP = C / 8;
   float acc = 0.f;
   for (int pl = 0; pl < CP; ++pl) {
@@ -230,7 +228,7 @@ __global__ void __launch_bounds__(256) conv_post_planes_kernel(const T* __restri
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       const int n = t + j - K / 2;
-      if (n < 0 || n >= L) continue;
+      if (n < 0 || n >= t_hi) continue;
       float v[8];
       load8(plane + (size_t)n * 8, v);
 #pragma unroll
@@ -240,7 +238,7 @@ __global__ void __launch_bounds__(256) conv_post_planes_kernel(const T* __restri
       }
     }
   }
-  wave[(size_t)b * L + t] = tanhf(acc);
+  wave[(size_t)b * L + t] = t < t_hi ? tanhf(acc) : 0.f;
 }
 
 unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
@@ -307,16 +305,16 @@ cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, const flo
 }
 
 cudaError_t launch_conv_post_planes(const void* x, DType dt, const float* w, float* wave, int B, int L, int C,
-                                    int K, float in_slope, cudaStream_t s) {
+                                    int K, float in_slope, const int* tlen, int len_mul, cudaStream_t s) {
   if (K != 7 || C % 8 || C > 256) return cudaErrorInvalidValue;
   dim3 grid((L + 255) / 256, B);
   const size_t smem = sizeof(float) * K * C;
   if (dt == DT_F32)
     conv_post_planes_kernel<float, 7><<<grid, 256, smem, s>>>(reinterpret_cast<const float*>(x), w, wave, L, C,
-                                                             in_slope);
+                                                             in_slope, tlen, len_mul);
   else
     conv_post_planes_kernel<__half, 7><<<grid, 256, smem, s>>>(reinterpret_cast<const __half*>(x), w, wave, L, C,
-                                                              in_slope);
+                                                              in_slope, tlen, len_mul);
   return cudaGetLastError();
 }
 

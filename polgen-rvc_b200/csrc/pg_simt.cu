@@ -175,14 +175,48 @@ cudaError_t launch_conv_simt(const ConvArgs& a, DType in_dt, DType out_dt, cudaS
 // ---------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------
-__global__ void prepare_ints_kernel(const int64_t* lengths, const int64_t* pitch, const int64_t* sid,
-                                    int* lens32, int* pitch32, int* sid32, int B, int T, int n_spk) {
+__global__ void set_call_kernel(CallMeta* meta, uint64_t* seeds, int B, int t_true, int ragged, uint64_t seed) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    meta->t_true = t_true;
+    meta->ragged = ragged;
+  }
+  if (i < B) seeds[i] = row_seed(seed, i);
+}
+
+cudaError_t launch_set_call(CallMeta* meta, uint64_t* seeds, int B, int t_true, int ragged, uint64_t seed,
+                            cudaStream_t s) {
+  set_call_kernel<<<(B + 255) / 256, 256, 0, s>>>(meta, seeds, B, t_true, ragged, seed);
+  return cudaGetLastError();
+}
+
+__global__ void set_rows_kernel(int64_t* lengths, int64_t* sid, const RowScalars rs, int n) {
+  const int i = threadIdx.x;
+  if (i < n) {
+    lengths[i] = rs.len[i];
+    sid[i] = rs.sid[i];
+  }
+}
+
+cudaError_t launch_set_rows(int64_t* lengths, int64_t* sid, const RowScalars& rs, int n, cudaStream_t s) {
+  set_rows_kernel<<<1, RowScalars::N, 0, s>>>(lengths, sid, rs, n);
+  return cudaGetLastError();
+}
+
+__global__ void prepare_ints_kernel(const int64_t* lengths, const int64_t* pitch, const int64_t* sid,
+                                    const CallMeta* meta, int* lens32, int* tlen32, int* pitch32, int* sid32,
+                                    int B, int T, int n_spk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t_true = meta ? min(meta->t_true, T) : T;
+  const int ragged = meta ? meta->ragged : 0;
   if (i < B) {
+    int len = t_true;
     if (lengths) {
       long long l = lengths[i];
-      lens32[i] = l < 0 ? 0 : (l > T ? T : (int)l);
+      len = l < 0 ? 0 : (l > t_true ? t_true : (int)l);
+      lens32[i] = len;
     }
+    if (tlen32) tlen32[i] = ragged ? len : t_true;
     if (sid) {
       long long v = sid[i];
       sid32[i] = v < 0 ? 0 : (v >= n_spk ? n_spk - 1 : (int)v);
@@ -195,11 +229,11 @@ __global__ void prepare_ints_kernel(const int64_t* lengths, const int64_t* pitch
 }
 
 cudaError_t launch_prepare_ints(const int64_t* lengths, const int64_t* pitch, const int64_t* sid,
-                                int* lens32, int* pitch32, int* sid32, int B, int T, int n_spk,
-                                cudaStream_t s) {
+                                const CallMeta* meta, int* lens32, int* tlen32, int* pitch32, int* sid32,
+                                int B, int T, int n_spk, cudaStream_t s) {
   const int n = B * T > B ? B * T : B;
-  prepare_ints_kernel<<<(n + 255) / 256, 256, 0, s>>>(lengths, pitch, sid, lens32, pitch32, sid32, B,
-                                                      T, n_spk);
+  prepare_ints_kernel<<<(n + 255) / 256, 256, 0, s>>>(lengths, pitch, sid, meta, lens32, tlen32, pitch32,
+                                                      sid32, B, T, n_spk);
   return cudaGetLastError();
 }
 
@@ -463,21 +497,16 @@ cudaError_t launch_rel_attention(const float* qkv, const float* rel_k, const flo
   constexpr int DD = 96;
   const size_t smem = sizeof(float) * (DD * (ABQ + 4) + DD * (ABK + 4) + ABK * DD + ABQ * (ABK + 1) +
                                        2 * ABQ * AMAXR);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rel_attention_kernel<DD>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  if (cudaError_t e = ensure_dyn_smem(rel_attention_kernel<DD>, once, (int)smem)) return e;
   dim3 grid((T + ABQ - 1) / ABQ, n_heads, B);
   rel_attention_kernel<DD><<<grid, 256, smem, s>>>(qkv, rel_k, rel_v, lens, out, T, H, window);
   return cudaGetLastError();
 }
 
 // synthesizers.py:174: z_p = (m_p + exp(logs_p) * randn * 0.66666) * x_mask
-__global__ void reparam_kernel(const float* __restrict__ stats, const float* __restrict__ eps,
-                               uint64_t seed, const uint64_t* __restrict__ seed_dev,
+__global__ void reparam_kernel(const float* __restrict__ stats, const float* __restrict__ eps, int eps_T,
+                               uint64_t seed, const uint64_t* __restrict__ seeds_dev,
                                const int* __restrict__ lens, float* __restrict__ m_p,
                                float* __restrict__ logs_p, float* __restrict__ z_p,
                                float* __restrict__ z, int B, int T, int C) {
@@ -488,35 +517,30 @@ __global__ void reparam_kernel(const float* __restrict__ stats, const float* __r
   const size_t row = i / C;
   const int t = (int)(row % T), b = (int)(row / T);
   const float m = stats[row * 2 * C + c], lg = stats[row * 2 * C + C + c];
-  float e;
-  if (eps) {
-    e = eps[i];
-  } else {
-    curandStatePhilox4_32_10_t st;
-    curand_init(seed_dev ? *seed_dev : seed, i, 0, &st);   // seed_dev: replayed CUDA graphs
-    e = curand_normal(&st);
+  float v = 0.f;
+  if (t < lens[b]) {
+    float e;
+    if (eps) {
+      e = t < eps_T ? eps[((size_t)b * eps_T + t) * C + c] : 0.f;
+    } else {
+      curandStatePhilox4_32_10_t st;
+      curand_init(seeds_dev ? seeds_dev[b] : row_seed(seed, b), (unsigned long long)t * C + c, 0, &st);
+      e = curand_normal(&st);
+    }
+    v = m + __expf(lg) * e * 0.66666f;
   }
-  const float v = t < lens[b] ? m + __expf(lg) * e * 0.66666f : 0.f;
   m_p[i] = m;
   logs_p[i] = lg;
   z_p[i] = v;
   z[i] = v;
 }
 
-cudaError_t launch_reparam(const float* stats, const float* eps, uint64_t seed, const uint64_t* seed_dev,
-                           const int* lens, float* m_p, float* logs_p, float* z_p, float* z, int B,
-                           int T, int C, cudaStream_t s) {
+cudaError_t launch_reparam(const float* stats, const float* eps, int eps_T, uint64_t seed,
+                           const uint64_t* seeds_dev, const int* lens, float* m_p, float* logs_p, float* z_p,
+                           float* z, int B, int T, int C, cudaStream_t s) {
   const size_t total = (size_t)B * T * C;
-  reparam_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(stats, eps, seed, seed_dev, lens, m_p,
+  reparam_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(stats, eps, eps_T, seed, seeds_dev, lens, m_p,
                                                                  logs_p, z_p, z, B, T, C);
-  return cudaGetLastError();
-}
-
-// per-call Philox seed of a replayed CUDA graph (the graph's kernels read it through seed_dev)
-__global__ void set_seed_kernel(uint64_t* dst, uint64_t seed) { *dst = seed; }
-
-cudaError_t launch_set_seed(uint64_t* dst, uint64_t seed, cudaStream_t s) {
-  set_seed_kernel<<<1, 1, 0, s>>>(dst, seed);
   return cudaGetLastError();
 }
 

@@ -62,17 +62,21 @@ __global__ void __launch_bounds__(256) frame_phase_kernel(const float* __restric
 }
 
 __global__ void source_kernel(const float* __restrict__ f0, const double* __restrict__ P,
-                              const float* __restrict__ eps, uint64_t seed,
-                              const uint64_t* __restrict__ seed_dev, float lin_w, float lin_b,
-                              float* __restrict__ source, float* __restrict__ sine_out, int B, int T,
+                              const float* __restrict__ eps, int eps_T, uint64_t seed,
+                              const uint64_t* __restrict__ seeds_dev, const int* __restrict__ tlen, float lin_w,
+                              float lin_b, float* __restrict__ source, float* __restrict__ sine_out, int B, int T,
                               int upp, float sr) {
   const size_t L = (size_t)T * upp;
   const size_t total = (size_t)B * L;
-  if (seed_dev) seed = *seed_dev;   // replayed CUDA graphs read the per-call seed from memory
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const size_t b = i / L, n = i % L;
     const int t = (int)(n / upp), r = (int)(n % upp);
+    if (tlen && t >= tlen[b]) {        // past the hard end of the row: the noise convs see zero padding
+      source[i] = 0.f;
+      if (sine_out) sine_out[i] = 0.f;
+      continue;
+    }
     const float f = f0[b * T + t];
     const float rad = fmodf(__fdiv_rn(f, sr), 1.0f);
     const double ph = P[b * T + t] + (double)(r + 1) * (double)rad;
@@ -81,10 +85,10 @@ __global__ void source_kernel(const float* __restrict__ f0, const double* __rest
     const float sine = sinpif(2.f * fr) * 0.1f * uv;
     float e;
     if (eps) {
-      e = eps[i];
+      e = t < eps_T ? eps[b * ((size_t)eps_T * upp) + n] : 0.f;
     } else {
       curandStatePhilox4_32_10_t st;
-      curand_init(seed ^ 0x9E3779B97F4A7C15ull, i, 0, &st);
+      curand_init((seeds_dev ? seeds_dev[b] : row_seed(seed, (int)b)) ^ 0x9E3779B97F4A7C15ull, n, 0, &st);
       e = curand_normal(&st);
     }
     const float amp = uv * 0.003f + (1.f - uv) * (0.1f / 3.f);
@@ -94,17 +98,18 @@ __global__ void source_kernel(const float* __restrict__ f0, const double* __rest
   }
 }
 
-cudaError_t launch_source(const float* f0, const float* eps, uint64_t seed, const uint64_t* seed_dev,
-                          float lin_w, float lin_b, double* frame_phase, float* source, float* sine, int B, int T, int upp,
-                          int sr, cudaStream_t s) {
+cudaError_t launch_source(const float* f0, const float* eps, int eps_T, uint64_t seed, const uint64_t* seeds_dev,
+                          const int* tlen, float lin_w, float lin_b, double* frame_phase, float* source,
+                          float* sine, int B, int T, int upp, int sr, cudaStream_t s) {
   frame_phase_kernel<<<B, 256, 0, s>>>(f0, frame_phase, T, upp, (float)sr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const size_t total = (size_t)B * T * upp;
   size_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  source_kernel<<<(unsigned)blocks, 256, 0, s>>>(f0, frame_phase, eps, seed, seed_dev, lin_w, lin_b, source, sine,
-                                                 B, T, upp, (float)sr);
+  const size_t cap = (size_t)device_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  source_kernel<<<(unsigned)blocks, 256, 0, s>>>(f0, frame_phase, eps, eps_T, seed, seeds_dev, tlen, lin_w, lin_b,
+                                                 source, sine, B, T, upp, (float)sr);
   return cudaGetLastError();
 }
 

@@ -216,6 +216,5 @@ static inline uint32_t make_idesc(int M, int N) {
 // cached cuTensorMap of a [K][Cout][Cin] f16 weight tensor viewed as 2-D {Cin, K*Cout}, box {kc, nt},
 // 128B swizzle (kc == 64) or 64B swizzle (kc == 32).  Implemented in pg_conv_umma.cu.
 bool get_weight_map(const void* w16, int cin, int cout, int k, int kc, int nt, CUtensorMap* out);
-int device_sm_count();
 
 }  // namespace pg

@@ -123,37 +123,93 @@ class Engine:
                 "conv_umma": (ms[2], fl[2], int(n[2]))}
 
     def profile_table(self, max_rows: int = 256):
-        """Per-shape rows (cls, Cin, N, K, dil, launches, ms, flops) of the records profile_read() consumed."""
-        buf = (C.c_double * (8 * max_rows))()
+        """Per-shape rows (cls, Cin, N, K, dil, MT, launches, ms, flops) of the records profile_read() consumed."""
+        W = _lib.PROFILE_COLS
+        buf = (C.c_double * (W * max_rows))()
         n = self.lib.pg_profile_table(self._h, buf, max_rows)
         if n < 0:
             raise RuntimeError(self.lib.pg_last_error().decode())
-        return [tuple(buf[8 * i + k] for k in range(8)) for i in range(n)]
+        return [tuple(buf[W * i + k] for k in range(W)) for i in range(n)]
+
+    def _on_capturable_stream(self, fn):
+        """Run fn(stream_handle) on the caller's current stream -- or, when that is the legacy default
+        stream (which CUDA cannot capture, so pg_infer would never replay a graph), on a private side
+        stream ordered after and before it.  This is what lets the plain drop-in call
+        ``net_g.infer(...)`` of rvc/infer/pipeline.py:275 use the graph path."""
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != 0:
+            return fn(C.c_void_p(cur.cuda_stream))
+        side = self.__dict__.get("_side")
+        if side is None:
+            with torch.cuda.device(self.device):
+                side = self.__dict__["_side"] = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        out = fn(C.c_void_p(side.cuda_stream))
+        cur.wait_stream(side)
+        return out
+
+    def padded_frames(self, T: int) -> int:
+        """the launch-shape bucket a T-frame call runs at (one CUDA graph per (B, bucket))"""
+        return int(self.lib.pg_padded_frames(self._h, int(T)))
+
+    def set_graph_cache(self, max_graphs: int):
+        _lib.check(self.lib.pg_set_graph_cache(self._h, int(max_graphs)), "pg_set_graph_cache")
 
     def infer(self, phone, lengths, pitch, f0, sid, eps_zp=None, eps_src=None, seed: int = 0,
               want_aux: bool = True, wave_out=None):
         """Time-major tensors on this engine's GPU.  Returns (wave [B][L], aux [4][B][T][C] | None).
-        `wave_out` (optional) receives the waveform instead of a fresh tensor.  On a non-default
-        stream with device-drawn noise the call is staged (include/polgen_rvc.h: pg_infer), and the
-        inputs / `wave_out` may then be pinned CPU tensors."""
+        `wave_out` (optional) receives the waveform instead of a fresh tensor.  The call is staged
+        (include/polgen_rvc.h: pg_infer), so the inputs / `wave_out` may also be pinned CPU tensors."""
         B, T, _ = phone.shape
         dev = self._dev()
         wave = wave_out if wave_out is not None else torch.empty(B, T * self.cfg.upp, device=dev, dtype=torch.float32)
         aux = torch.empty(4, B, T, self.cfg.inter_channels, device=dev, dtype=torch.float32) if want_aux else None
-        _lib.check(self.lib.pg_infer(self._h, self._stream(), B, T, self._ptr(phone), self._ptr(lengths),
-                                     self._ptr(pitch), self._ptr(f0), self._ptr(sid), self._ptr(eps_zp),
-                                     self._ptr(eps_src), C.c_uint64(seed & (2 ** 64 - 1)), self._ptr(wave),
-                                     self._ptr(aux)), "pg_infer")
+        self._on_capturable_stream(lambda st: _lib.check(
+            self.lib.pg_infer(self._h, st, B, T, self._ptr(phone), self._ptr(lengths),
+                              self._ptr(pitch), self._ptr(f0), self._ptr(sid), self._ptr(eps_zp),
+                              self._ptr(eps_src), C.c_uint64(seed & (2 ** 64 - 1)), self._ptr(wave),
+                              self._ptr(aux)), "pg_infer"))
         return wave, aux
 
-    def infer_host(self, phone, lengths, pitch, f0, sid, wave_out, seed: int = 0):
-        """Host (pinned) tensors in, host waveform out; H2D/D2H inside the call."""
-        B, T, _ = phone.shape
-        _lib.check(self.lib.pg_infer_host(self._h, B, T, self._ptr(phone), self._ptr(lengths),
-                                          self._ptr(pitch), self._ptr(f0), self._ptr(sid),
-                                          C.c_uint64(seed & (2 ** 64 - 1)), self._ptr(wave_out)),
-                   "pg_infer_host")
-        return wave_out
+    def infer_segments(self, segs, seed: int = 0, trim: int = 0, want_aux: bool = False):
+        """The silence-split segments of a clip as ONE ragged call (pg_infer_segments; the loop of
+        rvc/infer/pipeline.py:381-447).  `segs`: list of dicts with phone [T][D] f32, pitch [T] i64,
+        f0 [T] f32, sid (int) and optionally eps_zp [T][C], eps_src [T*upp], wave (out buffer of
+        T*upp - 2*trim f32); tensors on this GPU or pinned CPU.  Returns (waves, auxes): every wave has
+        `trim` samples dropped at both ends (t_pad_tgt, pipeline.py:397)."""
+        n = len(segs)
+        arr = (_lib.PgSegment * n)()
+        dev = self._dev()
+        waves, auxes, keep = [], [], []
+        for i, g in enumerate(segs):
+            phone, pitch, f0 = g["phone"], g["pitch"], g["f0"]
+            T = phone.shape[-2]
+            for t in (phone, pitch, f0):
+                if not t.is_contiguous():
+                    raise ValueError("segment tensors must be contiguous")
+            wave = g.get("wave")
+            if wave is None:
+                wave = torch.empty(T * self.cfg.upp - 2 * trim, device=dev, dtype=torch.float32)
+            aux = torch.empty(4, T, self.cfg.inter_channels, device=dev, dtype=torch.float32) if want_aux else None
+            arr[i].T = T
+            arr[i].trim = trim
+            arr[i].sid = int(g.get("sid", 0))
+            arr[i].phone = phone.data_ptr()
+            arr[i].pitch = pitch.data_ptr()
+            arr[i].f0 = f0.data_ptr()
+            ez, es = g.get("eps_zp"), g.get("eps_src")
+            arr[i].eps_zp = 0 if ez is None else ez.data_ptr()
+            arr[i].eps_src = 0 if es is None else es.data_ptr()
+            arr[i].wave = wave.data_ptr()
+            arr[i].aux = 0 if aux is None else aux.data_ptr()
+            waves.append(wave)
+            auxes.append(aux)
+            keep.append((phone, pitch, f0, ez, es))
+        self._on_capturable_stream(lambda st: _lib.check(
+            self.lib.pg_infer_segments(self._h, st, n, arr, C.c_uint64(seed & (2 ** 64 - 1))), "pg_infer_segments"))
+        # the copies are asynchronous: the inputs of the last few calls stay referenced
+        self._keep_alive = (getattr(self, "_keep_alive", []) + [keep])[-4:]
+        return waves, auxes
 
     def text_encoder(self, phone, lengths, pitch):
         B, T, _ = phone.shape
@@ -480,69 +536,113 @@ class SynthesizerTrnMs256NSFsid(Synthesizer):
 
 # --------------------------------------------------------------------------
 # Segment scheduler: the reference decodes the silence-split segments of
-# a clip one after another (rvc/infer/pipeline.py:381-447).  Segments are independent, so this
-# host-side scheduler keeps `lanes` engines (handle + workspace + CUDA stream each) on one GPU and
-# deals the segments round-robin: the latency-bound TextEncoder / flow kernels of one segment overlap
-# the SM-filling decoder kernels of another.  Results are identical to sequential decoding.
+# a clip one after another as B=1 infer calls (rvc/infer/pipeline.py:381-447).  Segments are
+# independent, so this host-side scheduler
+#   * packs them into ragged batches (pg_infer_segments: every layer treats a row's own length as
+#     its hard end, so a row equals its stand-alone B=1 decode whatever it is batched with),
+#     which divides the number of latency-bound TextEncoder / flow launches per clip, and
+#   * deals the batches over `lanes` engines (handle + workspace + CUDA stream each) on one GPU, so
+#     the TextEncoder / flow phase of one batch overlaps the SM-filling decoder phase of another.
 # --------------------------------------------------------------------------
 class SegmentScheduler:
     def __init__(self, cfg: SynthConfig, weights: Dict[str, torch.Tensor], device: int = 0, lanes: int = 2,
-                 flags: int = 0):
+                 flags: int = 0, max_batch: int = 64, max_batch_frames: int = 36000):
         self.cfg = cfg
         self.device = int(device)
+        self.max_batch = int(max_batch)
+        self.max_batch_frames = int(max_batch_frames)     # ~430 KB of workspace per frame
         self.engines = [Engine(cfg, weights, device, flags) for _ in range(max(1, lanes))]
-        # staged pg_infer (fixed I/O buffers + CUDA graph replay) accepts pinned host pointers
-        self._staged = not (flags & (_lib.PG_FLAG_NO_GRAPHS | _lib.PG_FLAG_PROFILE | _lib.PG_FLAG_KEEP_TAPS))
         with torch.cuda.device(self.device):
             self.streams = [torch.cuda.Stream(device=self.device) for _ in self.engines]
+        self._next_lane = 0
 
     def close(self):
         for e in self.engines:
             e.close()
 
-    def decode(self, segments, seeds=None, host_out=None, join=True, out=None):
-        """segments: list of (phone, lengths, pitch, f0, sid) -- CUDA tensors, or pinned CPU tensors
-        (copied to the device on the lane's stream).  Returns the list of waveforms [B][T*upp]: fresh
-        CUDA tensors, or the caller's buffers when given -- `host_out` (pinned CPU tensors, filled by
-        async D2H copies; the host is synchronised before returning) or `out` (preallocated CUDA
-        tensors: a steady stream of clips then makes no allocator calls at all).  The caller's current
-        stream waits for every lane before this returns control to it.  join=False (streaming use:
-        clip after clip) skips both joins, so the lanes run on into the next call and their phases
-        interleave freely; call join() before touching the results.  Inputs must then already be
-        complete on the device (or in pinned host memory)."""
+    def plan_batches(self, lengths):
+        """Indices grouped into ragged batches: longest first, a batch grows while it stays within
+        max_batch rows and max_batch_frames padded frames (rows x bucket of its longest row)."""
+        order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+        batches, cur, cur_T = [], [], 0
+        for i in order:
+            T = self.engines[0].padded_frames(int(lengths[i]))
+            top = max(cur_T, T)
+            if cur and (len(cur) + 1 > self.max_batch or (len(cur) + 1) * top > self.max_batch_frames):
+                batches.append(cur)
+                cur, top = [], T
+            cur.append(i)
+            cur_T = top
+        if cur:
+            batches.append(cur)
+        return batches
+
+    @staticmethod
+    def _segment_dict(seg):
+        """(phone, lengths, pitch, f0, sid) tensors of one B=1 segment (the reference's infer arguments) or a
+        ready dict -> the row description Engine.infer_segments takes"""
+        if isinstance(seg, dict):
+            return seg
+        phone, _, pitch, f0, sid = seg
+        sid = int(sid.reshape(-1)[0]) if torch.is_tensor(sid) else int(sid)   # a CUDA sid costs a sync: pass CPU
+        return {"phone": phone.reshape(-1, phone.shape[-1]), "pitch": pitch.reshape(-1), "f0": f0.reshape(-1),
+                "sid": sid}
+
+    def decode(self, segments, seed: Optional[int] = None, host_out=None, join=True, out=None, trim: int = 0):
+        """segments: list of (phone, lengths, pitch, f0, sid) per segment (B = 1 each; CUDA tensors on
+        this GPU or pinned CPU tensors -- sid a CPU tensor or int).  Returns the list of waveforms
+        [1][T*upp - 2*trim]: fresh CUDA tensors, or the caller's buffers when given -- `host_out` (pinned
+        CPU tensors, filled by async copies; the host is synchronised before returning) or `out`
+        (preallocated CUDA tensors: a steady stream of clips then makes no allocator calls at all; they
+        may be views into one clip-long buffer, see `trim`).  `trim` drops that many samples at both ends
+        of every waveform (t_pad_tgt, pipeline.py:397).  `seed` None draws a fresh base seed from torch's
+        CPU generator (as the reference draws fresh noise per call); batch k of the call uses seed + k
+        and row b of a batch Philox(seed_k + b*0x9E37...).  The caller's current stream waits for every
+        lane before this returns control to it.  join=False (streaming use: clip after clip) skips both
+        joins, so the lanes run on into the next call and their phases interleave freely; call join()
+        before touching the results.  Inputs must then already be complete on the device (or pinned)."""
         dev = torch.device("cuda", self.device)
         cur = torch.cuda.current_stream(self.device)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         ev0 = None
         if join:
             ev0 = torch.cuda.Event()
             ev0.record(cur)
+        rows = [self._segment_dict(s) for s in segments]
+        lengths = [r["phone"].shape[0] for r in rows]
         dst = host_out if host_out is not None else out
-        outs = [None] * len(segments)
-        keep = []
+        outs = [None] * len(rows)
         self.last_launches = 0
-        for i, seg in enumerate(segments):
-            lane = i % len(self.engines)
+        self.last_batches = self.plan_batches(lengths)
+        for k, idx in enumerate(self.last_batches):
+            lane = self._next_lane
+            self._next_lane = (lane + 1) % len(self.engines)
             st = self.streams[lane]
             if ev0 is not None:
                 st.wait_event(ev0)
             with torch.cuda.stream(st):
-                # pinned host tensors go straight to the library (its staged path copies them on the
-                # lane's stream); anything else pageable is first brought to the device by torch
-                args = [t.contiguous() if (t.is_cuda or (self._staged and t.is_pinned()))
-                        else t.to(dev, non_blocking=True) for t in seg]
-                keep.append(args)
-                seed = 0 if seeds is None else int(seeds[i])
-                direct = dst is not None and dst[i].is_contiguous() and (
-                    dst[i].is_cuda or (self._staged and dst[i].is_pinned()))
-                wave, _ = self.engines[lane].infer(*args, None, None, seed, want_aux=False,
-                                                   wave_out=dst[i] if direct else None)
+                batch = []
+                for i in idx:
+                    r = dict(rows[i])
+                    for key in ("phone", "pitch", "f0"):
+                        t = r[key]
+                        if not (t.is_cuda or t.is_pinned()):
+                            t = t.to(dev, non_blocking=True)      # pageable host memory: through torch
+                        r[key] = t.contiguous()
+                    n_out = lengths[i] * self.cfg.upp - 2 * trim
+                    if dst is not None:
+                        w = dst[i].reshape(-1)
+                        if w.numel() != n_out or not w.is_contiguous():
+                            raise ValueError(f"output buffer {i} must hold {n_out} contiguous samples")
+                        r["wave"] = w
+                    batch.append(r)
+                waves, _ = self.engines[lane].infer_segments(batch, seed + k, trim=trim)
                 self.last_launches += self.engines[lane].launch_count()
-                if dst is not None and not direct:
-                    dst[i].copy_(wave, non_blocking=True)
-                outs[i] = wave if dst is None else dst[i]
-                if dst is None:
-                    wave.record_stream(cur)
-        self._keep = getattr(self, "_keep", [])[-4 * len(self.engines):] + keep   # inputs stay alive
+                for i, w in zip(idx, waves):
+                    outs[i] = dst[i] if dst is not None else w.reshape(1, -1)
+                    if dst is None:
+                        w.record_stream(cur)
         if join:
             self.join(host_sync=host_out is not None)
         return outs
