@@ -19,3 +19,6 @@ __all__ += ["Engine", "SegmentScheduler", "Synthesizer", "SynthesizerTrnMs256NSF
 from .pipeline import ClipConverter, coarse_pitch, postprocess, prepare_features
 
 __all__ += ["ClipConverter", "coarse_pitch", "postprocess", "prepare_features"]
+from .tiling import TimeTiledDecoder, plan_tiles
+
+__all__ += ["TimeTiledDecoder", "plan_tiles"]

@@ -100,18 +100,25 @@ class ClipConverter:
     int16 clip: the waveform crosses PCIe once, as int16 (half the fp32 bytes of the reference loop).
     """
 
-    def __init__(self, sched: SegmentScheduler, tgt_sr: int, plan: SegmentPlan = SegmentPlan()):
+    def __init__(self, sched: SegmentScheduler, tgt_sr: int, plan: SegmentPlan = SegmentPlan(), depth: int = 2):
         self.sched = sched
         self.tgt_sr = int(tgt_sr)
         self.t_pad_tgt = self.tgt_sr * plan.x_pad
-        self._buf = None
-        self._pcm = None
+        # `depth` clips in flight: each slot owns a clip-long f32 device buffer, a pinned int16 buffer and
+        # the event that marks its post step done (the lanes wait on it before reusing the slot)
+        self._slots = [{"buf": None, "pcm": None, "done": None} for _ in range(max(1, depth))]
+        self._n = 0
+        with torch.cuda.device(sched.device):
+            self._post = torch.cuda.Stream(device=sched.device)
 
     def convert(self, segments: Sequence, source_audio: Optional[torch.Tensor] = None, volume_envelope: float = 1.0,
                 seed: Optional[int] = None, pcm_out: Optional[torch.Tensor] = None, sync: bool = True):
-        """segments: list of (phone, lengths, pitch, f0, sid) per segment, in clip order.
-        source_audio: the 16 kHz clip (for change_rms when volume_envelope != 1).  Returns int16 [n]:
-        ``pcm_out`` (pinned CPU or CUDA) or a pinned CPU tensor owned by this converter."""
+        """segments: list of (phone, lengths, pitch, f0, sid) per segment, in clip order (CUDA tensors that
+        are complete on the caller's current stream, or pinned CPU tensors).  source_audio: the 16 kHz clip
+        (for change_rms when volume_envelope != 1).  Returns int16 [n]: ``pcm_out`` (pinned CPU or CUDA) or a
+        pinned CPU tensor owned by this converter (valid until `depth` more clips were converted).
+        sync=False returns without waiting (a stream of clips: the TextEncoder / flow phase of the next clip
+        overlaps this clip's decoder and post step); call ``wait()`` before reading the result."""
         sched, upp, trim = self.sched, self.sched.cfg.upp, self.t_pad_tgt
         dev = torch.device("cuda", sched.device)
         frames = [int((s["phone"] if isinstance(s, dict) else s[0]).shape[-2]) for s in segments]
@@ -119,23 +126,42 @@ class ClipConverter:
         if min(counts) <= 0:
             raise ValueError("a segment is shorter than its two t_pad_tgt ends")
         n = sum(counts)
-        if self._buf is None or self._buf.numel() < n:
-            self._buf = torch.empty(n, dtype=torch.float32, device=dev)
-        clip = self._buf[:n]
+        slot = self._slots[self._n % len(self._slots)]
+        self._n += 1
+        if slot["buf"] is None or slot["buf"].numel() < n:
+            slot["buf"] = torch.empty(n, dtype=torch.float32, device=dev)
+        clip = slot["buf"][:n]
         views, off = [], 0
         for c in counts:
             views.append(clip[off:off + c])
             off += c
-        sched.decode(segments, seed=seed, out=views, trim=trim, join=True)
-        eng = sched.engines[0]
+        cur = torch.cuda.current_stream(sched.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        for st in sched.streams:
+            st.wait_event(ready)                       # the caller's inputs are complete
+            if slot["done"] is not None:
+                st.wait_event(slot["done"])            # the slot's previous clip has left its buffers
+        sched.decode(segments, seed=seed, out=views, trim=trim, join=False)
         if pcm_out is None:
-            if self._pcm is None or self._pcm.numel() < n:
-                self._pcm = torch.empty(n, dtype=torch.int16).pin_memory()
-            pcm_out = self._pcm[:n]
-        src = None
-        if source_audio is not None and volume_envelope != 1.0:
-            src = source_audio.to(dev, torch.float32, non_blocking=True)
-        postprocess(eng, clip, src, 16000, self.tgt_sr, float(volume_envelope), pcm_out=pcm_out)
+            if slot["pcm"] is None or slot["pcm"].numel() < n:
+                slot["pcm"] = torch.empty(n, dtype=torch.int16).pin_memory()
+            pcm_out = slot["pcm"][:n]
+        for st in sched.streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self._post.wait_event(ev)
+        with torch.cuda.stream(self._post):
+            src = None
+            if source_audio is not None and volume_envelope != 1.0:
+                src = source_audio.to(dev, torch.float32, non_blocking=True)
+            postprocess(sched.engines[0], clip, src, 16000, self.tgt_sr, float(volume_envelope), pcm_out=pcm_out)
+            slot["done"] = torch.cuda.Event()
+            slot["done"].record(self._post)
         if sync:
-            torch.cuda.current_stream(sched.device).synchronize()
+            self.wait()
         return pcm_out
+
+    def wait(self):
+        """block the host until every clip handed to convert() so far is complete"""
+        self._post.synchronize()

@@ -133,3 +133,30 @@ def decode_sharded(decode_fn: Callable[[List[int]], Dict[int, np.ndarray]], leng
     if len(merged) != len(lengths):
         raise RuntimeError("missing segments after gather")
     return [merged[i] for i in range(len(lengths))]
+
+
+def gather_waveforms(local, owner_of: Sequence[int], n_samples: int, rank: int = 0, world: int = 1, group=None):
+    """Device-side gather of equal-length waveforms for a sharded batch (the one
+    communication step of the path, after the decode): ``local`` is this rank's [n_local][n_samples]
+    CUDA tensor holding its segments in ``plan_shards`` order; rank 0 receives a [n_total][n_samples]
+    tensor in SEGMENT order (one ``torch.distributed.gather`` of equal-size, zero-padded shards over
+    NCCL / NVLink), other ranks get None.  ``owner_of``: the plan_shards bins."""
+    import torch
+    n_total = sum(len(b) for b in owner_of)
+    if world == 1:
+        out = torch.empty(n_total, n_samples, dtype=local.dtype, device=local.device)
+        out[torch.as_tensor(owner_of[0], device=local.device)] = local
+        return out
+    import torch.distributed as dist
+    width = max(len(b) for b in owner_of)
+    send = torch.zeros(width, n_samples, dtype=local.dtype, device=local.device)
+    send[:local.shape[0]] = local
+    recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+    dist.gather(send, recv, dst=0, group=group)
+    if rank != 0:
+        return None
+    out = torch.empty(n_total, n_samples, dtype=local.dtype, device=local.device)
+    for r, idx in enumerate(owner_of):
+        if idx:
+            out[torch.as_tensor(idx, device=local.device)] = recv[r][:len(idx)]
+    return out

@@ -45,7 +45,7 @@ def test_header_symbols_all_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.load().pg_abi_version() == 1
+    assert lib.load().pg_abi_version() == lib.PG_ABI_VERSION == 2
 
 
 def test_config_struct_layout_matches_header(lib):
@@ -72,6 +72,25 @@ int main(void) {
     assert S.flags.offset == o_flags
 
 
+def test_segment_struct_layout_matches_header(lib):
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "polgen_rvc.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(pg_segment), offsetof(pg_segment, trim), offsetof(pg_segment, sid),
+         offsetof(pg_segment, phone), offsetof(pg_segment, wave), offsetof(pg_segment, aux));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "t.c"), os.path.join(d, "t")
+        open(src, "w").write(prog)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        out = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    S = lib.PgSegment
+    assert [C.sizeof(S), S.trim.offset, S.sid.offset, S.phone.offset, S.wave.offset, S.aux.offset] == out
+
+
 def test_argument_errors_without_device(lib):
     L = lib.load()
     assert L.pg_create(None, 0, None) == -1
@@ -79,6 +98,9 @@ def test_argument_errors_without_device(lib):
     assert L.pg_finalize(None) == -1
     assert L.pg_workspace_bytes(None, 1, 1) == 0
     assert L.pg_destroy(None) == 0
+    assert L.pg_infer_segments(None, None, 0, None, 0) == -1
+    assert L.pg_postprocess(None, None, None, 0, None, 0, 16000, 48000, 1.0, None, None) == -1
+    assert L.pg_coarse_pitch(None, None, 0, None, 0, 50.0, 1100.0, None, None) == -1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

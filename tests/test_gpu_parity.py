@@ -193,7 +193,10 @@ def test_tcgen05_path_matches_cuda_core_path():
 
 @pytest.mark.parametrize("shape", [(128, 3, 1, 1000, 1), (128, 11, 5, 777, 2), (64, 7, 3, 1500, 1),
                                    (32, 11, 5, 130, 3), (32, 3, 1, 5000, 1), (256, 7, 1, 300, 2),
-                                   (256, 11, 5, 129, 1), (64, 3, 1, 1, 1)])
+                                   (256, 11, 5, 129, 1), (64, 3, 1, 1, 1),
+                                   # long rows: the launch plan grows the tile to MT = 2 / 4 (>= 2 tiles per SM)
+                                   (128, 11, 1, 90000, 1), (128, 7, 3, 40000, 2), (64, 11, 5, 170000, 1),
+                                   (32, 3, 1, 200000, 1), (256, 7, 1, 80000, 1)])
 def test_conv_op_tcgen05_bit_level(shape):
     """One conv layer through the tcgen05 kernel vs fp32 torch conv on the same f16 inputs
     (ragged L, batch > 1, every channel width of the generator)."""
@@ -310,37 +313,98 @@ def test_dropin_synthesizer_surface():
     assert z_r.shape == (B, cfg.inter_channels, T - head)
 
 
-def test_segment_scheduler_matches_sequential():
-    """SegmentScheduler (two engines / streams on one GPU) returns bit-identical waveforms to decoding
-    the same segments one after another, for device and pinned-host inputs (pipeline.py:381-447)."""
+def _seg_rows(cfg, frames, seed0, d, noise=False):
+    import polgen_rvc_b200 as pg
+    rows, raw = [], []
+    for i, T in enumerate(frames):
+        phone, lengths, pitch, f0, sid = pg.synth_inputs(cfg, 1, T, seed=seed0 + i)
+        r = {"phone": phone[0].to(d), "pitch": pitch[0].to(d), "f0": f0[0].to(d), "sid": 3 + i}
+        n = None
+        if noise:
+            n = pg.synth_noise(cfg, 1, T, seed=seed0 + i)
+            r["eps_zp"] = n[0][0].transpose(0, 1).contiguous().to(d)
+            r["eps_src"] = n[1].reshape(-1).contiguous().to(d)
+        rows.append(r)
+        raw.append(((phone, lengths, pitch, f0, torch.tensor([3 + i])), n))
+    return rows, raw
+
+
+def test_ragged_segment_batch_vs_oracle_and_standalone():
+    """pg_infer_segments: rows of different lengths in one call, every layer treating the row's own length
+    as its hard end -> each row equals the oracle's (and our own) stand-alone B=1 decode of that segment
+    (pipeline.py:381-447 runs them one by one), unlike a padded reference batch."""
+    import polgen_rvc_b200 as pg
+    from oracle import rvc_oracle as orc
+    cfg = pg.CONFIGS["v2-48k"]
+    sd = pg.synth_weights(cfg, seed=6, post_std=0.05)
+    d = _dev()
+    eng = _engine(cfg, sd)
+    frames = [150, 97, 33, 64]
+    rows, raw = _seg_rows(cfg, frames, 70, d, noise=True)
+    waves, auxes = eng.infer_segments(rows, seed=0, want_aux=True)
+    torch.cuda.synchronize()
+    for (inputs, noise), w, aux, T in zip(raw, waves, auxes, frames):
+        o, _, (z, z_p, m_p, logs_p) = orc.infer(sd, cfg, *inputs, *noise)
+        assert w.shape == (T * cfg.upp,)
+        assert snr_db(w.cpu(), o[0, 0]) >= WAVE_SNR_DB, T
+        assert (w.cpu() - o[0, 0]).abs().max().item() <= WAVE_MAXABS
+        for got, want in zip(aux.cpu(), (z, z_p, m_p, logs_p)):
+            assert latent_err(got.transpose(0, 1)[None], want) <= LATENT_REL
+        # and the same segment through the dense B=1 entry (the call the reference pipeline makes)
+        alone, _ = _run(eng, inputs, noise)
+        assert snr_db(w.cpu(), alone[0]) >= 90.0
+    # trim: t_pad_tgt dropped at both ends on copy-out
+    trimmed, _ = eng.infer_segments(rows, seed=0, trim=480)
+    torch.cuda.synchronize()
+    for w, t in zip(waves, trimmed):
+        assert torch.equal(t, w[480:-480])
+
+
+def test_segment_scheduler_batches_and_lanes():
+    """SegmentScheduler: ragged batches dealt over two engines / streams give the waveforms of the same
+    batches decoded one after another on one engine (bit-identical), for device, pinned-host and
+    caller-owned outputs, with and without joining between clips (pipeline.py:381-447)."""
     import polgen_rvc_b200 as pg
     cfg = pg.CONFIGS["v2-48k"]
     sd = pg.synth_weights(cfg, seed=0)
     folded = pg.fold_state_dict(sd)
     d = _dev()
-    frames = [130, 97, 64]
+    frames = [130, 97, 64, 40, 200]
     segs = [pg.synth_inputs(cfg, 1, T, seed=40 + i) for i, T in enumerate(frames)]
+    sched = pg.SegmentScheduler(cfg, folded, 0, lanes=2, max_batch=2)
+    batches = sched.plan_batches(frames)
+    assert sorted(i for b in batches for i in b) == list(range(len(frames))) and max(len(b) for b in batches) == 2
     eng = pg.Engine(cfg, folded, 0)
-    want = [eng.infer(*[t.to(d) for t in s], None, None, 7 + i, want_aux=False)[0].cpu() for i, s in enumerate(segs)]
-    sched = pg.SegmentScheduler(cfg, folded, 0, lanes=2)
-    got = sched.decode([[t.to(d) for t in s] for s in segs], seeds=[7, 8, 9])
+    want = [None] * len(frames)
+    for k, idx in enumerate(batches):
+        rows = [sched._segment_dict(tuple(t.to(d) if torch.is_tensor(t) and j != 4 else t for j, t in enumerate(segs[i])))
+                for i in idx]
+        ws, _ = eng.infer_segments(rows, seed=7 + k)
+        torch.cuda.synchronize()
+        for i, w in zip(idx, ws):
+            want[i] = w.cpu()
+    dev_segs = [[t.to(d) if j != 4 else t for j, t in enumerate(s)] for s in segs]
+    got = sched.decode(dev_segs, seed=7)
     torch.cuda.synchronize()
     for g, w in zip(got, want):
-        assert torch.equal(g.cpu(), w)
+        assert torch.equal(g.cpu()[0], w)
     host_out = [torch.empty(1, T * cfg.upp).pin_memory() for T in frames]
-    got_h = sched.decode([[t.pin_memory() for t in s] for s in segs], seeds=[7, 8, 9], host_out=host_out)
+    got_h = sched.decode([[t.pin_memory() for t in s] for s in segs], seed=7, host_out=host_out)
     for g, w in zip(got_h, want):
-        assert torch.equal(g, w)
+        assert torch.equal(g[0], w)
     assert sched.launch_count() > 300
-    # caller-owned device buffers, streaming (join=False) over two clips, then one join
     bufs = [torch.empty(1, T * cfg.upp, device=d) for T in frames]
-    for _ in range(2):
-        got_d = sched.decode([[t.to(d) for t in s] for s in segs], seeds=[7, 8, 9], out=bufs, join=False)
+    for _ in range(3):
+        got_d = sched.decode(dev_segs, seed=7, out=bufs, join=False)
     sched.join(host_sync=True)
     assert all(g is b for g, b in zip(got_d, bufs))
     for g, w in zip(got_d, want):
-        assert torch.equal(g.cpu(), w)
+        assert torch.equal(g.cpu()[0], w)
     assert all(e.graph_count() >= 1 for e in sched.engines)
+    # seed=None draws fresh noise per call (the reference draws randn_like per infer)
+    a = sched.decode(dev_segs)[0].clone()
+    b = sched.decode(dev_segs)[0].clone()
+    assert not torch.equal(a, b)
 
 
 def test_cuda_graph_replay_matches_direct_launches():
@@ -413,9 +477,11 @@ def test_fused_pair_kernel_matches_unfused_path():
         noise = pg.synth_noise(cfg, B, T, seed=3)
         fused = _engine(cfg, sd, 0)
         a, _ = _run(fused, inputs, noise)
-        b, _ = _run(_engine(cfg, sd, _lib.PG_FLAG_NO_PAIR_FUSION), inputs, noise)
+        n_fused = fused.launch_count()
+        twin = _engine(cfg, sd, _lib.PG_FLAG_NO_PAIR_FUSION)
+        b, _ = _run(twin, inputs, noise)
         assert snr_db(a, b) >= 90.0
-        assert fused.launch_count() < 189          # pairs really ran fused (fewer launches)
+        assert n_fused < twin.launch_count()       # pairs really ran fused (fewer launches)
 
 
 def test_repeatable_across_interleaved_calls():

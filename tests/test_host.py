@@ -145,7 +145,8 @@ def test_plan_shards_balanced_and_complete():
 
 def test_bench_reference_arm_line_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the
-    same metric / unit / workload as our arm, kind "port", no GPU work."""
+    same metric / unit / workload as our arm, no GPU work; kind "reference" when build() vendored the
+    unmodified reference module under baseline/_ref (this container), "port" (oracle) otherwise."""
     import json
     import os
     import subprocess
@@ -159,7 +160,8 @@ def test_bench_reference_arm_line_contract():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "audio-s/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    have_ref = os.path.isfile(os.path.join(root, "baseline", "_ref", "rvc", "lib", "algorithm", "synthesizers.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     assert "[3435, 2965]" in d["config"]["workload"] and "sample" in d["config"]
     assert d["gpu_launches"] == 0
@@ -183,3 +185,36 @@ def test_plan_shards_properties_random():
             loads = [sum(lengths[i] for i in b) for b in bins]
             assert max(loads) <= sum(lengths) / world + max(lengths)
     check()
+
+
+def test_scheduler_batch_planning_without_engine():
+    """SegmentScheduler.plan_batches (host logic only): longest first, bounded rows and padded frames."""
+    import polgen_rvc_b200 as pg
+
+    class FakeEngine:
+        def padded_frames(self, T):
+            q = 32 if T <= 512 else (64 if T <= 2048 else 128)
+            return (T + q - 1) // q * q
+
+    s = pg.SegmentScheduler.__new__(pg.SegmentScheduler)
+    s.engines, s.max_batch, s.max_batch_frames = [FakeEngine()], 3, 8000
+    lengths = [3435, 2965, 100, 4100, 1000, 1000, 1000, 50]
+    batches = s.plan_batches(lengths)
+    assert sorted(i for b in batches for i in b) == list(range(len(lengths)))
+    for b in batches:
+        top = max(FakeEngine().padded_frames(lengths[i]) for i in b)
+        assert len(b) <= 3 and (len(b) == 1 or len(b) * top <= 8000)
+    assert batches[0][0] == 3            # longest first
+    assert s.plan_batches([]) == []
+
+
+def test_time_tile_planning():
+    """plan_tiles: tiles cover [0, T) exactly once, interior cuts aligned, never more tiles than asked."""
+    import polgen_rvc_b200 as pg
+    for T, n in ((3435, 8), (3435, 2), (100, 8), (7, 4), (1, 3), (4100, 5)):
+        tiles = pg.plan_tiles(T, n)
+        assert 1 <= len(tiles) <= n
+        assert tiles[0][0] == 0 and tiles[-1][1] == T
+        assert all(tiles[i][1] == tiles[i + 1][0] for i in range(len(tiles) - 1))
+        assert all(b > a for a, b in tiles)
+        assert all(a % 8 == 0 for a, _ in tiles)

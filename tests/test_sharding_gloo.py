@@ -40,13 +40,20 @@ def _worker(rank, world, port, out_path):
     t = torch.tensor([float(sum(lengths[i] for i in mine))])
     dist.all_reduce(t)
     assert int(t.item()) == sum(lengths)
+    # equal-length batch (BASELINE configs[2]): tensor gather of unequal shards, rank 0 gets segment order
+    n_seg, n_samples = 7, 5
+    bins = seg.plan_shards([1000] * n_seg, world)
+    local = torch.stack([torch.full((n_samples,), float(i)) for i in bins[rank]])
+    full = seg.gather_waveforms(local, bins, n_samples, rank, world)
     if rank == 0:
         assert res is not None and len(res) == len(lengths)
         for i, w in enumerate(res):
             assert w.shape[0] == lengths[i] * 3 and float(w[0]) == float(i)
+        assert full.shape == (n_seg, n_samples)
+        assert torch.equal(full[:, 0], torch.arange(n_seg, dtype=torch.float32))
         open(out_path, "w").write("ok")
     else:
-        assert res is None
+        assert res is None and full is None
     dist.barrier()
     dist.destroy_process_group()
 
