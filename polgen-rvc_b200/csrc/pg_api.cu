@@ -118,6 +118,7 @@ struct pg_handle_s {
   DevBuf io;
   DevBuf io_eps;                // explicit-noise staging of pg_infer_segments
   DevBuf post;                  // pg_postprocess scratch
+  double live_frac = 1.0;       // true frames / padded frames of the current call (profile FLOP accounting)
   bool planes_ok = true;        // every decoder stage fits the channel-plane kernels (else: time-major path)
   cudaStream_t own_stream = nullptr;   // pg_infer_host and callers on the legacy default stream
 
@@ -484,7 +485,7 @@ int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_d
     rec.e0 = take_event(h);
     rec.e1 = take_event(h);
     rec.cls = umma ? 2 : 1;
-    rec.flops = 2.0 * a.B * a.L_out * (double)a.Cin * a.Cout * a.K;
+    rec.flops = h->live_frac * 2.0 * a.B * a.L_out * (double)a.Cin * a.Cout * a.K;
     rec.shape[0] = a.Cin; rec.shape[1] = a.Cout; rec.shape[2] = a.K; rec.shape[3] = a.dil; rec.shape[4] = a.L_out;
     rec.shape[5] = 0;
     cudaEventRecord(rec.e0, s);
@@ -738,7 +739,7 @@ int run_plane_conv(pg_handle h, cudaStream_t s, PlaneConvArgs a, const ConvW& w)
     rec.e0 = take_event(h);
     rec.e1 = take_event(h);
     rec.cls = 0;
-    rec.flops = 2.0 * a.B * a.L * (double)a.Cin * a.N * (w.algo_taps > 0 ? w.algo_taps : (double)a.K);
+    rec.flops = h->live_frac * 2.0 * a.B * a.L * (double)a.Cin * a.N * (w.algo_taps > 0 ? w.algo_taps : (double)a.K);
     rec.shape[0] = a.Cin; rec.shape[1] = a.N; rec.shape[2] = a.K; rec.shape[3] = a.dil; rec.shape[4] = a.L;
     rec.shape[5] = plane_conv_mt(a);
     cudaEventRecord(rec.e0, s);
@@ -765,7 +766,7 @@ int run_pair_conv(pg_handle h, cudaStream_t s, PairConvArgs a, const ConvW& w1, 
     rec.e0 = take_event(h);
     rec.e1 = take_event(h);
     rec.cls = 0;
-    rec.flops = 2.0 * 2.0 * a.B * a.L * (double)a.C * a.C * a.K;
+    rec.flops = h->live_frac * 2.0 * 2.0 * a.B * a.L * (double)a.C * a.C * a.K;
     rec.shape[0] = a.C; rec.shape[1] = -a.C; rec.shape[2] = a.K; rec.shape[3] = a.dil; rec.shape[4] = a.L;
     rec.shape[5] = pair_conv_mt(a);
     cudaEventRecord(rec.e0, s);
@@ -1278,6 +1279,11 @@ static int infer_staged(pg_handle h, cudaStream_t s, const CallIo& io_in, uint64
   }
   const IoPtrs io = io_layout(c, h->upp, reinterpret_cast<char*>(h->io.p), B, Tp);
   const size_t D = c.input_dim, U = h->upp, C = c.inter_channels;
+  {   // algorithmic work is counted over the rows that exist, not over the padding
+    double live = 0;
+    for (int b = 0; b < B; ++b) live += io_in.segs ? io_in.segs[b].T : T;
+    h->live_frac = live / ((double)B * Tp);
+  }
   const float* eps_zp = io_in.eps_zp;
   const float* eps_src = io_in.eps_src;
   int eps_T = T;
@@ -1585,6 +1591,7 @@ int pg_source(pg_handle h, void* stream, int B, int T, const float* f0, const fl
 int pg_generator(pg_handle h, void* stream, int B, int T, const float* z, const float* source,
                  const int64_t* sid, float* wave) {
   PG_TRY(check_ready(h, B, T));
+  h->live_frac = 1.0;
   if (!z || !source || !sid || !wave) return fail(PG_ERR_INVALID, "null argument");
   Guard g(h->device);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

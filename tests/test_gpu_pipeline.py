@@ -95,7 +95,7 @@ def test_pipeline_replay_on_device_matches_reference_pcm():
         waves = [torch.from_numpy(stub_waveform(ph, pi, pf, UPP)).to(d) for ph, pi, pf in calls]
         clip = torch.cat([w[TGT_SR:-TGT_SR] for w in waves])
         vol = float(g["vol"])
-        pcm = pg.postprocess(eng, clip, torch.from_numpy(audio).to(d) if vol != 1 else None, 16000, TGT_SR, vol)
+        pcm = pg.postprocess(eng, clip, torch.from_numpy(audio.copy()).to(d) if vol != 1 else None, 16000, TGT_SR, vol)
         torch.cuda.synchronize()
         diff = np.abs(pcm.cpu().numpy().astype(np.int32) - g["pcm"].astype(np.int32)).max()
         assert diff == 0 if vol == 1 else diff <= 1, (name, diff)

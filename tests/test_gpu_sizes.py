@@ -100,7 +100,7 @@ def test_equal_length_batch_8x1000_vs_oracle():
     torch.cuda.synchronize()
     _check(wave.cpu(), [aux[i].cpu().transpose(1, 2) for i in range(4)], ref, "B=8")
     mt = _max_mt(eng)
-    assert mt.get(128, 0) >= 2 and mt.get(256, 0) >= 2, mt
+    assert mt.get(128, 0) >= 2 and mt.get(64, 0) >= 2, mt      # (C = 256: N = 256 fills TMEM at MT = 1)
 
 
 @pytest.mark.parametrize("name", ["v2-32k", "v1-40k", "v2-40k"])
@@ -175,7 +175,8 @@ def test_graph_buckets_replay_distinct_lengths_and_lru():
     eng = net.engine()
     assert eng.graph_count() == 1                        # one graph served all six lengths
     eng.set_graph_cache(2)
-    for T in (40, 200, 300, 400):                        # four more buckets, twice each -> captured, then trimmed
+    net.infer(*[t.to(d) for t in pg.synth_inputs(cfg, 1, 400, seed=400)])   # grow the workspace first: a growth drops all graphs
+    for T in (400, 40, 200, 300):                        # four more buckets, twice each -> captured, then trimmed
         inp = [t.to(d) for t in pg.synth_inputs(cfg, 1, T, seed=T)]
         for _ in range(2):
             net.infer(*inp)
