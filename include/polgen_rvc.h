@@ -88,7 +88,7 @@ typedef struct pg_config {
 #define PG_FLAG_NO_PAIR_FUSION 32 /* run every ResBlock conv as its own kernel (validation twin of the fused pair kernel) */
 #define PG_FLAG_LEGACY_DECODER 16 /* decoder on the time-major tcgen05 kernel (A/B comparison aid) */
 #define PG_FLAG_NO_GRAPHS 64    /* launch every kernel of pg_infer directly (default: a CUDA graph per (B,T) is captured on the second call of a shape and replayed afterwards when the stream is capturable and the noise is device-drawn) */
-#define PG_FLAG_PLANES_SWAP 128  /* C=128 ResBlock convs with swapped MMA operands (weights = M, 256 time rows = N); opt-in, results identical */
+#define PG_FLAG_NO_PLANES_SWAP 128  /* validation twin: C=128 ResBlock convs WITHOUT the swapped MMA operands (default: weights = M, 256 time rows = N where the shape qualifies) */
 #define PG_FLAG_NO_PAD 256       /* do not pad T up to a launch-shape bucket (validation twin of the padded path) */
 #define PG_FLAG_F16_LATENTS 8  /* TextEncoder / flow GEMMs with single-pass f16 tensor-core operands (default: fp32-accurate) */
 

@@ -22,7 +22,7 @@ PG_FLAG_F16_LATENTS = 8
 PG_FLAG_LEGACY_DECODER = 16
 PG_FLAG_NO_PAIR_FUSION = 32
 PG_FLAG_NO_GRAPHS = 64
-PG_FLAG_PLANES_SWAP = 128
+PG_FLAG_NO_PLANES_SWAP = 128
 PG_FLAG_NO_PAD = 256
 PG_F32 = 0
 PG_F64 = 3

@@ -731,7 +731,7 @@ int run_plane_conv(pg_handle h, cudaStream_t s, PlaneConvArgs a, const ConvW& w)
   a.K = w.K;
   a.tapmask = w.tapmask;
   if (a.Cout_real == 0) a.Cout_real = w.Cout;
-  a.swap = (h->cfg.flags & PG_FLAG_PLANES_SWAP) != 0;
+  a.swap = (h->cfg.flags & PG_FLAG_NO_PLANES_SWAP) == 0;
   if (!plane_conv_supported(a)) return fail(PG_ERR_UNSUPPORTED, "layer shape not supported by the plane conv kernel");
   const bool prof = (h->cfg.flags & PG_FLAG_PROFILE) != 0;
   pg_handle_s::ProfRec rec;

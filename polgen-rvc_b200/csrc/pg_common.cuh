@@ -105,7 +105,7 @@ struct PlaneConvArgs {
   const __half* accin16 = nullptr; const float* accin32 = nullptr;
   __half* out16 = nullptr; float out16_slope = 1.f; float* out32 = nullptr;
   float out_scale = 1.f;
-  int swap = 0;   // PG_FLAG_PLANES_SWAP: operand-swapped MMA where the shape qualifies (C = 128, MT = 2)
+  int swap = 1;   // operand-swapped MMA where the shape qualifies (C = 128, MT = 2); 0: PG_FLAG_NO_PLANES_SWAP twin
 };
 bool plane_conv_supported(const PlaneConvArgs& a);
 int plane_conv_mt(const PlaneConvArgs& a);   // 128-row tiles per CTA tile the launch plan picks (0: unsupported)

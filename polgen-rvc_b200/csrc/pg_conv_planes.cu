@@ -877,9 +877,10 @@ cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s) {
   if (!dbg && pl.bias_smem && a.N == pl.NT && a.row_mul == 1 && !a.bbias && !a.res32 && !a.accin16 && !a.accin32 &&
       !a.out32 && a.out16 && a.out_scale == 1.f && a.out16_slope <= 1.f && a.res_inv >= 1.f)
     epi = a.res16 ? EPI_C2 : EPI_C1;
-  // operand-swapped variant for the C = 128 ResBlock convs (opt-in until validated on hardware)
-  static const bool swap_on = env_int("PG_PLANES_SWAP", 0) != 0;
-  if ((swap_on || a.swap) && epi != EPI_GENERIC && pl.MT == 2 && pl.NT == 128 && pl.KC == 64 && pl.res_cols == 64 &&
+  // operand-swapped variant for the C = 128 ResBlock convs: +13 % on the conv1 shapes (1190 -> 1345 TFLOP/s at
+  // k = 11, profiles/r02b), neutral on conv2 -- on by default, PG_FLAG_NO_PLANES_SWAP / PG_PLANES_SWAP=0 is the twin
+  static const bool swap_on = env_int("PG_PLANES_SWAP", 1) != 0;
+  if (swap_on && a.swap && epi != EPI_GENERIC && pl.MT == 2 && pl.NT == 128 && pl.KC == 64 && pl.res_cols == 64 &&
       a.Cout_real == 128)
     return epi == EPI_C1 ? launch_t<2, 4, EPI_C1, false, true>(a, pl, s) : launch_t<2, 4, EPI_C2, false, true>(a, pl, s);
 #define PG_DISPATCH(MT_, KC16_)                                                        \

@@ -49,6 +49,8 @@ struct PairParams {
   int w_tile_bytes;
   int r_slots, r_slot_bytes;
   int tmem_cols;
+  int lag;      // GEMM 2 trails GEMM 1 by this many tiles (1 .. depth-1)
+  int depth;    // D: tiles in flight between GEMM 1 and E2 (accumulator pairs and intermediates are D-buffered)
   uint32_t idesc;
   int no_ring;  // PG_PAIR_NORING (debug): fp32 residual read straight from global memory in E2
   int no_pre;   // PG_PAIR_NOPRE (debug): accumulate input loaded at use instead of prefetched
@@ -76,7 +78,12 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   return q;
 }
 
-template <int MT, int C>
+// RES_X: the residual is the raw value of the f16 input stream (else: the fp32 stream through the ring)
+// PLAIN (RES_X only): the 2 of 3 pairs of a ResBlock that just write y16 = lrelu(conv2 + bias2 + raw(x)) -- no
+// accumulate input, unit scale, no fp32 output -- get a straight-line E2 (the generic one spends ~360
+// instructions per 32x16 item on run-time options and re-derived addresses, which made E2 the issue-bound
+// stage of the C = 64 pairs: profiles/r02d_pair64k3)
+template <int MT, int C, bool RES_X, bool PLAIN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_constant__ CUtensorMap wmap2,
                    const PairParams p) {
@@ -88,18 +95,19 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
   uint8_t* w1 = smem;                                              // [K] tiles, GEMM 1
   uint8_t* w2 = w1 + (size_t)p.K * p.w_tile_bytes;                 // [K] tiles, GEMM 2
   uint8_t* a_ring = w2 + (size_t)p.K * p.w_tile_bytes;
-  uint8_t* tmp = a_ring + (size_t)p.a_slots * p.a_slot_bytes;      // [2] intermediate planes
-  uint8_t* r_ring = tmp + 2 * (size_t)p.tmp_bytes;
+  uint8_t* tmp = a_ring + (size_t)p.a_slots * p.a_slot_bytes;      // [D] intermediate planes
+  const uint32_t D = (uint32_t)p.depth;
+  uint8_t* r_ring = tmp + (size_t)D * p.tmp_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(r_ring + (size_t)p.r_slots * p.r_slot_bytes);
   uint64_t* a_full = bars;                    // [a_slots]
-  uint64_t* a_empty = a_full + p.a_slots;     // [a_slots]  GEMM 1 commit + every E2 warp
-  uint64_t* acc1_full = a_empty + p.a_slots;  // [2]
-  uint64_t* acc1_empty = acc1_full + 2;       // [2]  E1 warps
-  uint64_t* tmp_full = acc1_empty + 2;        // [2]  E1 warps
-  uint64_t* tmp_empty = tmp_full + 2;         // [2]  GEMM 2 commit
-  uint64_t* acc2_full = tmp_empty + 2;        // [2]
-  uint64_t* acc2_empty = acc2_full + 2;       // [2]  E2 warps
-  uint64_t* w_ready = acc2_empty + 2;
+  uint64_t* a_empty = a_full + p.a_slots;     // [a_slots]  GEMM 1 commit
+  uint64_t* acc1_full = a_empty + p.a_slots;  // [D]
+  uint64_t* acc1_empty = acc1_full + D;       // [D]  E1 warps
+  uint64_t* tmp_full = acc1_empty + D;        // [D]  E1 warps
+  uint64_t* tmp_empty = tmp_full + D;         // [D]  GEMM 2 commit
+  uint64_t* acc2_full = tmp_empty + D;        // [D]
+  uint64_t* acc2_empty = acc2_full + D;       // [D]  E2 warps
+  uint64_t* w_ready = acc2_empty + D;
   uint64_t* r_full = w_ready + 1;             // [r_slots]
   uint64_t* r_empty = r_full + p.r_slots;     // [r_slots]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_empty + p.r_slots);
@@ -109,9 +117,14 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
   if (tid == 0) {
     for (int s = 0; s < p.a_slots; ++s) {
       mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 1 + E2_WARPS);
+      // The window slot is released by GEMM 1's commit alone.  E2 used to read the residual rows from the
+      // window and so held the slot through E1 / GEMM 2 / E2: with 3 slots that left ~1/3 of the ring's
+      // bytes in flight towards HBM and the kernel latency-bound (ncu r02d: MMA lane and loader both spinning
+      // on the ring, DRAM 22 %, tensor pipe 19 % at C = 64 k = 3).  E2 now re-reads its residual rows from
+      // global memory -- they were fetched microseconds ago, so they come from L2.
+      mbar_init(&a_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < (int)D; ++s) {
       mbar_init(&acc1_full[s], 1);
       mbar_init(&acc1_empty[s], E1_WARPS);
       mbar_init(&tmp_full[s], E1_WARPS);
@@ -137,7 +150,7 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int rows = BM * MT + (p.K - 1) * p.dil;        // input window rows
-  const uint32_t acc1_col = 0u, acc2_col = 2u * MT * C;  // TMEM columns of the two accumulator pairs
+  const uint32_t acc1_col = 0u, acc2_col = D * MT * C;  // TMEM columns of the two accumulator sets
 
   if (warp == LOAD_WARP) {
     // ===== input window loader (bulk copies + zero fill outside [0, L)) =====
@@ -201,11 +214,14 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
       int n_my = 0;     // live tiles of this CTA (dead ones are skipped by every role)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
         n_my += (tile % p.n_row_tiles) * p.MO < row_end(p, tile / p.n_row_tiles) ? 1 : 0;
-      for (int it = 0; it <= n_my; ++it) {
+      // GEMM 2 trails GEMM 1 by LAG tiles: E1 of a tile has LAG GEMM-1 times to finish before the tensor pipe
+      // needs its intermediate (each mbarrier hand-off costs a few hundred cycles, more than a k = 3 GEMM)
+      const int LAG = p.lag;
+      for (int it = 0; it < n_my + LAG; ++it) {
         if (it < n_my) {   // GEMM 1 (dilated conv) of tile it
-          const uint32_t slot = (uint32_t)it % (uint32_t)p.a_slots, b = (uint32_t)it & 1u;
+          const uint32_t slot = (uint32_t)it % (uint32_t)p.a_slots, b = (uint32_t)it % D;
           mbar_wait(&a_full[slot], ((uint32_t)it / (uint32_t)p.a_slots) & 1u);
-          mbar_wait(&acc1_empty[b], (((uint32_t)it >> 1) & 1u) ^ 1u);
+          mbar_wait(&acc1_empty[b], (((uint32_t)it / D) & 1u) ^ 1u);
           tcgen05_fence_after();
           const uint32_t d_base = tmem_base + acc1_col + b * (uint32_t)(MT * C);
           const uint32_t a_base = a_lo0 + a_units0 + slot * slot_units;
@@ -223,10 +239,10 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
           tcgen05_commit(&acc1_full[b]);
           tcgen05_commit(&a_empty[slot]);
         }
-        if (it >= 1) {     // GEMM 2 (plain conv over the shared-memory intermediate) of tile it-1
-          const uint32_t j = (uint32_t)(it - 1), b = j & 1u;
-          mbar_wait(&tmp_full[b], (j >> 1) & 1u);
-          mbar_wait(&acc2_empty[b], ((j >> 1) & 1u) ^ 1u);
+        if (it >= LAG) {   // GEMM 2 (plain conv over the shared-memory intermediate) of tile it-LAG
+          const uint32_t j = (uint32_t)(it - LAG), b = j % D;
+          mbar_wait(&tmp_full[b], (j / D) & 1u);
+          mbar_wait(&acc2_empty[b], ((j / D) & 1u) ^ 1u);
           tcgen05_fence_after();
           const uint32_t d_base = tmem_base + acc2_col + b * (uint32_t)(MT * C);
           const uint32_t t_base = t_lo0 + tmp_units0 + b * tmp_units;
@@ -284,9 +300,9 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
       const int t_end = row_end(p, tile / p.n_row_tiles);
       if (rt * p.MO >= t_end) continue;
       const int t_first = rt * p.MO - p.h2;            // time of intermediate row 0
-      const uint32_t b = j & 1u;
-      mbar_wait(&acc1_full[b], (j >> 1) & 1u);
-      mbar_wait(&tmp_empty[b], ((j >> 1) & 1u) ^ 1u);
+      const uint32_t b = j % D;
+      mbar_wait(&acc1_full[b], (j / D) & 1u);
+      mbar_wait(&tmp_empty[b], ((j / D) & 1u) ^ 1u);
       tcgen05_fence_after();
       uint8_t* tb = tmp + (size_t)b * p.tmp_bytes;
 #pragma unroll 1
@@ -317,6 +333,69 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
       }
       ++j;
     }
+  } else if (warp >= E2_WARP0 && PLAIN) {
+    // ===== E2, straight-line form: y16 = lrelu(acc2 + bias2 + raw(x), slope) =====
+    const int quarter = warp & 3, grp = (warp - E2_WARP0) >> 2;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc2_col;
+    const float* bias2 = bias_s + C;
+    const float rinv = p.res_inv, slope = p.out16_slope;
+    const int L = p.L, MO = p.MO;
+    constexpr int IPW = ITEMS / (E2_WARPS / 4);
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int rt = tile % p.n_row_tiles, bb = tile / p.n_row_tiles;
+      const int o0 = rt * MO;
+      if (o0 >= row_end(p, bb)) continue;
+      const uint32_t b = j % D;
+      const size_t plane_base = (size_t)bb * PLANES * L;
+      const uint4* xin = reinterpret_cast<const uint4*>(p.x) + plane_base;
+      uint4* yout = reinterpret_cast<uint4*>(p.out16) + plane_base;
+      uint4 rpre[2 * IPW];
+#pragma unroll
+      for (int ii = 0; ii < IPW; ++ii) {     // residual rows: fetched (from L2) before waiting for the accumulator
+        const int it = grp + ii * (E2_WARPS / 4);
+        const int m = it / NCB, cb = it - m * NCB;
+        const int o = m * BM + quarter * 32 + lane;
+        const int t = o0 + o;
+        if (o < MO && t < L) {
+          const uint4* g = xin + (size_t)(cb * 2) * L + t;
+          rpre[2 * ii] = g[0];
+          rpre[2 * ii + 1] = g[L];
+        }
+      }
+      mbar_wait(&acc2_full[b], (j / D) & 1u);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int ii = 0; ii < IPW; ++ii) {
+        const int it = grp + ii * (E2_WARPS / 4);
+        const int m = it / NCB, cb = it - m * NCB;
+        const int o = m * BM + quarter * 32 + lane;
+        const int t = o0 + o;
+        uint32_t acc[ECOLS];
+        tmem_ld16(lane_taddr + b * (uint32_t)(MT * C) + (uint32_t)(m * C + cb * ECOLS), acc);
+        if (o < MO && t < L) {
+          uint4* dst = yout + (size_t)(cb * 2) * L + t;
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            float v[8], rr[8];
+            unpack8(rpre[2 * ii + jj], rr);
+            const float4 b0 = *reinterpret_cast<const float4*>(bias2 + cb * ECOLS + jj * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias2 + cb * ECOLS + jj * 8 + 4);
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float a = __uint_as_float(acc[jj * 8 + i]) + bv[i] + fminf(rr[i], rr[i] * rinv);
+              v[i] = fmaxf(a, a * slope);
+            }
+            dst[(size_t)jj * L] = pack8(v);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc2_empty[b]);
+      ++j;
+    }
   } else if (warp >= E2_WARP0) {
     // ===== E2: acc2 -> + bias2 + residual -> scale / accumulate -> HBM =====
     const int quarter = warp & 3, grp = (warp - E2_WARP0) >> 2;
@@ -327,7 +406,7 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
       const int rt = tile % p.n_row_tiles, bb = tile / p.n_row_tiles;
       const int o0 = rt * p.MO;
       if (o0 >= row_end(p, bb)) continue;
-      const uint32_t b = j & 1u, slot = j % (uint32_t)p.a_slots;
+      const uint32_t b = j % D;
       const size_t plane_base = (size_t)bb * PLANES * p.L;
       // the accumulate input of this warp's items is fetched BEFORE waiting for the accumulator, so its
       // HBM latency hides behind GEMM 2 (registers: IPW items x 2 chunks, x2 for fp32)
@@ -356,10 +435,24 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
           }
         }
       }
-      mbar_wait(&acc2_full[b], (j >> 1) & 1u);
-      mbar_wait(&a_full[slot], (j / (uint32_t)p.a_slots) & 1u);   // residual rows of the window (already landed)
+      // f16 stream: the residual (raw x of the output rows) is prefetched from global memory (L2) as well
+      uint4 rpre[RES_X ? 2 * IPW : 1];
+      if (RES_X) {
+#pragma unroll
+        for (int ii = 0; ii < IPW; ++ii) {
+          const int it = grp + ii * (E2_WARPS / 4);
+          const int m = it / NCB, cb = it - m * NCB;
+          const int o = m * BM + quarter * 32 + lane;
+          const int t = o0 + o;
+          if (o < p.MO && t < p.L) {
+            const uint4* g = reinterpret_cast<const uint4*>(p.x) + plane_base + (size_t)(cb * 2) * p.L + t;
+            rpre[2 * ii] = g[0];
+            rpre[2 * ii + 1] = g[p.L];
+          }
+        }
+      }
+      mbar_wait(&acc2_full[b], (j / D) & 1u);
       tcgen05_fence_after();
-      const uint8_t* aw = a_ring + (size_t)slot * p.a_slot_bytes;
 #pragma unroll
       for (int ii = 0; ii < IPW; ++ii) {
         const int it = grp + ii * (E2_WARPS / 4);
@@ -369,13 +462,13 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
         const bool ok = o < p.MO && t < p.L;
         uint4 rq[4];
         int ring_slot = -1;
-        if (p.r_slots > 0 && p.no_ring) {
+        if (!RES_X && p.no_ring) {
           if (ok) {
             const uint4* g0 = reinterpret_cast<const uint4*>(p.res32) + (plane_base + (size_t)(cb * 2) * p.L + t) * 2;
             const uint4* g1 = reinterpret_cast<const uint4*>(p.res32) + (plane_base + (size_t)(cb * 2 + 1) * p.L + t) * 2;
             rq[0] = g0[0]; rq[1] = g0[1]; rq[2] = g1[0]; rq[3] = g1[1];
           }
-        } else if (p.r_slots > 0) {
+        } else if (!RES_X) {
           const uint32_t sidx = j * (uint32_t)MT + (uint32_t)m;
           const uint32_t rslot = sidx % (uint32_t)p.r_slots;
           mbar_wait(&r_full[rslot], (sidx / (uint32_t)p.r_slots) & 1u);
@@ -387,9 +480,8 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
           rq[3] = *reinterpret_cast<const uint4*>(rs + BM * 32 + 16);
           ring_slot = (int)rslot;   // released below, once the loads have landed in registers
         } else {
-          const uint8_t* ar = aw + (size_t)(cb * 2) * p.plane_bytes + (size_t)(o + p.h2 + p.h1) * 16;
-          rq[0] = *reinterpret_cast<const uint4*>(ar);
-          rq[1] = *reinterpret_cast<const uint4*>(ar + p.plane_bytes);
+          rq[0] = rpre[RES_X ? 2 * ii : 0];
+          rq[1] = rpre[RES_X ? 2 * ii + 1 : 0];
         }
         uint32_t acc[ECOLS];
         tmem_ld16(lane_taddr + b * (uint32_t)(MT * C) + (uint32_t)(m * C + cb * ECOLS), acc);
@@ -409,7 +501,7 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[jj * 8 + i]) + bias2[cb * ECOLS + jj * 8 + i];
-            if (p.r_slots > 0) {
+            if (!RES_X) {
               const uint4 q0 = rq[2 * jj], q1 = rq[2 * jj + 1];
               v[0] += __uint_as_float(q0.x); v[1] += __uint_as_float(q0.y);
               v[2] += __uint_as_float(q0.z); v[3] += __uint_as_float(q0.w);
@@ -460,10 +552,7 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&acc2_empty[b]);
-        mbar_arrive(&a_empty[slot]);
-      }
+      if (lane == 0) mbar_arrive(&acc2_empty[b]);
       ++j;
     }
   }
@@ -474,7 +563,7 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
 
 struct PairPlan {
   int MT, a_slots, a_slot_bytes, plane_bytes, tmp_plane_bytes, tmp_bytes, w_tile_bytes, r_slots, r_slot_bytes,
-      tmem_cols;
+      tmem_cols, depth;
   size_t smem;
 };
 
@@ -487,10 +576,16 @@ bool make_pair_plan(const PairConvArgs& a, PairPlan* out) {
   const size_t budget = (size_t)227 * 1024;
   const size_t w_all = 2 * (size_t)a.K * w_tile;
   static const int forced_mt = [] { const char* e = getenv("PG_PAIR_MT"); return e ? atoi(e) : 0; }();
-  // pass 0 insists on rings deep enough to hide the HBM latency (3 input windows in flight and, for
-  // the fp32 residual stream, two tiles of residual slots); pass 1 takes whatever fits
+  static const int forced_depth = [] { const char* e = getenv("PG_PAIR_DEPTH"); return e ? atoi(e) : 0; }();
+  // MT: measured on the bench clip (profiles/r02f): C = 64 prefers 128-row tiles (k = 3: 0.148 vs 0.200 ms), C = 32
+  // 256-row tiles (0.204 vs 0.245 / 0.230 ms at MT = 1 / 4).  pass 0 insists on rings deep enough to hide the HBM
+  // latency (3 input windows in flight and, for the fp32 residual stream, two tiles of residual slots) and on a
+  // pipeline depth of 3; pass 1 takes whatever fits.
+  const int order64[3] = {1, 2, 0}, order32[3] = {2, 4, 1};
   for (int pass = 0; pass < 2; ++pass)
-  for (int MT : {4, 2, 1}) {
+  for (int mi = 0; mi < 3; ++mi) {
+    const int MT = a.C == 64 ? order64[mi] : order32[mi];
+    if (MT == 0) continue;
     if (forced_mt && MT != forced_mt) continue;
     if (4 * MT * a.C > 512) continue;
     const int MO = BM * MT - (a.K - 1);
@@ -505,7 +600,10 @@ bool make_pair_plan(const PairConvArgs& a, PairPlan* out) {
     size_t need = fixed + w_all + 2 * (size_t)a_slot + 2 * (size_t)tmp_bytes + (size_t)r_slots * r_slot;
     if (need > budget) continue;
     size_t left = budget - need;
-    int a_slots = 2;
+    int a_slots = 2, depth = 2;
+    // depth / lag sweeps (profiles/r02h: depth 2-4, lag 1-2) moved nothing: the stage that bounds the pairs is
+    // not the GEMM 1 -> E1 -> GEMM 2 hand-off, so the shared memory goes to the rings instead
+    const int max_depth = std::min(forced_depth > 0 ? forced_depth : 2, 512 / (2 * MT * a.C));
     auto grow = [&](int* v, int cap, size_t unit) {
       while (*v < cap && left >= unit) {
         ++*v;
@@ -514,19 +612,21 @@ bool make_pair_plan(const PairConvArgs& a, PairPlan* out) {
     };
     grow(&a_slots, 3, a_slot);
     if (a.res32) grow(&r_slots, 2 * MT, r_slot);
+    grow(&depth, std::min(3, max_depth), tmp_bytes);
     grow(&a_slots, 4, a_slot);
+    grow(&depth, max_depth, tmp_bytes);
     if (a.res32) grow(&r_slots, 3 * MT, r_slot);
-    if (pass == 0 && (a_slots < 3 || (a.res32 && r_slots < 2 * MT))) continue;
+    if (pass == 0 && (a_slots < 3 || (a.res32 && r_slots < 2 * MT) || depth < std::min(3, max_depth))) continue;
     int tm = 32;
-    while (tm < 4 * MT * a.C) tm <<= 1;
-    *out = PairPlan{MT, a_slots, a_slot, plane_bytes, tmp_plane, tmp_bytes, w_tile, r_slots, r_slot, tm,
-                    fixed + w_all + (size_t)a_slots * a_slot + 2 * (size_t)tmp_bytes + (size_t)r_slots * r_slot};
+    while (tm < 2 * depth * MT * a.C) tm <<= 1;
+    *out = PairPlan{MT, a_slots, a_slot, plane_bytes, tmp_plane, tmp_bytes, w_tile, r_slots, r_slot, tm, depth,
+                    fixed + w_all + (size_t)a_slots * a_slot + (size_t)depth * tmp_bytes + (size_t)r_slots * r_slot};
     return true;
   }
   return false;
 }
 
-template <int MT, int C>
+template <int MT, int C, bool RES_X, bool PLAIN>
 cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_t s) {
   CUtensorMap m1, m2;
   const int kc = C == 64 ? 64 : 32;
@@ -544,7 +644,9 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
   p.h1 = (a.K - 1) * a.dil / 2; p.h2 = (a.K - 1) / 2;
   p.plane_bytes = pl.plane_bytes; p.a_slots = pl.a_slots; p.a_slot_bytes = pl.a_slot_bytes;
   p.tmp_plane_bytes = pl.tmp_plane_bytes; p.tmp_bytes = pl.tmp_bytes; p.w_tile_bytes = pl.w_tile_bytes;
-  p.r_slots = pl.r_slots; p.r_slot_bytes = pl.r_slot_bytes; p.tmem_cols = pl.tmem_cols;
+  p.r_slots = pl.r_slots; p.r_slot_bytes = pl.r_slot_bytes; p.tmem_cols = pl.tmem_cols; p.depth = pl.depth;
+  static const int forced_lag = [] { const char* e = getenv("PG_PAIR_LAG"); return e ? atoi(e) : 0; }();
+  p.lag = forced_lag > 0 ? std::min(forced_lag, pl.depth - 1) : pl.depth - 1;
   p.idesc = make_idesc(BM, C);
   static const int no_pre = [] { const char* e = getenv("PG_PAIR_NOPRE"); return e ? atoi(e) : 0; }();
   p.no_pre = no_pre;
@@ -552,12 +654,12 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
   p.no_ring = no_ring;
 
   static DeviceOnce once;
-  if (cudaError_t e = ensure_dyn_smem(pair_planes_kernel<MT, C>, once, 227 * 1024)) return e;
+  if (cudaError_t e = ensure_dyn_smem(pair_planes_kernel<MT, C, RES_X, PLAIN>, once, 227 * 1024)) return e;
   int grid = device_sm_count();
   if (grid > p.total_tiles) grid = p.total_tiles;
   static const int dbg_sync = [] { const char* e = getenv("PG_PAIR_SYNC"); return e ? atoi(e) : 0; }();
   if (dbg_sync & 1) cudaStreamSynchronize(s);
-  pair_planes_kernel<MT, C><<<grid, NTHREADS, pl.smem, s>>>(m1, m2, p);
+  pair_planes_kernel<MT, C, RES_X, PLAIN><<<grid, NTHREADS, pl.smem, s>>>(m1, m2, p);
   if (dbg_sync & 2) cudaStreamSynchronize(s);
   return cudaGetLastError();
 }
@@ -579,18 +681,23 @@ int pair_conv_mt(const PairConvArgs& a) {
 cudaError_t launch_pair_planes(const PairConvArgs& a, cudaStream_t s) {
   PairPlan pl;
   if (!pair_conv_supported(a) || !make_pair_plan(a, &pl)) return cudaErrorInvalidValue;
+  const bool plain = !a.res32 && !a.accin16 && !a.accin32 && !a.out32 && a.out16 && a.out_scale == 1.f;
+#define PG_PAIR(MT_, C_)                                                          \
+  return a.res32 ? launch_pair_t<MT_, C_, false, false>(a, pl, s)                 \
+                 : (plain ? launch_pair_t<MT_, C_, true, true>(a, pl, s) : launch_pair_t<MT_, C_, true, false>(a, pl, s))
   if (a.C == 32) {
     switch (pl.MT) {
-      case 4: return launch_pair_t<4, 32>(a, pl, s);
-      case 2: return launch_pair_t<2, 32>(a, pl, s);
-      case 1: return launch_pair_t<1, 32>(a, pl, s);
+      case 4: PG_PAIR(4, 32);
+      case 2: PG_PAIR(2, 32);
+      case 1: PG_PAIR(1, 32);
     }
   } else {
     switch (pl.MT) {
-      case 2: return launch_pair_t<2, 64>(a, pl, s);
-      case 1: return launch_pair_t<1, 64>(a, pl, s);
+      case 2: PG_PAIR(2, 64);
+      case 1: PG_PAIR(1, 64);
     }
   }
+#undef PG_PAIR
   return cudaErrorInvalidValue;
 }
 

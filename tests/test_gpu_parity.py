@@ -445,9 +445,9 @@ def test_cuda_graph_replay_matches_direct_launches():
 
 
 def test_operand_swapped_conv_matches_default():
-    """PG_FLAG_PLANES_SWAP runs the C = 128 ResBlock convs with the MMA operands swapped (weights as the
-    M operand, 256 time rows as N, shuffle-transposed epilogue).  Same products, same fp32 accumulation:
-    the waveform must match the default path to rounding on a segment long enough for MT = 2 tiles."""
+    """The C = 128 ResBlock convs run with the MMA operands swapped (weights as the M operand, 256 time rows
+    as N, shuffle-transposed epilogue); PG_FLAG_NO_PLANES_SWAP is the unswapped twin.  Same products, same
+    fp32 accumulation: the waveforms must match to rounding on a segment long enough for MT = 2 tiles."""
     import polgen_rvc_b200 as pg
     from polgen_rvc_b200 import _lib
     cfg = pg.CONFIGS["v2-48k"]
@@ -457,7 +457,7 @@ def test_operand_swapped_conv_matches_default():
     T = 1400
     inp = [t.to(d) for t in pg.synth_inputs(cfg, 1, T, seed=1)]
     a = pg.Engine(cfg, folded, 0).infer(*inp, None, None, 5, want_aux=False)[0]
-    b = pg.Engine(cfg, folded, 0, _lib.PG_FLAG_PLANES_SWAP).infer(*inp, None, None, 5, want_aux=False)[0]
+    b = pg.Engine(cfg, folded, 0, _lib.PG_FLAG_NO_PLANES_SWAP).infer(*inp, None, None, 5, want_aux=False)[0]
     torch.cuda.synchronize()
     assert bool(torch.isfinite(b).all())
     assert snr_db(a, b) >= 90.0
