@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpolgen_rvc.so")
+LIB_PATH = os.environ.get("PG_LIB_PATH") or os.path.join(_HERE, "libpolgen_rvc.so")   # PG_LIB_PATH: A/B builds
 
 PG_MAX_UPS = 8
 PG_MAX_RESBLOCK_KERNELS = 4
@@ -24,6 +24,7 @@ PG_FLAG_NO_PAIR_FUSION = 32
 PG_FLAG_NO_GRAPHS = 64
 PG_FLAG_NO_PLANES_SWAP = 128
 PG_FLAG_NO_PAD = 256
+PG_FLAG_F32_STREAM = 512
 PG_F32 = 0
 PG_F64 = 3
 PG_ABI_VERSION = 2

@@ -398,14 +398,17 @@ int pad_frames(const pg_handle h, int T) {
   return (T + q - 1) / q * q;
 }
 
-int ensure_ws(pg_handle h, size_t bytes) {
+// `s`: the stream the call runs on -- the zero fill must be ORDERED with the kernels that follow (a plain
+// cudaMemset runs on the legacy stream, which a non-blocking caller stream does not wait for: the fill then
+// lands on top of results the first kernels have already written)
+int ensure_ws(pg_handle h, size_t bytes, cudaStream_t s) {
   if (h->ws.bytes >= bytes) return PG_OK;
   invalidate_graphs(h);
   if (h->ws.p) PG_CUDA_CHECK(cudaFree(h->ws.p));
   h->ws.p = nullptr;
   h->ws.bytes = 0;
   PG_CUDA_CHECK(cudaMalloc(&h->ws.p, bytes));
-  PG_CUDA_CHECK(cudaMemset(h->ws.p, 0, bytes));   // rows past a hard end are never written: keep them finite
+  PG_CUDA_CHECK(cudaMemsetAsync(h->ws.p, 0, bytes, s));   // rows past a hard end are never written: keep them finite
   h->ws.bytes = bytes;
   return PG_OK;
 }
@@ -779,6 +782,23 @@ int run_pair_conv(pg_handle h, cudaStream_t s, PairConvArgs a, const ConvW& w1, 
   return PG_OK;
 }
 
+// the hi/lo form of the last stage needs every ResBlock pair on the fused pair kernel
+bool wide_hl_ok(pg_handle h, const StageW& S, int B, int L) {
+  if (h->cfg.flags & (PG_FLAG_NO_PAIR_FUSION | PG_FLAG_KEEP_TAPS | PG_FLAG_F32_STREAM)) return false;
+  static __half dummy;
+  for (size_t i = 0; i < S.c1.size(); ++i) {
+    const ConvW &w1 = S.c1[i], &w2 = S.c2[i];
+    if (w1.Cin != w1.Cout || w2.Cin != w2.Cout || w1.Cin != w2.Cin || w1.K != w2.K || !w1.bias || !w2.bias) return false;
+    PairConvArgs pa;
+    pa.x = &dummy; pa.x_lo = &dummy; pa.B = B; pa.L = L; pa.C = w1.Cin; pa.K = w1.K;
+    pa.dil = h->cfg.resblock_dilations[i / h->cfg.n_dilations][i % h->cfg.n_dilations];
+    pa.w1 = w1.w16; pa.w2 = w2.w16; pa.bias1 = w1.bias; pa.bias2 = w2.bias; pa.res_inv = 10.f;
+    pa.out16 = &dummy; pa.out_lo = &dummy;
+    if (!pair_conv_supported(pa)) return false;
+  }
+  return true;
+}
+
 // ---- GeneratorNSF.forward (nsf.py:120-144) on the channel-plane layout ------------------
 // Conv inputs live in HBM as f16 planes in L-form (already leaky-ReLU'd with the slope the next
 // conv applies, 0.1); residuals are recovered from them in the epilogue.  The LAST stage keeps
@@ -836,7 +856,7 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
         a.out16 = x0;   // raw
         PG_TRY(run_plane_conv(h, s, a, S.up));
       }
-      PG_LAUNCH(h, launch_noise_inject_planes(x0, DT_F16, x0, source, S.noise_w, S.noise_b, B, (int)L, C,
+      PG_LAUNCH(h, launch_noise_inject_planes(x0, DT_F16, x0, nullptr, source, S.noise_w, S.noise_b, B, (int)L, C,
                                               (int)Lsrc, S.noise_k, S.noise_stride, S.noise_pad, SL, s));
       PG_TRY(record_tap_planes(h, s, "dec.ups" + std::to_string(i), x0, DT_F16, INV, B, L, C));
       for (int j = 0; j < nk; ++j) {
@@ -874,6 +894,51 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
         }
       }
       PG_TRY(record_tap_planes(h, s, "dec.stage" + std::to_string(i), acc, DT_F16, INV, B, L, C));
+    } else if (wide_hl_ok(h, S, B, (int)L)) {
+      // Last stage, hi/lo form: the residual stream is carried as two f16 planes (x = hi + lo, 2^-22 relative);
+      // hi is the conv operand itself, so a pair moves 256 instead of 384 bytes per sample.  The 1/3-mean that
+      // feeds conv_post stays in fp32 planes.
+      float* r0 = reinterpret_cast<float*>(buf[fr[0]]);           // ups output before the source injection
+      float* acc = reinterpret_cast<float*>(buf[fr[3]]);
+      __half *a0 = h16[0], *aa = h16[1], *ab = h16[2];
+      __half *l0 = reinterpret_cast<__half*>(buf[fr[1]]), *la = reinterpret_cast<__half*>(buf[fr[2]]),
+             *lb = reinterpret_cast<__half*>(buf[cur]);          // the ups input is dead once r0 exists
+      {
+        PlaneConvArgs a;
+        a.x = reinterpret_cast<const __half*>(buf[cur]); a.B = B; a.L = (int)Lin; a.pad = S.up_pad;
+        a.tlen = tlen; a.len_mul = mul_in;
+        a.Cout_real = C; a.row_mul = S.u;
+        a.out32 = r0;
+        PG_TRY(run_plane_conv(h, s, a, S.up));
+      }
+      PG_LAUNCH(h, launch_noise_inject_planes(r0, DT_F32, a0, l0, source, S.noise_w, S.noise_b, B, (int)L, C,
+                                              (int)Lsrc, S.noise_k, S.noise_stride, S.noise_pad, SL, s));
+      for (int j = 0; j < nk; ++j) {
+        const __half *xc = a0, *lc = l0;
+        for (int d = 0; d < nd; ++d) {
+          const bool last = d == nd - 1;
+          PairConvArgs pa;
+          pa.x = xc; pa.x_lo = lc; pa.B = B; pa.L = (int)L; pa.dil = c.resblock_dilations[j][d]; pa.res_inv = INV;
+          pa.tlen = tlen; pa.len_mul = mul;
+          if (last) {
+            pa.out_scale = 1.f / nk;
+            pa.accin32 = j > 0 ? acc : nullptr;
+            pa.out32 = acc;
+          } else {
+            const bool to_b = xc == aa;
+            pa.out16 = to_b ? ab : aa;
+            pa.out_lo = to_b ? lb : la;
+            pa.out16_slope = SL;
+          }
+          const int prc = run_pair_conv(h, s, pa, S.c1[j * nd + d], S.c2[j * nd + d]);
+          if (prc != PG_OK) return prc == PG_ERR_UNSUPPORTED ? fail(prc, "hi/lo pair unexpectedly unsupported") : prc;
+          xc = pa.out16;
+          lc = pa.out_lo;
+        }
+      }
+      PG_TRY(record_tap_planes(h, s, "dec.stage" + std::to_string(i), acc, DT_F32, 1.f, B, L, C));
+      PG_LAUNCH(h, launch_conv_post_planes(acc, DT_F32, h->conv_post_w, wave, B, (int)L, C, 7, 0.01f, tlen, mul, s));
+      return PG_OK;
     } else {
       float* r0 = reinterpret_cast<float*>(buf[fr[0]]);
       float* ra = reinterpret_cast<float*>(buf[fr[1]]);
@@ -888,7 +953,7 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
         a.out32 = r0;
         PG_TRY(run_plane_conv(h, s, a, S.up));
       }
-      PG_LAUNCH(h, launch_noise_inject_planes(r0, DT_F32, a0, source, S.noise_w, S.noise_b, B, (int)L, C,
+      PG_LAUNCH(h, launch_noise_inject_planes(r0, DT_F32, a0, nullptr, source, S.noise_w, S.noise_b, B, (int)L, C,
                                               (int)Lsrc, S.noise_k, S.noise_stride, S.noise_pad, SL, s));
       PG_TRY(record_tap_planes(h, s, "dec.ups" + std::to_string(i), r0, DT_F32, 1.f, B, L, C));
       for (int j = 0; j < nk; ++j) {
@@ -1184,7 +1249,7 @@ size_t pg_workspace_bytes(pg_handle h, int B, int T) {
 
 static int prepare(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, const int64_t* lengths,
                    const int64_t* pitch, const int64_t* sid, const CallMeta* meta = nullptr) {
-  PG_TRY(ensure_ws(h, w.total));
+  PG_TRY(ensure_ws(h, w.total, s));
   PG_LAUNCH(h, launch_prepare_ints(lengths, pitch, sid, meta, at<int>(h, w.lens), at<int>(h, w.tlen),
                                    at<int>(h, w.pitch), at<int>(h, w.sid), B, T, h->cfg.spk_embed_dim, s));
   return PG_OK;
@@ -1266,7 +1331,7 @@ static int infer_staged(pg_handle h, cudaStream_t s, const CallIo& io_in, uint64
   const int B = io_in.B, T = io_in.T;
   const int Tp = pad_frames(h, T);
   const Ws w = plan_ws(c, B, Tp);
-  PG_TRY(ensure_ws(h, w.total));
+  PG_TRY(ensure_ws(h, w.total, s));
   const size_t need = io_layout(c, h->upp, nullptr, B, Tp).total;
   if (h->io.bytes < need) {
     invalidate_graphs(h);
@@ -1274,7 +1339,7 @@ static int infer_staged(pg_handle h, cudaStream_t s, const CallIo& io_in, uint64
     h->io.p = nullptr;
     h->io.bytes = 0;
     PG_CUDA_CHECK(cudaMalloc(&h->io.p, need));
-    PG_CUDA_CHECK(cudaMemset(h->io.p, 0, need));   // padding rows are read (and masked): keep them finite
+    PG_CUDA_CHECK(cudaMemsetAsync(h->io.p, 0, need, s));   // padding rows are read (and masked): keep them finite
     h->io.bytes = need;
   }
   const IoPtrs io = io_layout(c, h->upp, reinterpret_cast<char*>(h->io.p), B, Tp);
@@ -1581,7 +1646,7 @@ int pg_source(pg_handle h, void* stream, int B, int T, const float* f0, const fl
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const Ws w = plan_ws(h->cfg, B, T);
   h->launches = 0;
-  PG_TRY(ensure_ws(h, w.total));
+  PG_TRY(ensure_ws(h, w.total, s));
   PG_LAUNCH(h, launch_source(f0, eps_src, T, seed, nullptr, nullptr, h->src_w, h->src_b, at<double>(h, w.phase),
                              source, sine, B, T, h->upp, h->cfg.sr, s));
   ++h->launches;
@@ -1597,7 +1662,7 @@ int pg_generator(pg_handle h, void* stream, int B, int T, const float* z, const 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const Ws w = plan_ws(h->cfg, B, T);
   h->launches = 0;
-  PG_TRY(ensure_ws(h, w.total));
+  PG_TRY(ensure_ws(h, w.total, s));
   // the generator ignores x_mask after its input: all rows valid
   std::vector<int64_t> full(B, T);
   int64_t* d_len = reinterpret_cast<int64_t*>(at<char>(h, w.qkv));

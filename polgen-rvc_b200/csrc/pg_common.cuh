@@ -122,6 +122,9 @@ struct PairConvArgs {
   const void* w1 = nullptr; const void* w2 = nullptr;      // [K][C][C] f16 each
   const float* bias1 = nullptr; const float* bias2 = nullptr;
   const float* res32 = nullptr; float res_inv = 1.f;
+  // hi/lo stream (last decoder stage): x is the hi plane, x_lo its f16 remainder; the residual is raw(x + x_lo)
+  // and, with out_lo, the output is written as the same two planes (out16 = hi, out_lo = lo)
+  const __half* x_lo = nullptr; __half* out_lo = nullptr;
   const __half* accin16 = nullptr; const float* accin32 = nullptr;
   __half* out16 = nullptr; float out16_slope = 1.f; float* out32 = nullptr;
   float out_scale = 1.f;
@@ -140,10 +143,11 @@ cudaError_t launch_planes_to_nlc(const void* x, DType dt, float* y, int B, int L
 // planes f16 -> time-major f16 [B][L][C]
 cudaError_t launch_planes_to_nlc_f16(const __half* x, __half* y, int B, int L, int C, cudaStream_t s);
 // x_raw (planes, f16 or f32, in place) += bn[c] + sum_j wn[j][c] * src[b][t*stride + j - pad];
-// a16 = lrelu(x, slope) (f16 planes); f32 raw kept in x when dt == DT_F32
-cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, const float* src, const float* wn,
-                                       const float* bn, int B, int L, int C, int Lsrc, int k, int stride,
-                                       int pad, float slope, cudaStream_t s);
+// a16 = lrelu(x, slope) (f16 planes); f32 raw kept in x when dt == DT_F32 -- unless lo16 is given: then the
+// L-form value leaves as the hi/lo pair (a16, lo16) and x is not written back
+cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, __half* lo16, const float* src,
+                                       const float* wn, const float* bn, int B, int L, int C, int Lsrc, int k,
+                                       int stride, int pad, float slope, cudaStream_t s);
 // wave = tanh(conv_post(lrelu(x, in_slope))) over planes (f16 or f32)
 // tlen (nullable): rows >= tlen[b]*len_mul read as zero (hard end of row b)
 cudaError_t launch_conv_post_planes(const void* x, DType dt, const float* w /*[K][C]*/, float* wave, int B,

@@ -41,6 +41,7 @@ struct PairParams {
   const int* tlen; int len_mul;        // hard end of row b: tlen[b]*len_mul (nullptr = L)
   const float* bias1; const float* bias2;
   const float* res32; float res_inv;
+  const __half* x_lo; __half* out_lo;     // HL stream: remainder planes of the input / output
   const __half* accin16; const float* accin32;
   __half* out16; float out16_slope; float* out32; float out_scale;
   int MO, n_row_tiles, total_tiles, h1, h2;
@@ -83,7 +84,10 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 // accumulate input, unit scale, no fp32 output -- get a straight-line E2 (the generic one spends ~360
 // instructions per 32x16 item on run-time options and re-derived addresses, which made E2 the issue-bound
 // stage of the C = 64 pairs: profiles/r02d_pair64k3)
-template <int MT, int C, bool RES_X, bool PLAIN>
+// HL (with RES_X): the stream is carried as TWO f16 planes, x = hi + lo (hi is the conv operand, lo its rounding
+// remainder: 2^-22 relative, fp32-class), so the last decoder stage keeps its residual stream at full precision
+// without a separate fp32 copy -- 256 instead of 384 bytes per sample and pair.
+template <int MT, int C, bool RES_X, bool PLAIN, bool HL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_constant__ CUtensorMap wmap2,
                    const PairParams p) {
@@ -283,7 +287,18 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
         __syncwarp();
         if (mine && pl == 0) mbar_expect_tx(&r_full[slot], (uint32_t)PLANES * bytes);
         __syncwarp();
-        if (mine && bytes)
+        if (HL) {
+          // hi/lo stream: the slot holds [hi planes][lo planes], 16 B per row each (same bytes as an fp32 slot);
+          // lanes 0..PLANES-1 of the sub-group copy the hi planes, PLANES..2*PLANES-1 the lo planes
+          const bool mine2 = sub < batch && m < MT && pl < 2 * PLANES;
+          if (mine2 && bytes) {
+            const int q = pl < PLANES ? pl : pl - PLANES;
+            const __half* srcp = pl < PLANES ? p.x : p.x_lo;
+            bulk_g2s(r_ring + (size_t)slot * p.r_slot_bytes + (size_t)pl * (BM * 16),
+                     reinterpret_cast<const char*>(srcp) + (((size_t)b * PLANES + q) * p.L + row0) * 16, bytes / 2,
+                     &r_full[slot]);
+          }
+        } else if (mine && bytes)
           bulk_g2s(r_ring + (size_t)slot * p.r_slot_bytes + (size_t)pl * (BM * 32),
                    reinterpret_cast<const char*>(p.res32) + (((size_t)b * PLANES + pl) * p.L + row0) * 32, bytes,
                    &r_full[slot]);
@@ -350,17 +365,20 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
       const size_t plane_base = (size_t)bb * PLANES * L;
       const uint4* xin = reinterpret_cast<const uint4*>(p.x) + plane_base;
       uint4* yout = reinterpret_cast<uint4*>(p.out16) + plane_base;
-      uint4 rpre[2 * IPW];
+      uint4* lout = reinterpret_cast<uint4*>(p.out_lo) + plane_base;
+      uint4 rpre[HL ? 1 : 2 * IPW];
+      if (!HL) {
 #pragma unroll
-      for (int ii = 0; ii < IPW; ++ii) {     // residual rows: fetched (from L2) before waiting for the accumulator
-        const int it = grp + ii * (E2_WARPS / 4);
-        const int m = it / NCB, cb = it - m * NCB;
-        const int o = m * BM + quarter * 32 + lane;
-        const int t = o0 + o;
-        if (o < MO && t < L) {
-          const uint4* g = xin + (size_t)(cb * 2) * L + t;
-          rpre[2 * ii] = g[0];
-          rpre[2 * ii + 1] = g[L];
+        for (int ii = 0; ii < IPW; ++ii) {     // residual rows: fetched (from L2) before waiting for the accumulator
+          const int it = grp + ii * (E2_WARPS / 4);
+          const int m = it / NCB, cb = it - m * NCB;
+          const int o = m * BM + quarter * 32 + lane;
+          const int t = o0 + o;
+          if (o < MO && t < L) {
+            const uint4* g = xin + (size_t)(cb * 2) * L + t;
+            rpre[2 * ii] = g[0];
+            rpre[2 * ii + 1] = g[L];
+          }
         }
       }
       mbar_wait(&acc2_full[b], (j / D) & 1u);
@@ -371,6 +389,22 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
         const int m = it / NCB, cb = it - m * NCB;
         const int o = m * BM + quarter * 32 + lane;
         const int t = o0 + o;
+        uint4 hq[2], lq[2];
+        if (HL) {     // hi/lo rows of this item from the residual ring (the loader runs tiles ahead of the MMAs)
+          const uint32_t sidx = j * (uint32_t)MT + (uint32_t)m;
+          const uint32_t rslot = sidx % (uint32_t)p.r_slots;
+          mbar_wait(&r_full[rslot], (sidx / (uint32_t)p.r_slots) & 1u);
+          const uint8_t* rs = r_ring + (size_t)rslot * p.r_slot_bytes + (size_t)(cb * 2) * (BM * 16) +
+                              (size_t)(quarter * 32 + lane) * 16;
+          hq[0] = *reinterpret_cast<const uint4*>(rs);
+          hq[1] = *reinterpret_cast<const uint4*>(rs + BM * 16);
+          lq[0] = *reinterpret_cast<const uint4*>(rs + PLANES * (BM * 16));
+          lq[1] = *reinterpret_cast<const uint4*>(rs + (PLANES + 1) * (BM * 16));
+          uint32_t dep = hq[0].x ^ hq[1].x ^ lq[0].x ^ lq[1].x ^ hq[0].w ^ hq[1].w ^ lq[0].w ^ lq[1].w;
+          asm volatile("" : "+r"(dep));
+          __syncwarp();
+          if (lane == 0) mbar_arrive_dep(&r_empty[rslot], dep);   // released once the loads have landed
+        }
         uint32_t acc[ECOLS];
         tmem_ld16(lane_taddr + b * (uint32_t)(MT * C) + (uint32_t)(m * C + cb * ECOLS), acc);
         if (o < MO && t < L) {
@@ -378,7 +412,13 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
             float v[8], rr[8];
-            unpack8(rpre[2 * ii + jj], rr);
+            unpack8(HL ? hq[jj] : rpre[HL ? 0 : 2 * ii + jj], rr);
+            if (HL) {
+              float ll[8];
+              unpack8(lq[jj], ll);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) rr[i] += ll[i];
+            }
             const float4 b0 = *reinterpret_cast<const float4*>(bias2 + cb * ECOLS + jj * 8);
             const float4 b1 = *reinterpret_cast<const float4*>(bias2 + cb * ECOLS + jj * 8 + 4);
             const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -387,7 +427,15 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
               const float a = __uint_as_float(acc[jj * 8 + i]) + bv[i] + fminf(rr[i], rr[i] * rinv);
               v[i] = fmaxf(a, a * slope);
             }
-            dst[(size_t)jj * L] = pack8(v);
+            const uint4 hi = pack8(v);
+            dst[(size_t)jj * L] = hi;
+            if (HL) {     // remainder of the f16 rounding, itself in f16
+              float hv[8];
+              unpack8(hi, hv);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] -= hv[i];
+              (lout + (size_t)(cb * 2) * L + t)[(size_t)jj * L] = pack8(v);
+            }
           }
         }
       }
@@ -436,8 +484,8 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
         }
       }
       // f16 stream: the residual (raw x of the output rows) is prefetched from global memory (L2) as well
-      uint4 rpre[RES_X ? 2 * IPW : 1];
-      if (RES_X) {
+      uint4 rpre[RES_X && !HL ? 2 * IPW : 1];
+      if (RES_X && !HL) {
 #pragma unroll
         for (int ii = 0; ii < IPW; ++ii) {
           const int it = grp + ii * (E2_WARPS / 4);
@@ -479,9 +527,20 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
           rq[2] = *reinterpret_cast<const uint4*>(rs + BM * 32);
           rq[3] = *reinterpret_cast<const uint4*>(rs + BM * 32 + 16);
           ring_slot = (int)rslot;   // released below, once the loads have landed in registers
+        } else if (HL) {   // ring slot = [hi planes][lo planes]: rq[0..1] = hi chunks, rq[2..3] = lo chunks
+          const uint32_t sidx = j * (uint32_t)MT + (uint32_t)m;
+          const uint32_t rslot = sidx % (uint32_t)p.r_slots;
+          mbar_wait(&r_full[rslot], (sidx / (uint32_t)p.r_slots) & 1u);
+          const uint8_t* rs = r_ring + (size_t)rslot * p.r_slot_bytes + (size_t)(cb * 2) * (BM * 16) +
+                              (size_t)(quarter * 32 + lane) * 16;
+          rq[0] = *reinterpret_cast<const uint4*>(rs);
+          rq[1] = *reinterpret_cast<const uint4*>(rs + BM * 16);
+          rq[2] = *reinterpret_cast<const uint4*>(rs + PLANES * (BM * 16));
+          rq[3] = *reinterpret_cast<const uint4*>(rs + (PLANES + 1) * (BM * 16));
+          ring_slot = (int)rslot;
         } else {
-          rq[0] = rpre[RES_X ? 2 * ii : 0];
-          rq[1] = rpre[RES_X ? 2 * ii + 1 : 0];
+          rq[0] = rpre[RES_X && !HL ? 2 * ii : 0];
+          rq[1] = rpre[RES_X && !HL ? 2 * ii + 1 : 0];
         }
         uint32_t acc[ECOLS];
         tmem_ld16(lane_taddr + b * (uint32_t)(MT * C) + (uint32_t)(m * C + cb * ECOLS), acc);
@@ -510,6 +569,12 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
             } else {
               float rr[8];
               unpack8(rq[jj], rr);
+              if (HL) {
+                float ll[8];
+                unpack8(rq[2 + jj], ll);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rr[i] += ll[i];
+              }
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] += fminf(rr[i], rr[i] * p.res_inv);
             }
@@ -545,7 +610,15 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
             if (p.out16) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * p.out16_slope);   // slope <= 1
-              *(reinterpret_cast<uint4*>(p.out16) + off) = pack8(v);
+              const uint4 hi = pack8(v);
+              *(reinterpret_cast<uint4*>(p.out16) + off) = hi;
+              if (HL && p.out_lo) {
+                float hv[8];
+                unpack8(hi, hv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] -= hv[i];
+                *(reinterpret_cast<uint4*>(p.out_lo) + off) = pack8(v);
+              }
             }
           }
         }
@@ -595,8 +668,9 @@ bool make_pair_plan(const PairConvArgs& a, PairPlan* out) {
     const int a_slot = (planes * plane_bytes + 127) & ~127;
     const int tmp_plane = 16 * (BM * MT + 16);
     const int tmp_bytes = (planes * tmp_plane + 127) & ~127;
-    const int r_slot = a.res32 ? BM * planes * 32 : 0;
-    int r_slots = a.res32 ? 2 : 0;
+    const bool ring = a.res32 || a.x_lo;       // fp32 stream or hi/lo planes: [planes][128 rows] x 32 B per slot
+    const int r_slot = ring ? BM * planes * 32 : 0;
+    int r_slots = ring ? 2 : 0;
     size_t need = fixed + w_all + 2 * (size_t)a_slot + 2 * (size_t)tmp_bytes + (size_t)r_slots * r_slot;
     if (need > budget) continue;
     size_t left = budget - need;
@@ -611,12 +685,12 @@ bool make_pair_plan(const PairConvArgs& a, PairPlan* out) {
       }
     };
     grow(&a_slots, 3, a_slot);
-    if (a.res32) grow(&r_slots, 2 * MT, r_slot);
+    if (ring) grow(&r_slots, 2 * MT, r_slot);
     grow(&depth, std::min(3, max_depth), tmp_bytes);
     grow(&a_slots, 4, a_slot);
     grow(&depth, max_depth, tmp_bytes);
-    if (a.res32) grow(&r_slots, 3 * MT, r_slot);
-    if (pass == 0 && (a_slots < 3 || (a.res32 && r_slots < 2 * MT) || depth < std::min(3, max_depth))) continue;
+    if (ring) grow(&r_slots, 3 * MT, r_slot);
+    if (pass == 0 && (a_slots < 3 || (ring && r_slots < 2 * MT) || depth < std::min(3, max_depth))) continue;
     int tm = 32;
     while (tm < 2 * depth * MT * a.C) tm <<= 1;
     *out = PairPlan{MT, a_slots, a_slot, plane_bytes, tmp_plane, tmp_bytes, w_tile, r_slots, r_slot, tm, depth,
@@ -626,7 +700,7 @@ bool make_pair_plan(const PairConvArgs& a, PairPlan* out) {
   return false;
 }
 
-template <int MT, int C, bool RES_X, bool PLAIN>
+template <int MT, int C, bool RES_X, bool PLAIN, bool HL>
 cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_t s) {
   CUtensorMap m1, m2;
   const int kc = C == 64 ? 64 : 32;
@@ -636,6 +710,7 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
   p.x = a.x; p.L = a.L; p.B = a.B; p.K = a.K; p.dil = a.dil;
   p.tlen = a.tlen; p.len_mul = a.len_mul;
   p.bias1 = a.bias1; p.bias2 = a.bias2; p.res32 = a.res32; p.res_inv = a.res_inv;
+  p.x_lo = a.x_lo; p.out_lo = a.out_lo;
   p.accin16 = a.accin16; p.accin32 = a.accin32;
   p.out16 = a.out16; p.out16_slope = a.out16_slope; p.out32 = a.out32; p.out_scale = a.out_scale;
   p.MO = BM * MT - (a.K - 1);
@@ -654,12 +729,12 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
   p.no_ring = no_ring;
 
   static DeviceOnce once;
-  if (cudaError_t e = ensure_dyn_smem(pair_planes_kernel<MT, C, RES_X, PLAIN>, once, 227 * 1024)) return e;
+  if (cudaError_t e = ensure_dyn_smem(pair_planes_kernel<MT, C, RES_X, PLAIN, HL>, once, 227 * 1024)) return e;
   int grid = device_sm_count();
   if (grid > p.total_tiles) grid = p.total_tiles;
   static const int dbg_sync = [] { const char* e = getenv("PG_PAIR_SYNC"); return e ? atoi(e) : 0; }();
   if (dbg_sync & 1) cudaStreamSynchronize(s);
-  pair_planes_kernel<MT, C, RES_X, PLAIN><<<grid, NTHREADS, pl.smem, s>>>(m1, m2, p);
+  pair_planes_kernel<MT, C, RES_X, PLAIN, HL><<<grid, NTHREADS, pl.smem, s>>>(m1, m2, p);
   if (dbg_sync & 2) cudaStreamSynchronize(s);
   return cudaGetLastError();
 }
@@ -669,6 +744,9 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
 bool pair_conv_supported(const PairConvArgs& a) {
   if (!a.x || !a.w1 || !a.w2 || !a.bias1 || !a.bias2 || (!a.out16 && !a.out32)) return false;
   if (a.L <= 0 || a.B <= 0 || a.res_inv < 1.f || a.out16_slope > 1.f) return false;
+  if (a.x_lo && a.res32) return false;          // the residual is either hi + lo or the fp32 stream
+  if (a.x_lo && a.C != 32) return false;        // the hi/lo ring loader serves 2 x 4 planes with 8 lanes
+  if (a.out_lo && (!a.out16 || !a.x_lo)) return false;
   PairPlan pl;
   return make_pair_plan(a, &pl);
 }
@@ -681,10 +759,15 @@ int pair_conv_mt(const PairConvArgs& a) {
 cudaError_t launch_pair_planes(const PairConvArgs& a, cudaStream_t s) {
   PairPlan pl;
   if (!pair_conv_supported(a) || !make_pair_plan(a, &pl)) return cudaErrorInvalidValue;
-  const bool plain = !a.res32 && !a.accin16 && !a.accin32 && !a.out32 && a.out16 && a.out_scale == 1.f;
-#define PG_PAIR(MT_, C_)                                                          \
-  return a.res32 ? launch_pair_t<MT_, C_, false, false>(a, pl, s)                 \
-                 : (plain ? launch_pair_t<MT_, C_, true, true>(a, pl, s) : launch_pair_t<MT_, C_, true, false>(a, pl, s))
+  const bool hl = a.x_lo != nullptr;
+  const bool plain = !a.res32 && !a.accin16 && !a.accin32 && !a.out32 && a.out16 && a.out_scale == 1.f &&
+                     (!hl || a.out_lo);
+#define PG_PAIR(MT_, C_)                                                                          \
+  return a.res32 ? launch_pair_t<MT_, C_, false, false, false>(a, pl, s)                          \
+         : hl    ? (plain ? launch_pair_t<MT_, C_, true, true, true>(a, pl, s)                    \
+                          : launch_pair_t<MT_, C_, true, false, true>(a, pl, s))                  \
+                 : (plain ? launch_pair_t<MT_, C_, true, true, false>(a, pl, s)                   \
+                          : launch_pair_t<MT_, C_, true, false, false>(a, pl, s))
   if (a.C == 32) {
     switch (pl.MT) {
       case 4: PG_PAIR(4, 32);

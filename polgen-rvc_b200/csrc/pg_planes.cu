@@ -93,8 +93,9 @@ __global__ void planes_to_nlc_kernel(const TIn* __restrict__ x, TOut* __restrict
 // nsf.py:131  x = x + noise_convs[i](har_source), then the L-form copy the next conv reads
 template <typename T>
 __global__ void __launch_bounds__(256) noise_inject_planes_kernel(
-    T* __restrict__ x, __half* __restrict__ a16, const float* __restrict__ src, const float* __restrict__ wn,
-    const float* __restrict__ bn, int B, int L, int C, int Lsrc, int k, int stride, int pad, float slope) {
+    T* __restrict__ x, __half* __restrict__ a16, __half* __restrict__ lo16, const float* __restrict__ src,
+    const float* __restrict__ wn, const float* __restrict__ bn, int B, int L, int C, int Lsrc, int k, int stride,
+    int pad, float slope) {
   const int CP = C / 8;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * CP * L) return;
@@ -119,10 +120,18 @@ __global__ void __launch_bounds__(256) noise_inject_planes_kernel(
   load8(x + i * 8, v);
 #pragma unroll
   for (int q = 0; q < 8; ++q) v[q] += acc[q];
-  if (sizeof(T) == 4) store8(x + i * 8, v);   // fp32 residual stream keeps the raw value
+  if (sizeof(T) == 4 && !lo16) store8(x + i * 8, v);   // fp32 residual stream keeps the raw value
 #pragma unroll
   for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * slope;
-  store8(a16 + i * 8, v);
+  const uint4 hi = pack8(v);
+  *reinterpret_cast<uint4*>(a16 + i * 8) = hi;
+  if (lo16) {                                           // hi/lo stream: the f16 rounding remainder
+    float hv[8];
+    unpack8(hi, hv);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] -= hv[q];
+    store8(lo16 + i * 8, v);
+  }
 }
 
 
@@ -278,9 +287,9 @@ cudaError_t launch_planes_to_nlc_f16(const __half* x, __half* y, int B, int L, i
   return cudaGetLastError();
 }
 
-cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, const float* src, const float* wn,
-                                       const float* bn, int B, int L, int C, int Lsrc, int k, int stride,
-                                       int pad, float slope, cudaStream_t s) {
+cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, __half* lo16, const float* src,
+                                       const float* wn, const float* bn, int B, int L, int C, int Lsrc, int k,
+                                       int stride, int pad, float slope, cudaStream_t s) {
   if (C % 8) return cudaErrorInvalidValue;
   if (dt == DT_F16 && a16 == x && k >= 8) {   // long-tap stages of the f16 stream: shared-memory tiled kernel
     // (measured: 268 -> 90 us at k = 80; at k = 4 the plain kernel is already HBM-bound and faster)
@@ -296,11 +305,11 @@ cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, const flo
   }
   const size_t n = (size_t)B * (C / 8) * L;
   if (dt == DT_F32)
-    noise_inject_planes_kernel<float><<<blocks_for(n), 256, 0, s>>>(reinterpret_cast<float*>(x), a16, src, wn, bn,
-                                                                   B, L, C, Lsrc, k, stride, pad, slope);
+    noise_inject_planes_kernel<float><<<blocks_for(n), 256, 0, s>>>(reinterpret_cast<float*>(x), a16, lo16, src, wn,
+                                                                   bn, B, L, C, Lsrc, k, stride, pad, slope);
   else
-    noise_inject_planes_kernel<__half><<<blocks_for(n), 256, 0, s>>>(reinterpret_cast<__half*>(x), a16, src, wn,
-                                                                    bn, B, L, C, Lsrc, k, stride, pad, slope);
+    noise_inject_planes_kernel<__half><<<blocks_for(n), 256, 0, s>>>(reinterpret_cast<__half*>(x), a16, nullptr, src,
+                                                                    wn, bn, B, L, C, Lsrc, k, stride, pad, slope);
   return cudaGetLastError();
 }
 

@@ -63,7 +63,11 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+#ifdef PG_NO_WAIT_HINT
+  while (!mbar_try_wait(bar, parity)) {
+#else
   while (!mbar_try_wait_hint(bar, parity, 2000u)) {
+#endif
     if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s: sticky launch failure, never a hang
   }
 }
