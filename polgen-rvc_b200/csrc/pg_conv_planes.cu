@@ -48,7 +48,8 @@ constexpr int LOAD_WARP = 0, TMA_WARP = 1, MMA_WARP = 2, RES_WARP = 3, EPI_WARP0
 constexpr int EPI_GROUPS = EPI_WARPS / 4;   // warps per TMEM lane quarter
 constexpr int EPI_COLS = 16;                // accumulator columns per epilogue item
 // epilogue specialisations: the two shapes that make up 5/6 of the ResBlock convs get straight-line code
-constexpr int EPI_GENERIC = 0, EPI_C1 = 1 /* y16 = lrelu(acc + bias) */, EPI_C2 = 2 /* y16 = lrelu(acc + bias + raw(res16)) */;
+constexpr int EPI_GENERIC = 0, EPI_C1 = 1 /* y16 = lrelu(acc + bias) */, EPI_C2 = 2 /* y16 = lrelu(acc + bias + raw(res16)) */,
+              EPI_C3 = 3 /* last conv2 of a ResBlock: y16 = lrelu((acc + bias + raw(res16)) * scale [+ accin16]) */;
 constexpr int NTHREADS = (EPI_WARP0 + EPI_WARPS) * 32;
 constexpr int GROUP_PLANES = 16;   // 128 channels per activation-ring slot
 
@@ -477,7 +478,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
     const int quarter = warp & 3, grp = (warp - EPI_WARP0) >> 2;
     const int n_cb = p.NT / EPI_COLS, items = MT * n_cb, cb_shift = 31 - __clz(n_cb);
     const int CP = p.Cout_real / 8;
-    const float slope = p.out16_slope, rinv = p.res_inv;
+    const float slope = p.out16_slope, rinv = p.res_inv, scale = p.out_scale;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int rrow16 = (quarter * 32 + lane) * 16;
     uint32_t t_cnt = 0;
@@ -487,6 +488,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       const int qbase = rt * (BM * MT) + quarter * 32 + lane;
       const uint32_t accb = t_cnt & 1u;
       uint4* out_b = reinterpret_cast<uint4*>(p.out16) + (size_t)b * CP * p.L;
+      const uint4* acc_b = reinterpret_cast<const uint4*>(p.accin16) + (size_t)b * CP * p.L;
       mbar_wait(&acc_full[accb], (t_cnt >> 1) & 1u);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -494,6 +496,12 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         const int m = it >> cb_shift, cb = it & (n_cb - 1);
         const int q = qbase + m * BM;
         const int c0 = cb * EPI_COLS;
+        uint4 ain[2];
+        if (EPI == EPI_C3 && p.accin16 && q < p.L) {      // running mean: issued first, used last
+          const uint4* g = acc_b + (size_t)(c0 >> 3) * p.L + q;
+          ain[0] = g[0];
+          ain[1] = g[p.L];
+        }
         float bv[EPI_COLS];
 #pragma unroll
         for (int i = 0; i < EPI_COLS / 4; ++i) {
@@ -502,7 +510,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         }
         uint4 rcur[2];
         int ring_slot = 0;
-        if (EPI == EPI_C2) {
+        if (EPI == EPI_C2 || EPI == EPI_C3) {
           const uint32_t sidx = (t_cnt * (uint32_t)MT + (uint32_t)m) * (uint32_t)(p.NT / p.res_cols) + (uint32_t)(c0 / p.res_cols);
           const uint32_t slot = sidx % (uint32_t)p.r_slots;
           mbar_wait(&r_full[slot], (sidx / (uint32_t)p.r_slots) & 1u);
@@ -513,7 +521,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         }
         uint32_t acc[EPI_COLS];
         tmem_ld16(lane_taddr + accb * (uint32_t)(MT * p.NT) + (uint32_t)(m * p.NT + c0), acc);
-        if (EPI == EPI_C2) {   // release the slot only after the loads have landed (see mbar_arrive_dep)
+        if (EPI == EPI_C2 || EPI == EPI_C3) {   // release the slot only after the loads have landed (see mbar_arrive_dep)
           uint32_t dep = rcur[0].x ^ rcur[0].w ^ rcur[1].x ^ rcur[1].w;
           asm volatile("" : "+r"(dep));
           __syncwarp();
@@ -526,11 +534,21 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[j * 8 + i]) + bv[j * 8 + i];
-            if (EPI == EPI_C2) {
+            if (EPI == EPI_C2 || EPI == EPI_C3) {
               float rr[8];
               unpack8(rcur[j], rr);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] += fminf(rr[i], rr[i] * rinv);
+            }
+            if (EPI == EPI_C3) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= scale;
+              if (p.accin16) {
+                float av[8];
+                unpack8(ain[j], av);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += av[i];
+              }
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * slope);
@@ -874,20 +892,23 @@ cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s) {
   static const bool dbg = env_int("PG_PLANES_DEBUG", 0) != 0;
   // straight-line epilogues for the plain ResBlock shapes
   int epi = EPI_GENERIC;
-  if (!dbg && pl.bias_smem && a.N == pl.NT && a.row_mul == 1 && !a.bbias && !a.res32 && !a.accin16 && !a.accin32 &&
-      !a.out32 && a.out16 && a.out_scale == 1.f && a.out16_slope <= 1.f && a.res_inv >= 1.f)
-    epi = a.res16 ? EPI_C2 : EPI_C1;
+  if (!dbg && pl.bias_smem && a.N == pl.NT && a.row_mul == 1 && !a.bbias && !a.res32 && !a.accin32 &&
+      !a.out32 && a.out16 && a.out16_slope <= 1.f && a.res_inv >= 1.f) {
+    if (!a.accin16 && a.out_scale == 1.f) epi = a.res16 ? EPI_C2 : EPI_C1;
+    else if (a.res16) epi = EPI_C3;
+  }
   // operand-swapped variant for the C = 128 ResBlock convs: +13 % on the conv1 shapes (1190 -> 1345 TFLOP/s at
   // k = 11, profiles/r02b), neutral on conv2 -- on by default, PG_FLAG_NO_PLANES_SWAP / PG_PLANES_SWAP=0 is the twin
   static const bool swap_on = env_int("PG_PLANES_SWAP", 1) != 0;
-  if (swap_on && a.swap && epi != EPI_GENERIC && pl.MT == 2 && pl.NT == 128 && pl.KC == 64 && pl.res_cols == 64 &&
+  if (swap_on && a.swap && (epi == EPI_C1 || epi == EPI_C2) && pl.MT == 2 && pl.NT == 128 && pl.KC == 64 && pl.res_cols == 64 &&
       a.Cout_real == 128)
     return epi == EPI_C1 ? launch_t<2, 4, EPI_C1, false, true>(a, pl, s) : launch_t<2, 4, EPI_C2, false, true>(a, pl, s);
 #define PG_DISPATCH(MT_, KC16_)                                                        \
   return dbg ? launch_t<MT_, KC16_, EPI_GENERIC, true>(a, pl, s)                       \
              : (epi == EPI_C1 ? launch_t<MT_, KC16_, EPI_C1, false>(a, pl, s)          \
                               : (epi == EPI_C2 ? launch_t<MT_, KC16_, EPI_C2, false>(a, pl, s) \
-                                               : launch_t<MT_, KC16_, EPI_GENERIC, false>(a, pl, s)))
+                              : (epi == EPI_C3 ? launch_t<MT_, KC16_, EPI_C3, false>(a, pl, s) \
+                                               : launch_t<MT_, KC16_, EPI_GENERIC, false>(a, pl, s))))
   if (pl.KC == 64) {
     switch (pl.MT) {
       case 1: PG_DISPATCH(1, 4);

@@ -87,7 +87,9 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 // HL (with RES_X): the stream is carried as TWO f16 planes, x = hi + lo (hi is the conv operand, lo its rounding
 // remainder: 2^-22 relative, fp32-class), so the last decoder stage keeps its residual stream at full precision
 // without a separate fp32 copy -- 256 instead of 384 bytes per sample and pair.
-template <int MT, int C, bool RES_X, bool PLAIN, bool HL>
+// EPIM selects the E2 code: 0 generic (every run-time option), 1 plain pair, 2 last pair of a ResBlock (scaled by
+// 1/n_kernels; fp32 mean planes out for HL, f16 out otherwise), 3 the same plus the running mean as accumulate input
+template <int MT, int C, bool RES_X, int EPIM, bool HL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_constant__ CUtensorMap wmap2,
                    const PairParams p) {
@@ -348,8 +350,10 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
       }
       ++j;
     }
-  } else if (warp >= E2_WARP0 && PLAIN) {
-    // ===== E2, straight-line form: y16 = lrelu(acc2 + bias2 + raw(x), slope) =====
+  } else if (warp >= E2_WARP0 && EPIM > 0) {
+    // ===== E2, straight-line forms: v = (acc2 + bias2 + raw(x)) [* scale + accin]; y16 = lrelu(v, slope) / y32 = v =====
+    constexpr bool LASTP = EPIM >= 2, ACC = EPIM == 3, OUT32 = LASTP && HL;
+    const float scale = p.out_scale;
     const int quarter = warp & 3, grp = (warp - E2_WARP0) >> 2;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc2_col;
     const float* bias2 = bias_s + C;
@@ -366,6 +370,30 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
       const uint4* xin = reinterpret_cast<const uint4*>(p.x) + plane_base;
       uint4* yout = reinterpret_cast<uint4*>(p.out16) + plane_base;
       uint4* lout = reinterpret_cast<uint4*>(p.out_lo) + plane_base;
+      uint4 apre[ACC ? (HL ? 4 : 2) * IPW : 1];
+      if (ACC) {      // running mean of the earlier ResBlocks: fetched before waiting for the accumulator
+#pragma unroll
+        for (int ii = 0; ii < IPW; ++ii) {
+          const int it = grp + ii * (E2_WARPS / 4);
+          const int m = it / NCB, cb = it - m * NCB;
+          const int o = m * BM + quarter * 32 + lane;
+          const int t = o0 + o;
+          if (o < MO && t < L) {
+            const size_t off = plane_base + (size_t)(cb * 2) * L + t;
+            if (HL) {
+              const uint4* g = reinterpret_cast<const uint4*>(p.accin32) + off * 2;
+              apre[4 * ii] = g[0];
+              apre[4 * ii + 1] = g[1];
+              apre[4 * ii + 2] = g[2 * (size_t)L];
+              apre[4 * ii + 3] = g[2 * (size_t)L + 1];
+            } else {
+              const uint4* g = reinterpret_cast<const uint4*>(p.accin16) + off;
+              apre[2 * ii] = g[0];
+              apre[2 * ii + 1] = g[L];
+            }
+          }
+        }
+      }
       uint4 rpre[HL ? 1 : 2 * IPW];
       if (!HL) {
 #pragma unroll
@@ -423,10 +451,33 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
             const float4 b1 = *reinterpret_cast<const float4*>(bias2 + cb * ECOLS + jj * 8 + 4);
             const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float a = __uint_as_float(acc[jj * 8 + i]) + bv[i] + fminf(rr[i], rr[i] * rinv);
-              v[i] = fmaxf(a, a * slope);
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[jj * 8 + i]) + bv[i] + fminf(rr[i], rr[i] * rinv);
+            if (LASTP) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= scale;
             }
+            if (ACC) {
+              if (HL) {
+                const uint4 q0 = apre[4 * ii + 2 * jj], q1 = apre[4 * ii + 2 * jj + 1];
+                v[0] += __uint_as_float(q0.x); v[1] += __uint_as_float(q0.y);
+                v[2] += __uint_as_float(q0.z); v[3] += __uint_as_float(q0.w);
+                v[4] += __uint_as_float(q1.x); v[5] += __uint_as_float(q1.y);
+                v[6] += __uint_as_float(q1.z); v[7] += __uint_as_float(q1.w);
+              } else {
+                float av[8];
+                unpack8(apre[2 * ii + jj], av);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += av[i];
+              }
+            }
+            if (OUT32) {      // the 1/3-mean that feeds conv_post stays fp32
+              float4* o4 = reinterpret_cast<float4*>(p.out32) + (plane_base + (size_t)(cb * 2 + jj) * L + t) * 2;
+              o4[0] = make_float4(v[0], v[1], v[2], v[3]);
+              o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+              continue;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * slope);
             const uint4 hi = pack8(v);
             dst[(size_t)jj * L] = hi;
             if (HL) {     // remainder of the f16 rounding, itself in f16
@@ -700,7 +751,7 @@ bool make_pair_plan(const PairConvArgs& a, PairPlan* out) {
   return false;
 }
 
-template <int MT, int C, bool RES_X, bool PLAIN, bool HL>
+template <int MT, int C, bool RES_X, int EPIM, bool HL>
 cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_t s) {
   CUtensorMap m1, m2;
   const int kc = C == 64 ? 64 : 32;
@@ -729,12 +780,12 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
   p.no_ring = no_ring;
 
   static DeviceOnce once;
-  if (cudaError_t e = ensure_dyn_smem(pair_planes_kernel<MT, C, RES_X, PLAIN, HL>, once, 227 * 1024)) return e;
+  if (cudaError_t e = ensure_dyn_smem(pair_planes_kernel<MT, C, RES_X, EPIM, HL>, once, 227 * 1024)) return e;
   int grid = device_sm_count();
   if (grid > p.total_tiles) grid = p.total_tiles;
   static const int dbg_sync = [] { const char* e = getenv("PG_PAIR_SYNC"); return e ? atoi(e) : 0; }();
   if (dbg_sync & 1) cudaStreamSynchronize(s);
-  pair_planes_kernel<MT, C, RES_X, PLAIN, HL><<<grid, NTHREADS, pl.smem, s>>>(m1, m2, p);
+  pair_planes_kernel<MT, C, RES_X, EPIM, HL><<<grid, NTHREADS, pl.smem, s>>>(m1, m2, p);
   if (dbg_sync & 2) cudaStreamSynchronize(s);
   return cudaGetLastError();
 }
@@ -760,14 +811,32 @@ cudaError_t launch_pair_planes(const PairConvArgs& a, cudaStream_t s) {
   PairPlan pl;
   if (!pair_conv_supported(a) || !make_pair_plan(a, &pl)) return cudaErrorInvalidValue;
   const bool hl = a.x_lo != nullptr;
-  const bool plain = !a.res32 && !a.accin16 && !a.accin32 && !a.out32 && a.out16 && a.out_scale == 1.f &&
-                     (!hl || a.out_lo);
-#define PG_PAIR(MT_, C_)                                                                          \
-  return a.res32 ? launch_pair_t<MT_, C_, false, false, false>(a, pl, s)                          \
-         : hl    ? (plain ? launch_pair_t<MT_, C_, true, true, true>(a, pl, s)                    \
-                          : launch_pair_t<MT_, C_, true, false, true>(a, pl, s))                  \
-                 : (plain ? launch_pair_t<MT_, C_, true, true, false>(a, pl, s)                   \
-                          : launch_pair_t<MT_, C_, true, false, false>(a, pl, s))
+  // straight-line E2 forms (see EPIM): 1 plain pair, 2 / 3 last pair of a ResBlock without / with the running mean
+  int epim = 0;
+  if (!a.res32) {
+    if (hl) {
+      if (!a.accin16 && !a.accin32 && !a.out32 && a.out16 && a.out_lo && a.out_scale == 1.f) epim = 1;
+      else if (a.out32 && !a.out16 && !a.accin16) epim = a.accin32 ? 3 : 2;
+    } else {
+      if (!a.accin16 && !a.accin32 && !a.out32 && a.out16 && a.out_scale == 1.f) epim = 1;
+      else if (a.out16 && !a.out32 && !a.accin32) epim = a.accin16 ? 3 : 2;
+    }
+  }
+  static const int no_epim = [] { const char* e = getenv("PG_PAIR_GENERIC_E2"); return e ? atoi(e) : 0; }();
+  if (no_epim) epim = 0;
+#define PG_PAIR_E(MT_, C_, HL_)                                                      \
+  switch (epim) {                                                                   \
+    case 1: return launch_pair_t<MT_, C_, true, 1, HL_>(a, pl, s);                   \
+    case 2: return launch_pair_t<MT_, C_, true, 2, HL_>(a, pl, s);                   \
+    case 3: return launch_pair_t<MT_, C_, true, 3, HL_>(a, pl, s);                   \
+    default: return launch_pair_t<MT_, C_, true, 0, HL_>(a, pl, s);                  \
+  }
+#define PG_PAIR(MT_, C_)                                                             \
+  do {                                                                              \
+    if (a.res32) return launch_pair_t<MT_, C_, false, 0, false>(a, pl, s);           \
+    if (hl) { PG_PAIR_E(MT_, C_, true) }                                             \
+    PG_PAIR_E(MT_, C_, false)                                                        \
+  } while (0)
   if (a.C == 32) {
     switch (pl.MT) {
       case 4: PG_PAIR(4, 32);
@@ -781,6 +850,7 @@ cudaError_t launch_pair_planes(const PairConvArgs& a, cudaStream_t s) {
     }
   }
 #undef PG_PAIR
+#undef PG_PAIR_E
   return cudaErrorInvalidValue;
 }
 
