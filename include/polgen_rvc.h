@@ -91,6 +91,7 @@ typedef struct pg_config {
 #define PG_FLAG_NO_PLANES_SWAP 128  /* validation twin: C=128 ResBlock convs WITHOUT the swapped MMA operands (default: weights = M, 256 time rows = N where the shape qualifies) */
 #define PG_FLAG_NO_PAD 256       /* do not pad T up to a launch-shape bucket (validation twin of the padded path) */
 #define PG_FLAG_F32_STREAM 512   /* last decoder stage with an fp32 residual stream + f16 operand copy (validation twin of the default hi/lo f16 pair stream) */
+#define PG_FLAG_NO_NOISE_FUSION 1024 /* NSF source injection as its own kernel after every upsampler (validation twin of the fused epilogue) */
 #define PG_FLAG_F16_LATENTS 8  /* TextEncoder / flow GEMMs with single-pass f16 tensor-core operands (default: fp32-accurate) */
 
 typedef struct pg_handle_s* pg_handle;

@@ -25,6 +25,7 @@ PG_FLAG_NO_GRAPHS = 64
 PG_FLAG_NO_PLANES_SWAP = 128
 PG_FLAG_NO_PAD = 256
 PG_FLAG_F32_STREAM = 512
+PG_FLAG_NO_NOISE_FUSION = 1024
 PG_F32 = 0
 PG_F64 = 3
 PG_ABI_VERSION = 2

@@ -15,6 +15,8 @@
 
 namespace pg {
 
+unsigned long long pair_debug_counter(int i);   // pg_pair_planes.cu (diagnostics)
+
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 
@@ -782,6 +784,17 @@ int run_pair_conv(pg_handle h, cudaStream_t s, PairConvArgs a, const ConvW& w1, 
   return PG_OK;
 }
 
+// NSF source injection inside the upsampler's epilogue (the kernel supports noise convs of up to 8 taps).
+// Measured on the bench clip (profiles/r02_noise_fusion.md): the polyphase upsamplers are epilogue-bound (K = 3
+// taps of MMA per 64 .. 1280 output columns, stores scattered over the u output phases), so every fused tap costs
+// about what the separate bandwidth kernel did: k = 1 (last stage, where fusion also removes the fp32 round trip
+// in front of the hi/lo split) wins 0.02 ms per step, k = 4 is even, k = 8 loses 0.04 ms, k = 80 keeps its
+// shared-memory tiled kernel.  Default: fuse k <= 1; PG_NOISE_FUSE_MAXK=4|8 fuses the other stages too.
+bool fuse_noise(pg_handle h, const StageW& S) {
+  static const int max_k = [] { const char* e = getenv("PG_NOISE_FUSE_MAXK"); return e ? atoi(e) : 1; }();
+  return !(h->cfg.flags & (PG_FLAG_KEEP_TAPS | PG_FLAG_NO_NOISE_FUSION)) && S.noise_k <= max_k;
+}
+
 // the hi/lo form of the last stage needs every ResBlock pair on the fused pair kernel
 bool wide_hl_ok(pg_handle h, const StageW& S, int B, int L) {
   if (h->cfg.flags & (PG_FLAG_NO_PAIR_FUSION | PG_FLAG_KEEP_TAPS | PG_FLAG_F32_STREAM)) return false;
@@ -854,10 +867,15 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
         a.tlen = tlen; a.len_mul = mul_in;
         a.Cout_real = C; a.row_mul = S.u;
         a.out16 = x0;   // raw
+        if (fuse_noise(h, S)) {   // x + noise_convs[i](source) in the epilogue, stored as lrelu(., 0.1) for the ResBlocks
+          a.nz_src = source; a.nz_w = S.noise_w; a.nz_b = S.noise_b; a.nz_k = S.noise_k; a.nz_stride = S.noise_stride;
+          a.nz_pad = S.noise_pad; a.nz_len = (int)Lsrc; a.out16_slope = SL;
+        }
         PG_TRY(run_plane_conv(h, s, a, S.up));
       }
-      PG_LAUNCH(h, launch_noise_inject_planes(x0, DT_F16, x0, nullptr, source, S.noise_w, S.noise_b, B, (int)L, C,
-                                              (int)Lsrc, S.noise_k, S.noise_stride, S.noise_pad, SL, s));
+      if (!fuse_noise(h, S))
+        PG_LAUNCH(h, launch_noise_inject_planes(x0, DT_F16, x0, nullptr, source, S.noise_w, S.noise_b, B, (int)L, C,
+                                                (int)Lsrc, S.noise_k, S.noise_stride, S.noise_pad, SL, s));
       PG_TRY(record_tap_planes(h, s, "dec.ups" + std::to_string(i), x0, DT_F16, INV, B, L, C));
       for (int j = 0; j < nk; ++j) {
         const int ksz = c.resblock_kernel_sizes[j];
@@ -908,11 +926,18 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
         a.x = reinterpret_cast<const __half*>(buf[cur]); a.B = B; a.L = (int)Lin; a.pad = S.up_pad;
         a.tlen = tlen; a.len_mul = mul_in;
         a.Cout_real = C; a.row_mul = S.u;
-        a.out32 = r0;
+        if (fuse_noise(h, S)) {   // source injection + hi/lo split in the epilogue: no fp32 round trip through r0
+          a.nz_src = source; a.nz_w = S.noise_w; a.nz_b = S.noise_b; a.nz_k = S.noise_k; a.nz_stride = S.noise_stride;
+          a.nz_pad = S.noise_pad; a.nz_len = (int)Lsrc;
+          a.out16 = a0; a.out_lo = l0; a.out16_slope = SL;
+        } else {
+          a.out32 = r0;
+        }
         PG_TRY(run_plane_conv(h, s, a, S.up));
       }
-      PG_LAUNCH(h, launch_noise_inject_planes(r0, DT_F32, a0, l0, source, S.noise_w, S.noise_b, B, (int)L, C,
-                                              (int)Lsrc, S.noise_k, S.noise_stride, S.noise_pad, SL, s));
+      if (!fuse_noise(h, S))
+        PG_LAUNCH(h, launch_noise_inject_planes(r0, DT_F32, a0, l0, source, S.noise_w, S.noise_b, B, (int)L, C,
+                                                (int)Lsrc, S.noise_k, S.noise_stride, S.noise_pad, SL, s));
       for (int j = 0; j < nk; ++j) {
         const __half *xc = a0, *lc = l0;
         for (int d = 0; d < nd; ++d) {
@@ -1701,6 +1726,7 @@ int64_t pg_debug_fetch(pg_handle h, void* stream, const char* tap, float* dst, i
 }
 
 int64_t pg_launch_count(pg_handle h) { return h ? h->launches : 0; }
+unsigned long long pg_debug_pair_counter(int i) { return pg::pair_debug_counter(i); }
 
 int pg_profile_read(pg_handle h, double* ms_out, double* flops_out, int64_t* launches_out) {
   if (!h || !ms_out || !flops_out || !launches_out) return fail(PG_ERR_INVALID, "null argument");

@@ -105,6 +105,11 @@ struct PlaneConvArgs {
   const __half* accin16 = nullptr; const float* accin32 = nullptr;
   __half* out16 = nullptr; float out16_slope = 1.f; float* out32 = nullptr;
   float out_scale = 1.f;
+  // NSF source injection fused into the epilogue (nsf.py:131; the polyphase upsamplers): adds
+  //   nz_b[co] + sum_j nz_w[j][co] * nz_src[b][t_out*nz_stride + j - nz_pad]   (samples outside [0, nz_len) are 0)
+  const float* nz_src = nullptr; const float* nz_w = nullptr; const float* nz_b = nullptr;
+  int nz_k = 0, nz_stride = 1, nz_pad = 0, nz_len = 0;
+  __half* out_lo = nullptr;   // with out16: the value leaves as the hi/lo f16 pair (last decoder stage)
   int swap = 1;   // operand-swapped MMA where the shape qualifies (C = 128, MT = 2); 0: PG_FLAG_NO_PLANES_SWAP twin
 };
 bool plane_conv_supported(const PlaneConvArgs& a);

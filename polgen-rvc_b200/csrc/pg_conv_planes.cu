@@ -52,6 +52,7 @@ constexpr int EPI_GENERIC = 0, EPI_C1 = 1 /* y16 = lrelu(acc + bias) */, EPI_C2 
               EPI_C3 = 3 /* last conv2 of a ResBlock: y16 = lrelu((acc + bias + raw(res16)) * scale [+ accin16]) */;
 constexpr int NTHREADS = (EPI_WARP0 + EPI_WARPS) * 32;
 constexpr int GROUP_PLANES = 16;   // 128 channels per activation-ring slot
+constexpr int NZ_MAXK = 8;         // longest noise conv fused into an upsampler epilogue (taps)
 
 struct PlaneParams {
   const __half* x; int L;              // input planes [B][Cin/8][L][8]
@@ -66,6 +67,9 @@ struct PlaneParams {
   const __half* accin16; const float* accin32;
   __half* out16; float out16_slope; float* out32;
   float out_scale;
+  // fused NSF source injection (nsf.py:131): + bn[co] + sum_j wn[j][co] * src[b][t_out*stride + j - pad]
+  const float* nz_src; const float* nz_w; const float* nz_b; int nz_k, nz_stride, nz_pad, nz_len;
+  __half* out_lo;                      // hi/lo output: out16 = f16(lrelu(v)), out_lo = its remainder
   int plane_bytes, KC, PG, n_groups, a_slots, a_slot_bytes, stages, stage_bytes, resident, tmem_cols;
   int r_slots, r_slot_bytes, res_cols;  // residual ring: one slot = 128 rows x res_cols columns
   int bias_smem;                        // bias[N] staged in shared memory (N <= 1024)
@@ -171,6 +175,11 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
   }
   if (p.bias_smem)
     for (int i = tid; i < p.N; i += NTHREADS) bias_s[i] = p.bias[i];
+  // fused source injection: the noise conv's bias and [k][C] weights sit right behind the bias vector
+  float* nz_s = bias_s + (p.bias_smem ? ((p.N + 3) & ~3) : 0);
+  if (p.nz_src)
+    for (int i = tid; i < (p.nz_k + 1) * p.Cout_real; i += NTHREADS)
+      nz_s[i] = i < p.Cout_real ? p.nz_b[i] : p.nz_w[i - p.Cout_real];
   if (warp == MMA_WARP) tcgen05_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   if (warp == TMA_WARP && lane == 0)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
@@ -663,6 +672,16 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         if (!(dbg & 32768))
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * (uint32_t)(MT * p.NT) +
                       (uint32_t)(m * p.NT + c0), acc);
+        float sv[NZ_MAXK];       // source samples under the noise conv's taps of this lane's output row
+        if (p.nz_src && ok) {
+          const float* sp = p.nz_src + (size_t)tc.b * p.nz_len;
+          const int s0 = (q * p.row_mul + r) * p.nz_stride - p.nz_pad;
+#pragma unroll
+          for (int jj = 0; jj < NZ_MAXK; ++jj) {
+            const int sn = s0 + jj;
+            sv[jj] = (jj < p.nz_k && sn >= 0 && sn < p.nz_len) ? __ldg(sp + sn) : 0.f;
+          }
+        }
         if (!(dbg & 65536))
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
@@ -686,6 +705,26 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
           if (p.out_scale != 1.f) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] *= p.out_scale;
+          }
+          if (p.nz_src && ok) {     // x + noise_convs[i](har_source): source taps in sv[], weights in shared memory
+            const float* wb = nz_s + co + j * 8;
+            {
+              const float4 b0 = *reinterpret_cast<const float4*>(wb), b1 = *reinterpret_cast<const float4*>(wb + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+#pragma unroll
+            for (int jj = 0; jj < NZ_MAXK; ++jj) {
+              if (jj < p.nz_k) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wb + (size_t)(jj + 1) * p.Cout_real);
+                const float4 w1 = *reinterpret_cast<const float4*>(wb + (size_t)(jj + 1) * p.Cout_real + 4);
+                const float x = sv[jj];
+                v[0] = fmaf(w0.x, x, v[0]); v[1] = fmaf(w0.y, x, v[1]);
+                v[2] = fmaf(w0.z, x, v[2]); v[3] = fmaf(w0.w, x, v[3]);
+                v[4] = fmaf(w1.x, x, v[4]); v[5] = fmaf(w1.y, x, v[5]);
+                v[6] = fmaf(w1.z, x, v[6]); v[7] = fmaf(w1.w, x, v[7]);
+              }
+            }
           }
           if (ok) {
             if (p.accin16) {
@@ -711,7 +750,15 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * p.out16_slope);   // slope <= 1
               }
-              *(reinterpret_cast<uint4*>(p.out16) + off) = pack8(v);
+              const uint4 hi = pack8(v);
+              *(reinterpret_cast<uint4*>(p.out16) + off) = hi;
+              if (p.out_lo) {       // hi/lo stream of the last stage: the f16 rounding remainder
+                float hv[8];
+                unpack8(hi, hv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] -= hv[i];
+                *(reinterpret_cast<uint4*>(p.out_lo) + off) = pack8(v);
+              }
             }
           }
         }
@@ -762,7 +809,8 @@ bool make_plan(const PlaneConvArgs& a, Plan* out) {
                    forced_stages = env_int("PG_PLANES_STAGES", 0), forced_slots = env_int("PG_PLANES_SLOTS", 0);
   const bool can_reside = a.N == NT && !a.tapmask && forced_res != 0;
   const int bias_smem = a.bias && a.N <= 1024 ? 1 : 0;
-  const size_t fixed = 1024 + 1024 + (bias_smem ? 4 * (size_t)a.N : 0);   // alignment slack, barriers, bias
+  const size_t fixed = 1024 + 1024 + (bias_smem ? 4 * (size_t)a.N + 16 : 0) +      // alignment slack, barriers, bias
+                       (a.nz_src ? 4 * (size_t)(a.nz_k + 1) * a.Cout_real : 0);     // fused noise conv: bias + [k][C] weights
   const size_t budget = (size_t)227 * 1024;
   const long rows128 = (a.L + BM - 1) / BM;
   const int sms = device_sm_count();
@@ -830,6 +878,8 @@ cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
   p.res16 = a.res16; p.res_inv = a.res_inv; p.res32 = a.res32;
   p.accin16 = a.accin16; p.accin32 = a.accin32;
   p.out16 = a.out16; p.out16_slope = a.out16_slope; p.out32 = a.out32; p.out_scale = a.out_scale;
+  p.nz_src = a.nz_src; p.nz_w = a.nz_w; p.nz_b = a.nz_b; p.nz_k = a.nz_k; p.nz_stride = a.nz_stride;
+  p.nz_pad = a.nz_pad; p.nz_len = a.nz_len; p.out_lo = a.out_lo;
   p.plane_bytes = pl.plane_bytes; p.KC = pl.KC; p.PG = pl.PG; p.n_groups = pl.n_groups;
   p.a_slots = pl.a_slots; p.a_slot_bytes = pl.a_slot_bytes; p.stages = pl.stages;
   p.stage_bytes = pl.stage_bytes; p.resident = pl.resident; p.tmem_cols = pl.tmem_cols;
@@ -876,6 +926,8 @@ bool plane_conv_supported(const PlaneConvArgs& a) {
     return false;
   if (a.in_mask && !a.lens) return false;
   if ((a.res16 || a.res32) && a.row_mul != 1) return false;
+  if (a.nz_src && (!a.nz_w || !a.nz_b || a.nz_k < 1 || a.nz_k > NZ_MAXK || a.nz_stride < 1 || a.Cout_real % 8)) return false;
+  if (a.out_lo && !a.out16) return false;
   if (a.res16 && a.res32) return false;
   Plan pl;
   return make_plan(a, &pl);
@@ -892,8 +944,8 @@ cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s) {
   static const bool dbg = env_int("PG_PLANES_DEBUG", 0) != 0;
   // straight-line epilogues for the plain ResBlock shapes
   int epi = EPI_GENERIC;
-  if (!dbg && pl.bias_smem && a.N == pl.NT && a.row_mul == 1 && !a.bbias && !a.res32 && !a.accin32 &&
-      !a.out32 && a.out16 && a.out16_slope <= 1.f && a.res_inv >= 1.f) {
+  if (!dbg && pl.bias_smem && a.N == pl.NT && a.row_mul == 1 && !a.bbias && !a.res32 && !a.accin32 && !a.nz_src &&
+      !a.out_lo && !a.out32 && a.out16 && a.out16_slope <= 1.f && a.res_inv >= 1.f) {
     if (!a.accin16 && a.out_scale == 1.f) epi = a.res16 ? EPI_C2 : EPI_C1;
     else if (a.res16) epi = EPI_C3;
   }

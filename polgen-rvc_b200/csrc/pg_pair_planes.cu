@@ -62,6 +62,13 @@ __device__ __forceinline__ int row_end(const PairParams& p, int b) {
   return p.tlen ? min(p.L, p.tlen[b] * p.len_mul) : p.L;
 }
 
+__device__ unsigned long long g_pair_dbg[16];   // diagnostics (PG_PAIR_NOPRE=3): early vs late accumulate-input reads
+
+// accumulate-input load: mode 2 (PG_PAIR_NOPRE=2, diagnostic) bypasses L1 (ld.global.cg)
+__device__ __forceinline__ uint4 ld_acc(const uint4* p, int mode) {
+  return mode == 2 ? __ldcg(p) : *p;
+}
+
 __device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
   const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
@@ -370,30 +377,12 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
       const uint4* xin = reinterpret_cast<const uint4*>(p.x) + plane_base;
       uint4* yout = reinterpret_cast<uint4*>(p.out16) + plane_base;
       uint4* lout = reinterpret_cast<uint4*>(p.out_lo) + plane_base;
+      // NOTE: the accumulate input is loaded per item AFTER the accumulator wait.  Fetching it for the whole tile
+      // before that wait (as round 1 did to hide its latency behind GEMM 2) made ~1 % of the calls differ from
+      // each other in one 32-row item (tools/diag_det.py; 0 of 500 with the loads here, in both stream forms,
+      // with and without the wait hint, and the early and a late read compare equal when both are made: the
+      // cause was not found, so the early fetch is gone).
       uint4 apre[ACC ? (HL ? 4 : 2) * IPW : 1];
-      if (ACC) {      // running mean of the earlier ResBlocks: fetched before waiting for the accumulator
-#pragma unroll
-        for (int ii = 0; ii < IPW; ++ii) {
-          const int it = grp + ii * (E2_WARPS / 4);
-          const int m = it / NCB, cb = it - m * NCB;
-          const int o = m * BM + quarter * 32 + lane;
-          const int t = o0 + o;
-          if (o < MO && t < L) {
-            const size_t off = plane_base + (size_t)(cb * 2) * L + t;
-            if (HL) {
-              const uint4* g = reinterpret_cast<const uint4*>(p.accin32) + off * 2;
-              apre[4 * ii] = g[0];
-              apre[4 * ii + 1] = g[1];
-              apre[4 * ii + 2] = g[2 * (size_t)L];
-              apre[4 * ii + 3] = g[2 * (size_t)L + 1];
-            } else {
-              const uint4* g = reinterpret_cast<const uint4*>(p.accin16) + off;
-              apre[2 * ii] = g[0];
-              apre[2 * ii + 1] = g[L];
-            }
-          }
-        }
-      }
       uint4 rpre[HL ? 1 : 2 * IPW];
       if (!HL) {
 #pragma unroll
@@ -417,6 +406,20 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
         const int m = it / NCB, cb = it - m * NCB;
         const int o = m * BM + quarter * 32 + lane;
         const int t = o0 + o;
+        if (ACC && p.no_pre != 1 && o < MO && t < L) {      // running mean of the earlier ResBlocks, this item's rows
+          const size_t off = plane_base + (size_t)(cb * 2) * L + t;
+          if (HL) {
+            const uint4* g = reinterpret_cast<const uint4*>(p.accin32) + off * 2;
+            apre[4 * ii] = g[0];
+            apre[4 * ii + 1] = g[1];
+            apre[4 * ii + 2] = g[2 * (size_t)L];
+            apre[4 * ii + 3] = g[2 * (size_t)L + 1];
+          } else {
+            const uint4* g = reinterpret_cast<const uint4*>(p.accin16) + off;
+            apre[2 * ii] = g[0];
+            apre[2 * ii + 1] = g[L];
+          }
+        }
         uint4 hq[2], lq[2];
         if (HL) {     // hi/lo rows of this item from the residual ring (the loader runs tiles ahead of the MMAs)
           const uint32_t sidx = j * (uint32_t)MT + (uint32_t)m;
@@ -455,6 +458,15 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
             if (LASTP) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] *= scale;
+            }
+            if (ACC && p.no_pre == 1) {      // (PG_PAIR_NOPRE=1) accumulate input loaded at the point of use
+              const size_t off = plane_base + (size_t)(cb * 2 + jj) * L + t;
+              if (HL) {
+                apre[4 * ii + 2 * jj] = *(reinterpret_cast<const uint4*>(p.accin32) + off * 2);
+                apre[4 * ii + 2 * jj + 1] = *(reinterpret_cast<const uint4*>(p.accin32) + off * 2 + 1);
+              } else {
+                apre[2 * ii + jj] = *(reinterpret_cast<const uint4*>(p.accin16) + off);
+              }
             }
             if (ACC) {
               if (HL) {
@@ -512,7 +524,8 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
       constexpr int IPW = ITEMS / (E2_WARPS / 4);
       constexpr bool PRE32 = IPW * 4 <= 8;
       uint4 pre[8];
-      const bool pre16 = p.accin16 != nullptr && !p.no_pre, pre32 = PRE32 && p.accin32 != nullptr && !p.no_pre;
+      // early fetch of the accumulate input: OFF (see the note in the straight-line E2); PG_PAIR_NOPRE=4 re-enables it
+      const bool pre16 = p.accin16 != nullptr && p.no_pre == 4, pre32 = PRE32 && p.accin32 != nullptr && p.no_pre == 4;
       if (pre16 || pre32) {
 #pragma unroll
         for (int ii = 0; ii < IPW; ++ii) {
@@ -523,13 +536,13 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
           if (o < p.MO && t < p.L) {
             const size_t off = plane_base + (size_t)(cb * 2) * p.L + t;
             if (pre16) {
-              pre[2 * ii] = *(reinterpret_cast<const uint4*>(p.accin16) + off);
-              pre[2 * ii + 1] = *(reinterpret_cast<const uint4*>(p.accin16) + off + p.L);
+              pre[2 * ii] = ld_acc(reinterpret_cast<const uint4*>(p.accin16) + off, p.no_pre);
+              pre[2 * ii + 1] = ld_acc(reinterpret_cast<const uint4*>(p.accin16) + off + p.L, p.no_pre);
             } else if (PRE32) {
-              pre[(4 * ii) & 7] = *(reinterpret_cast<const uint4*>(p.accin32) + off * 2);
-              pre[(4 * ii + 1) & 7] = *(reinterpret_cast<const uint4*>(p.accin32) + off * 2 + 1);
-              pre[(4 * ii + 2) & 7] = *(reinterpret_cast<const uint4*>(p.accin32) + (off + p.L) * 2);
-              pre[(4 * ii + 3) & 7] = *(reinterpret_cast<const uint4*>(p.accin32) + (off + p.L) * 2 + 1);
+              pre[(4 * ii) & 7] = ld_acc(reinterpret_cast<const uint4*>(p.accin32) + off * 2, p.no_pre);
+              pre[(4 * ii + 1) & 7] = ld_acc(reinterpret_cast<const uint4*>(p.accin32) + off * 2 + 1, p.no_pre);
+              pre[(4 * ii + 2) & 7] = ld_acc(reinterpret_cast<const uint4*>(p.accin32) + (off + p.L) * 2, p.no_pre);
+              pre[(4 * ii + 3) & 7] = ld_acc(reinterpret_cast<const uint4*>(p.accin32) + (off + p.L) * 2 + 1, p.no_pre);
             }
           }
         }
@@ -792,6 +805,12 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
 
 }  // namespace
 
+unsigned long long pair_debug_counter(int i) {
+  unsigned long long v[16];
+  cudaMemcpyFromSymbol(v, g_pair_dbg, sizeof(v));
+  return v[i & 15];
+}
+
 bool pair_conv_supported(const PairConvArgs& a) {
   if (!a.x || !a.w1 || !a.w2 || !a.bias1 || !a.bias2 || (!a.out16 && !a.out32)) return false;
   if (a.L <= 0 || a.B <= 0 || a.res_inv < 1.f || a.out16_slope > 1.f) return false;
@@ -824,6 +843,8 @@ cudaError_t launch_pair_planes(const PairConvArgs& a, cudaStream_t s) {
   }
   static const int no_epim = [] { const char* e = getenv("PG_PAIR_GENERIC_E2"); return e ? atoi(e) : 0; }();
   if (no_epim) epim = 0;
+  static const int epim_mask = [] { const char* e = getenv("PG_PAIR_EPIM_MASK"); return e ? atoi(e) : 14; }();
+  if (!((epim_mask >> epim) & 1)) epim = 0;
 #define PG_PAIR_E(MT_, C_, HL_)                                                      \
   switch (epim) {                                                                   \
     case 1: return launch_pair_t<MT_, C_, true, 1, HL_>(a, pl, s);                   \

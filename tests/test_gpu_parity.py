@@ -523,3 +523,27 @@ def test_other_configs_medium_clip_vs_oracle_and_unfused(name):
     assert (wave - o[:, 0]).abs().max().item() <= WAVE_MAXABS
     twin, _ = _run(_engine(cfg, sd, _lib.PG_FLAG_NO_PAIR_FUSION), inputs, noise)
     assert snr_db(wave, twin) >= 90.0
+
+
+def test_fused_source_injection_matches_separate_kernel(monkeypatch):
+    """The NSF source injection (nsf.py:131) can run inside the upsampler's epilogue (default: the last stage;
+    PG_NOISE_FUSE_MAXK=8 here: every stage with a noise conv of <= 8 taps).  PG_FLAG_NO_NOISE_FUSION is the twin
+    with a separate kernel per stage (which rounds the upsampler output to f16 once more before adding).  Both
+    against the oracle, and against each other."""
+    monkeypatch.setenv("PG_NOISE_FUSE_MAXK", "8")
+    import polgen_rvc_b200 as pg
+    from polgen_rvc_b200 import _lib
+    from oracle import rvc_oracle as orc
+    for name, T in (("v2-48k", 193), ("v2-32k", 130)):
+        cfg = pg.CONFIGS[name]
+        sd = pg.synth_weights(cfg, seed=23)
+        inputs = pg.synth_inputs(cfg, 2, T, seed=23)
+        noise = pg.synth_noise(cfg, 2, T, seed=23)
+        o, *_ = orc.infer(sd, cfg, *inputs, *noise)
+        fused = _engine(cfg, sd, 0)
+        a, _ = _run(fused, inputs, noise)
+        twin = _engine(cfg, sd, _lib.PG_FLAG_NO_NOISE_FUSION)
+        b, _ = _run(twin, inputs, noise)
+        assert fused.launch_count() == twin.launch_count() - (len(cfg.upsample_rates) - 1)   # all but the 64/80-tap stage
+        assert snr_db(a, o[:, 0]) >= WAVE_SNR_DB and snr_db(b, o[:, 0]) >= WAVE_SNR_DB
+        assert snr_db(a, b) >= 55.0
