@@ -791,7 +791,8 @@ int run_pair_conv(pg_handle h, cudaStream_t s, PairConvArgs a, const ConvW& w1, 
 // in front of the hi/lo split) wins 0.02 ms per step, k = 4 is even, k = 8 loses 0.04 ms, k = 80 keeps its
 // shared-memory tiled kernel.  Default: fuse k <= 1; PG_NOISE_FUSE_MAXK=4|8 fuses the other stages too.
 bool fuse_noise(pg_handle h, const StageW& S) {
-  static const int max_k = [] { const char* e = getenv("PG_NOISE_FUSE_MAXK"); return e ? atoi(e) : 1; }();
+  const char* e = getenv("PG_NOISE_FUSE_MAXK");   // read per call: tests flip it inside one process
+  const int max_k = e ? atoi(e) : 1;
   return !(h->cfg.flags & (PG_FLAG_KEEP_TAPS | PG_FLAG_NO_NOISE_FUSION)) && S.noise_k <= max_k;
 }
 
