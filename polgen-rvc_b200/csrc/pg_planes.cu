@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(256) noise_inject_planes_kernel(
 // channels of one batch row.  The source window, the [k][C] weights and the x tile are staged in shared
 // memory with coalesced loads; a lane owns one 8-channel chunk (weights: two conflict-free 16 B reads per
 // tap, source sample: a broadcast) and CP/8 rows, so every weight read feeds 8*CP/8 FMAs.
-constexpr int NRB = 32;   // rows per block
+constexpr int NRB = 32;   // rows per sub-tile
+constexpr int NSUB = 8;   // sub-tiles per block: the [k][C] weights are staged once per 256 rows (r02: 207 -> us per launch
+                          // was dominated by re-staging them for every 32 rows)
 template <int CP>
 __global__ void __launch_bounds__(256) noise_inject_tiled_kernel(
     __half* __restrict__ x, const float* __restrict__ src, const float* __restrict__ wn,
@@ -152,10 +154,14 @@ __global__ void __launch_bounds__(256) noise_inject_tiled_kernel(
   float* ss = ws + (size_t)k * C;                               // [(NRB-1)*stride + k]
   uint8_t* xs = reinterpret_cast<uint8_t*>(ss + (((NRB - 1) * stride + k + 3) & ~3));   // [CP][NRB] x 16 B
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y, t0 = blockIdx.x * NRB;
+  const int b = blockIdx.y;
   for (int i = tid; i < k * C; i += 256) ws[i] = wn[i];
-  const int win = (NRB - 1) * stride + k, s_first = t0 * stride - pad;
   const float* sp = src + (size_t)b * Lsrc;
+  for (int sub = 0; sub < NSUB; ++sub) {
+  const int t0 = (blockIdx.x * NSUB + sub) * NRB;
+  if (t0 >= L) break;
+  __syncthreads();          // the previous sub-tile's stores have read xs / ss
+  const int win = (NRB - 1) * stride + k, s_first = t0 * stride - pad;
   for (int i = tid; i < win; i += 256) {
     const int n = s_first + i;
     ss[i] = (n >= 0 && n < Lsrc) ? sp[n] : 0.f;
@@ -201,6 +207,7 @@ __global__ void __launch_bounds__(256) noise_inject_tiled_kernel(
     if (t0 + r < L)
       *reinterpret_cast<uint4*>(xb + ((size_t)pl * L + t0 + r) * 8) = *reinterpret_cast<const uint4*>(xs + pl * XP + r * 16);
   }
+  }   // sub-tiles
 }
 
 template <int CP>
@@ -211,40 +218,60 @@ cudaError_t launch_noise_tiled(__half* x, const float* src, const float* wn, con
   static DeviceOnce once;
   if (smem > 48 * 1024)
     if (cudaError_t e = ensure_dyn_smem(noise_inject_tiled_kernel<CP>, once, (int)smem)) return e;
-  dim3 grid((L + NRB - 1) / NRB, B);
+  dim3 grid((L + NRB * NSUB - 1) / (NRB * NSUB), B);
   noise_inject_tiled_kernel<CP><<<grid, 256, smem, s>>>(x, src, wn, bn, L, Lsrc, k, stride, pad, slope);
   return cudaGetLastError();
 }
 
-// nsf.py:142-143  wave = tanh(conv_post(leaky_relu(x)))  (Cout = 1, no bias); one thread per sample
+// nsf.py:142-143  wave = tanh(conv_post(leaky_relu(x)))  (Cout = 1, no bias).  One block = 256 output samples: the
+// (256 + K - 1)-row window of every plane is staged RAW in shared memory by 16-byte cp.async copies (all in flight at
+// once, no register staging; rows outside [0, hard row end) are zero-filled by the copy itself), then one thread per
+// sample walks the K x C taps from shared memory, applying the leaky-ReLU on the way.  (The round-1 kernel re-read
+// every row K times through L1.)
+constexpr int CPB = 256;
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int n = valid ? 16 : 0;       // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
 template <typename T, int K>
-__global__ void __launch_bounds__(256) conv_post_planes_kernel(const T* __restrict__ x,
+__global__ void __launch_bounds__(CPB) conv_post_planes_kernel(const T* __restrict__ x,
                                                                const float* __restrict__ w /*[K][C]*/,
                                                                float* __restrict__ wave, int L, int C,
                                                                float in_slope, const int* __restrict__ tlen,
                                                                int len_mul) {
-  extern __shared__ float ws[];
-  for (int i = threadIdx.x; i < K * C; i += blockDim.x) ws[i] = w[i];
-  __syncthreads();
-  const int b = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= L) return;
+  extern __shared__ __align__(16) float cps[];
+  constexpr int RB = 8 * (int)sizeof(T);          // bytes per (row, plane): 32 (f32) / 16 (f16)
+  constexpr int PIECES = RB / 16;
+  const int CP = C / 8, ROWS = CPB + K - 1;
+  float* ws = cps;                                // [K][C]
+  uint8_t* xs = reinterpret_cast<uint8_t*>(cps + K * C);   // [CP][ROWS] x RB bytes, raw
+  const int b = blockIdx.y, t0 = blockIdx.x * CPB;
   const int t_hi = tlen ? min(L, tlen[b] * len_mul) : L;   // hard end of the row
-  const int CP = C / 8;
+  const uint8_t* xb = reinterpret_cast<const uint8_t*>(x) + (size_t)b * CP * (size_t)L * RB;
+  for (int i = threadIdx.x; i < CP * ROWS * PIECES; i += CPB) {
+    const int piece = i % PIECES, rr = i / PIECES;
+    const int pl = rr / ROWS, r = rr - pl * ROWS;
+    const int n = t0 + r - K / 2;
+    const bool valid = n >= 0 && n < t_hi;
+    cp_async16_zfill(xs + (size_t)rr * RB + piece * 16, xb + ((size_t)pl * L + (valid ? n : 0)) * RB + piece * 16, valid);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = threadIdx.x; i < K * C; i += CPB) ws[i] = w[i];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= L) return;
   float acc = 0.f;
   for (int pl = 0; pl < CP; ++pl) {
-    const T* plane = x + ((size_t)b * CP + pl) * (size_t)L * 8;
+    const T* row = reinterpret_cast<const T*>(xs + ((size_t)pl * ROWS + threadIdx.x) * RB);
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-      const int n = t + j - K / 2;
-      if (n < 0 || n >= t_hi) continue;
       float v[8];
-      load8(plane + (size_t)n * 8, v);
+      load8(row + j * 8, v);
+      const float* wj = ws + j * C + pl * 8;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float a = v[q] > 0.f ? v[q] : v[q] * in_slope;
-        acc = fmaf(ws[j * C + pl * 8 + q], a, acc);
-      }
+      for (int q = 0; q < 8; ++q) acc = fmaf(wj[q], fmaxf(v[q], v[q] * in_slope), acc);   // slope <= 1
     }
   }
   wave[(size_t)b * L + t] = t < t_hi ? tanhf(acc) : 0.f;
@@ -291,7 +318,8 @@ cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, __half* l
                                        const float* wn, const float* bn, int B, int L, int C, int Lsrc, int k,
                                        int stride, int pad, float slope, cudaStream_t s) {
   if (C % 8) return cudaErrorInvalidValue;
-  if (dt == DT_F16 && a16 == x && k >= 8) {   // long-tap stages of the f16 stream: shared-memory tiled kernel
+  static const int tiled_min_k = [] { const char* e = getenv("PG_NOISE_TILED_MINK"); return e ? atoi(e) : 8; }();
+  if (dt == DT_F16 && a16 == x && k >= tiled_min_k) {   // long-tap stages of the f16 stream: shared-memory tiled kernel
     // (measured: 268 -> 90 us at k = 80; at k = 4 the plain kernel is already HBM-bound and faster)
     const size_t smem_need = 4 * ((size_t)k * C + (NRB - 1) * stride + k + 4) + (size_t)(C / 8) * (NRB * 16 + 16);
     if (smem_need <= 200 * 1024) {
@@ -316,8 +344,17 @@ cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, __half* l
 cudaError_t launch_conv_post_planes(const void* x, DType dt, const float* w, float* wave, int B, int L, int C,
                                     int K, float in_slope, const int* tlen, int len_mul, cudaStream_t s) {
   if (K != 7 || C % 8 || C > 256) return cudaErrorInvalidValue;
-  dim3 grid((L + 255) / 256, B);
-  const size_t smem = sizeof(float) * K * C;
+  dim3 grid((L + CPB - 1) / CPB, B);
+  const size_t smem = sizeof(float) * (size_t)K * C + (size_t)(C / 8) * (CPB + K - 1) * (dt == DT_F32 ? 32 : 16);
+  if (in_slope > 1.f) return cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {
+    static DeviceOnce o32, o16;
+    if (dt == DT_F32) {
+      if (cudaError_t e = ensure_dyn_smem(conv_post_planes_kernel<float, 7>, o32, (int)smem)) return e;
+    } else {
+      if (cudaError_t e = ensure_dyn_smem(conv_post_planes_kernel<__half, 7>, o16, (int)smem)) return e;
+    }
+  }
   if (dt == DT_F32)
     conv_post_planes_kernel<float, 7><<<grid, 256, smem, s>>>(reinterpret_cast<const float*>(x), w, wave, L, C,
                                                              in_slope, tlen, len_mul);
