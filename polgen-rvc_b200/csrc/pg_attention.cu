@@ -97,6 +97,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) rel_attention_mma_kernel(
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z / splits, sp = blockIdx.z - b * splits, h = blockIdx.y, q0 = blockIdx.x * AQ;
   const int len = lens[b];
+  // Rows of a (ragged / bucket-padded) batch end at len: query tiles past it produce nothing anybody reads (every
+  // consumer masks rows >= len; the merge kernel writes zeros there), and key blocks past it carry exactly zero
+  // probability for the live queries (exp(-1e4 - max) underflows), so both are skipped.
+  if (q0 >= len) return;
   const int R = 2 * window + 1;
   const size_t bh = (size_t)b * heads + h;
   const __half* kh_b = kh + bh * Tp * AD;
@@ -121,7 +125,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) rel_attention_mma_kernel(
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   const int nblk = Tp / AK;
-  const int kb_begin = (int)((long long)sp * nblk / splits), kb_end = (int)((long long)(sp + 1) * nblk / splits);
+  const int kb_begin = (int)((long long)sp * nblk / splits);
+  const int kb_end = min((int)((long long)(sp + 1) * nblk / splits), (len + AK - 1) / AK);
+  if (kb_begin >= kb_end) {     // this split holds no live key: a neutral partial (weight e^{-inf} = 0 in the merge)
+    const size_t rows_all = (size_t)B * heads * Tp;
+    for (int i = tid; i < AQ; i += ATT_THREADS) {
+      part_m[(size_t)sp * rows_all + bh * Tp + q0 + i] = -INFINITY;
+      part_l[(size_t)sp * rows_all + bh * Tp + q0 + i] = 0.f;
+    }
+    for (int i = tid; i < AQ * AD; i += ATT_THREADS)
+      part_o[((size_t)sp * rows_all + bh * Tp + q0) * AD + i] = 0.f;
+    return;
+  }
   load_block(kb_begin, 0);
 
   // ---- prologue: rel-key logits (fp32) if this CTA's keys touch the band of its queries, Q fragments
@@ -322,8 +337,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) rel_attention_mma_kernel(
 // One warp per (b, head, query row); lanes cover the 96 channels three at a time.
 __global__ void attn_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_m,
                                   const float* __restrict__ part_l, const float* __restrict__ band_s,
-                                  const float* __restrict__ rel_v, float* __restrict__ out, int B, int T,
-                                  int Tp, int H, int heads, int window, int splits) {
+                                  const float* __restrict__ rel_v, const int* __restrict__ lens,
+                                  float* __restrict__ out, int B, int T, int Tp, int H, int heads, int window,
+                                  int splits) {
   const int lane = threadIdx.x & 31;
   const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (gw >= (size_t)B * heads * T) return;
@@ -331,6 +347,13 @@ __global__ void attn_merge_kernel(const float* __restrict__ part_o, const float*
   const size_t bh = gw / T;
   const int h = (int)(bh % heads), b = (int)(bh / heads);
   const size_t rows = (size_t)B * heads * Tp, row = bh * Tp + i;
+  const int len = lens[b];
+  if (i >= len) {      // past the row's end: no partials were produced; consumers mask these rows anyway
+    float* dst0 = out + ((size_t)b * T + i) * H + h * AD + lane;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dst0[32 * k] = 0.f;
+    return;
+  }
   float M = -INFINITY;
   for (int s = 0; s < splits; ++s) M = fmaxf(M, part_m[s * rows + row]);
   float L = 0.f, acc[3] = {0.f, 0.f, 0.f};
@@ -346,7 +369,7 @@ __global__ void attn_merge_kernel(const float* __restrict__ part_o, const float*
   float p = 0.f;   // band probability of key j = i + lane - window
   if (lane < R) {
     const int j = i + lane - window;
-    if (j >= 0 && j < T) p = __expf(band_s[row * RP + lane] - M) * inv_l;
+    if (j >= 0 && j < len) p = __expf(band_s[row * RP + lane] - M) * inv_l;   // keys >= len: probability exactly 0
   }
   float v[3] = {acc[0] * inv_l, acc[1] * inv_l, acc[2] * inv_l};
   for (int r = 0; r < R; ++r) {
@@ -418,8 +441,8 @@ cudaError_t launch_rel_attention_mma(const float* qkv, const float* rel_k, const
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const size_t warps = (size_t)B * n_heads * T;
-  attn_merge_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(part_o, part_m, part_l, band_s, rel_v, out, B, T, Tp,
-                                                               H, n_heads, window, ns);
+  attn_merge_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(part_o, part_m, part_l, band_s, rel_v, lens, out, B, T,
+                                                               Tp, H, n_heads, window, ns);
   return cudaGetLastError();
 }
 
