@@ -284,7 +284,8 @@ def run_ours(args):
     folded = pg.fold_state_dict(sd)
     batch512 = args.workload == "batch512"
     sched = pg.SegmentScheduler(cfg, folded, local, lanes=args.lanes, max_batch=args.max_batch,
-                                max_batch_frames=max(36000, args.max_batch * 1100))
+                                max_batch_frames=max(36000, args.max_batch * 1100),
+                                decoder_sms=args.decoder_sms)
     conv = pg.ClipConverter(sched, cfg.sr, depth=max(2, args.lanes))
     warm = max(args.warmup, 3)
 
@@ -473,7 +474,7 @@ def run_ours(args):
                        "audio_s_per_step": variants[0]["audio_s_global"],
                        "step_variants": [v["frames"] for v in variants] if not batch512 else None,
                        "l2": "no explicit flush: a step streams > 3 GB of activations through the 126 MB L2 (inputs larger than L2)",
-                       "segment_lanes_per_gpu": args.lanes, "ragged_batching": True,
+                       "segment_lanes_per_gpu": args.lanes, "decoder_sms": args.decoder_sms or None, "ragged_batching": True,
                        "steps_pipelined": bool(args.pipelined),
                        "cuda_graphs_held": graphs,
                        "parallelism": f"segment-sharded x{world} (plan_shards), no collective in the decode"},
@@ -547,6 +548,9 @@ def main():
     ap.add_argument("--no-pipelined", dest="pipelined", action="store_false",
                     help="join the scheduler's lanes after every step instead of streaming clip after clip")
     ap.add_argument("--lanes", type=int, default=2, help="engines/streams per GPU the batches are dealt over")
+    ap.add_argument("--decoder-sms", type=int, default=int(os.environ.get("PG_BENCH_DECODER_SMS", "0")),
+                    help="cap on the CTAs of the decoder's persistent kernels (0 = one per SM); with >= 2 lanes the SMs left "
+                         "free run the other lane's TextEncoder / flow kernels beside the decoder")
     ap.add_argument("--table", default="", help="write the per-layer-shape conv timing table to gpurun_out/<name>")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -92,6 +92,7 @@ typedef struct pg_config {
 #define PG_FLAG_NO_PAD 256       /* do not pad T up to a launch-shape bucket (validation twin of the padded path) */
 #define PG_FLAG_F32_STREAM 512   /* last decoder stage with an fp32 residual stream + f16 operand copy (validation twin of the default hi/lo f16 pair stream) */
 #define PG_FLAG_NO_NOISE_FUSION 1024 /* NSF source injection as its own kernel after every upsampler (validation twin of the fused epilogue) */
+#define PG_FLAG_LEGACY_ATTENTION 2048 /* TextEncoder attention on the mma.sync kernel (validation twin of the tcgen05 / TMEM kernel) */
 #define PG_FLAG_F16_LATENTS 8  /* TextEncoder / flow GEMMs with single-pass f16 tensor-core operands (default: fp32-accurate) */
 
 typedef struct pg_handle_s* pg_handle;
@@ -237,6 +238,12 @@ int64_t pg_launch_count(pg_handle h);
 int pg_graph_count(pg_handle h);
 /* Bound on that number (default 16, env PG_GRAPH_CACHE); least recently used graphs are dropped. */
 int pg_set_graph_cache(pg_handle h, int max_graphs);
+/* Cap on the CTAs of the decoder's persistent conv kernels (0 = one per SM, the default; env PG_DECODER_SMS).
+ * With two or more handles decoding a stream of clips on their own streams (SegmentScheduler lanes), a cap a
+ * few SMs below the device's count leaves those SMs free, so the short TextEncoder / flow kernels of one
+ * handle's next clip run beside another handle's decoder instead of queueing behind its persistent CTAs.
+ * Results do not depend on it (the tile walk is grid-stride).  Drops the handle's captured graphs. */
+int pg_set_decoder_sms(pg_handle h, int sms);
 /* The padded frame count pg_infer runs a T-frame call at (the graph bucket of T). */
 int pg_padded_frames(pg_handle h, int T);
 

@@ -26,6 +26,7 @@ PG_FLAG_NO_PLANES_SWAP = 128
 PG_FLAG_NO_PAD = 256
 PG_FLAG_F32_STREAM = 512
 PG_FLAG_NO_NOISE_FUSION = 1024
+PG_FLAG_LEGACY_ATTENTION = 2048
 PG_F32 = 0
 PG_F64 = 3
 PG_ABI_VERSION = 2
@@ -79,6 +80,7 @@ SYMBOLS = {
     "pg_launch_count": (C.c_int64, [_P]),
     "pg_graph_count": (C.c_int, [_P]),
     "pg_set_graph_cache": (_I, [_P, _I]),
+    "pg_set_decoder_sms": (_I, [_P, _I]),
     "pg_padded_frames": (_I, [_P, _I]),
     "pg_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pg_profile_table": (_I, [_P, C.POINTER(C.c_double), _I]),

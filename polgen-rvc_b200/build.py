@@ -21,28 +21,41 @@ FLAGS = [
 ]
 
 
-def _stale() -> bool:
-    if not os.path.exists(OUT):
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(HERE, "..", "include", "polgen_rvc.h"))
+    return hs
+
+
+def _obj_stale(src: str, obj: str) -> bool:
+    if not os.path.exists(obj):
         return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps.append(os.path.join(HERE, "..", "include", "polgen_rvc.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    t = os.path.getmtime(obj)
+    return any(os.path.getmtime(d) > t for d in [src, *_headers()])
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return OUT
-    objs = []
+    """compile the stale objects (in parallel: the big kernels take a minute each) and link"""
+    from concurrent.futures import ThreadPoolExecutor
+    jobs, objs = [], []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
+        path, obj = os.path.join(CSRC, src), os.path.join(CSRC, src.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _obj_stale(path, obj):
+            jobs.append((src, [NVCC, *FLAGS, "-c", path, "-o", obj]))
+    if not jobs and os.path.exists(OUT) and all(os.path.getmtime(o) <= os.path.getmtime(OUT) for o in objs):
+        return OUT
+
+    def run(job):
+        return job[0], subprocess.run(job[1], capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4) or 1) as ex:
+        results = list(ex.map(run, jobs))
+    for src, r in results:
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
         if r.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-        objs.append(obj)
     cmd = [NVCC, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
            "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)

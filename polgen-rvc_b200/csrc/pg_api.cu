@@ -117,6 +117,7 @@ struct pg_handle_s {
   std::map<std::pair<int, int>, GraphEntry> graphs;   // key (B, padded T); at most graph_cap instantiated
   uint64_t graph_clock = 0;
   int graph_cap = 16;
+  int decoder_sms = 0;          // > 0: the decoder's persistent kernels launch at most this many CTAs (pg_set_decoder_sms)
   DevBuf io;
   DevBuf io_eps;                // explicit-noise staging of pg_infer_segments
   DevBuf post;                  // pg_postprocess scratch
@@ -539,7 +540,7 @@ int run_text_encoder(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, con
                                         c.attn_window, s));
     } else {
       PG_LAUNCH(h, launch_rel_attention_mma(qkv, L.rel_k, L.rel_v, lens, att, at<char>(h, w.attn), B, T, H,
-                                            c.n_heads, c.attn_window, s));
+                                            c.n_heads, c.attn_window, (h->cfg.flags & PG_FLAG_LEGACY_ATTENTION) ? 1 : 0, s));
       h->launches += 2;   // prep + split attention + merge kernels
     }
     a.x = att; a.x_ld = H; a.y = y; a.y_ld = H;
@@ -737,6 +738,7 @@ int run_plane_conv(pg_handle h, cudaStream_t s, PlaneConvArgs a, const ConvW& w)
   a.tapmask = w.tapmask;
   if (a.Cout_real == 0) a.Cout_real = w.Cout;
   a.swap = (h->cfg.flags & PG_FLAG_NO_PLANES_SWAP) == 0;
+  a.grid_cap = h->decoder_sms;
   if (!plane_conv_supported(a)) return fail(PG_ERR_UNSUPPORTED, "layer shape not supported by the plane conv kernel");
   const bool prof = (h->cfg.flags & PG_FLAG_PROFILE) != 0;
   pg_handle_s::ProfRec rec;
@@ -763,6 +765,7 @@ int run_pair_conv(pg_handle h, cudaStream_t s, PairConvArgs a, const ConvW& w1, 
   if (h->cfg.flags & PG_FLAG_NO_PAIR_FUSION) return PG_ERR_UNSUPPORTED;
   a.w1 = w1.w16; a.w2 = w2.w16; a.bias1 = w1.bias; a.bias2 = w2.bias;
   a.C = w1.Cin; a.K = w1.K;
+  a.grid_cap = h->decoder_sms;
   if (w1.Cin != w1.Cout || w2.Cin != w2.Cout || w1.Cin != w2.Cin || w1.K != w2.K) return PG_ERR_UNSUPPORTED;
   if (!pair_conv_supported(a)) return PG_ERR_UNSUPPORTED;
   const bool prof = (h->cfg.flags & PG_FLAG_PROFILE) != 0;
@@ -1263,6 +1266,7 @@ int pg_finalize(pg_handle h) {
   if (h->stages.back().C % 8 || h->stages.back().C > 256)
     return fail(PG_ERR_UNSUPPORTED, "last decoder stage width must be a multiple of 8 and <= 256 channels");
   if (const char* e = getenv("PG_GRAPH_CACHE")) h->graph_cap = std::max(0, atoi(e));
+  if (const char* e = getenv("PG_DECODER_SMS")) h->decoder_sms = std::max(0, atoi(e));
   h->host.clear();
   h->finalized = true;
   return PG_OK;
@@ -1536,6 +1540,16 @@ int pg_set_graph_cache(pg_handle h, int max_graphs) {
   Guard g(h->device);
   h->graph_cap = max_graphs;
   trim_graphs(h);
+  return PG_OK;
+}
+
+int pg_set_decoder_sms(pg_handle h, int sms) {
+  if (!h || sms < 0) return fail(PG_ERR_INVALID, "bad argument");
+  Guard g(h->device);
+  if (sms != h->decoder_sms) {
+    h->decoder_sms = sms;
+    invalidate_graphs(h);   // grid sizes are baked into captured graphs
+  }
   return PG_OK;
 }
 

@@ -18,8 +18,10 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "pg_common.cuh"
+#include "pg_umma.cuh"
 
 namespace pg {
 
@@ -382,6 +384,379 @@ __global__ void attn_merge_kernel(const float* __restrict__ part_o, const float*
   for (int k = 0; k < 3; ++k) dst[32 * k] = v[k];
 }
 
+// =====================================================================================================
+// tcgen05 / TMEM version (the product path).  Same algorithm and the same split-key partials + merge kernel as
+// the mma.sync kernel above (kept as the validation twin, PG_ATTN_LEGACY=1), but both GEMMs run on the 5th-gen
+// tensor cores with fp32 accumulators in TMEM:
+//   * one CTA = 128 queries x a range of 64-key blocks; 6 warps: 4 softmax warps (thread = query row =
+//     TMEM lane), 1 MMA-issue warp, 1 bulk-copy loader warp
+//   * S = Q K^T: M = 128, N = 64, K = 96 as 3 split terms x 6 MMAs (Qh Kh + Qh Kl + Ql Kh) into one of two
+//     S accumulators (64 TMEM columns each); S(j+2) is issued right after PV(j), so the tensor pipe works on
+//     the next blocks' scores while the softmax warps are busy with block j+1
+//   * P = exp(S - m) leaves the softmax threads as a two-term f16 pair in shared memory in the canonical
+//     no-swizzle K-major operand layout ([key group of 8][row][8 keys]: a thread's 16 B stores are conflict-free)
+//   * O_j = P V: M = 128, N = 96, K = 64 as 3 terms x 4 MMAs into one of two O accumulators (96 columns, fresh
+//     per block); the running output stays in REGISTERS (o = o*alpha + O_j after a tcgen05.ld), so the online-
+//     softmax rescale never touches TMEM and the read of O_{j-1} is deferred behind the softmax of block j
+//   * operands come pre-split and pre-tiled from attn_prep_umma_kernel: a Q tile (48 KB), a K block and a V
+//     block (24 KB each; V as [key group][dim][8 keys]) are each ONE contiguous bulk copy (cp.async.bulk)
+//     completing on an mbarrier; K has a 2-deep ring (released by the commit of its S MMAs), V a 3-deep one
+//     (released by the commit of its PV MMAs)
+// =====================================================================================================
+constexpr int UQ = 128, UK = 64;                    // queries per CTA, keys per block
+constexpr int U_PLANES = AD / 8;                    // 12 planes of 8 head dims
+constexpr int UQ_TERM = U_PLANES * UQ * 16;         // 24576 B: one term (hi | lo) of a Q tile
+constexpr int UK_TERM = U_PLANES * UK * 16;         // 12288 B: one term of a K block  [plane][key][8]
+constexpr int UV_TERM = (UK / 8) * AD * 16;         // 12288 B: one term of a V block  [key group][dim][8 keys]
+constexpr int UP_TERM = (UK / 8) * UQ * 16;         // 16384 B: one term of P          [key group][row][8 keys]
+constexpr int U_KSTAGES = 2, U_VSTAGES = 3;
+constexpr int URL = 22;                             // rel-logit row pitch (floats): 21*i + j + w is conflict-free
+constexpr int U_THREADS = 192;
+constexpr int U_OFF_Q = 0;
+constexpr int U_OFF_K = U_OFF_Q + 2 * UQ_TERM;
+constexpr int U_OFF_V = U_OFF_K + U_KSTAGES * 2 * UK_TERM;
+constexpr int U_OFF_P = U_OFF_V + U_VSTAGES * 2 * UV_TERM;      // prologue: aliased by the fp32 rel-key table
+constexpr int U_OFF_RL = U_OFF_P + 2 * UP_TERM;
+constexpr int U_OFF_BAR = U_OFF_RL + UQ * URL * 4;
+constexpr int U_SMEM = U_OFF_BAR + 256;
+constexpr uint32_t U_TMEM_COLS = 512;               // S0 @0, S1 @64, O0 @128, O1 @256
+static_assert(RP * AD * 4 <= 2 * UP_TERM, "rel-key table must fit the P buffer it aliases");
+static_assert(U_SMEM <= 227 * 1024, "attention tile set exceeds shared memory");
+
+// qkv [B][T][3H] f32 -> pre-scaled Q tiles, K blocks, V blocks (two f16 terms each) in the layouts above; rows >= T
+// are zero.  One CTA per (b, head, 64-row block): items are (row, plane) for Q / K and (key group, dim) for V, so
+// the 16 B stores of consecutive threads are contiguous.
+__global__ void attn_prep_umma_kernel(const float* __restrict__ qkv, __half* __restrict__ qb, __half* __restrict__ kb,
+                                      __half* __restrict__ vb, int T, int Tp, int H, int heads, float qscale) {
+  const int blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const size_t bh = (size_t)b * heads + h;
+  const int j0 = blk * UK;
+  char* q_tile = reinterpret_cast<char*>(qb) + (bh * (Tp / UQ) + (size_t)(j0 / UQ)) * (2 * UQ_TERM);
+  char* k_blk = reinterpret_cast<char*>(kb) + (bh * (Tp / UK) + (size_t)blk) * (2 * UK_TERM);
+  char* v_blk = reinterpret_cast<char*>(vb) + (bh * (Tp / UK) + (size_t)blk) * (2 * UV_TERM);
+  const int rq0 = j0 % UQ;      // first row of this block inside its Q tile
+  for (int it = threadIdx.x; it < UK * U_PLANES; it += blockDim.x) {
+    const int r = it % UK, pl = it / UK;
+    const int j = j0 + r;
+    float q[8], k[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[e] = k[e] = 0.f;
+    if (j < T) {
+      const float* row = qkv + ((size_t)b * T + j) * 3 * H + h * AD + pl * 8;
+      const float4 q0 = *reinterpret_cast<const float4*>(row), q1 = *reinterpret_cast<const float4*>(row + 4);
+      const float4 k0 = *reinterpret_cast<const float4*>(row + H), k1 = *reinterpret_cast<const float4*>(row + H + 4);
+      q[0] = q0.x * qscale; q[1] = q0.y * qscale; q[2] = q0.z * qscale; q[3] = q0.w * qscale;
+      q[4] = q1.x * qscale; q[5] = q1.y * qscale; q[6] = q1.z * qscale; q[7] = q1.w * qscale;
+      k[0] = k0.x; k[1] = k0.y; k[2] = k0.z; k[3] = k0.w; k[4] = k1.x; k[5] = k1.y; k[6] = k1.z; k[7] = k1.w;
+    }
+    __align__(16) __half qh[8], ql[8], kh[8], kl[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      split_f16(q[e], &qh[e], &ql[e]);
+      split_f16(k[e], &kh[e], &kl[e]);
+    }
+    const size_t qo = ((size_t)pl * UQ + rq0 + r) * 16, ko = ((size_t)pl * UK + r) * 16;
+    *reinterpret_cast<uint4*>(q_tile + qo) = *reinterpret_cast<const uint4*>(qh);
+    *reinterpret_cast<uint4*>(q_tile + UQ_TERM + qo) = *reinterpret_cast<const uint4*>(ql);
+    *reinterpret_cast<uint4*>(k_blk + ko) = *reinterpret_cast<const uint4*>(kh);
+    *reinterpret_cast<uint4*>(k_blk + UK_TERM + ko) = *reinterpret_cast<const uint4*>(kl);
+  }
+  for (int it = threadIdx.x; it < (UK / 8) * AD; it += blockDim.x) {
+    const int c = it % AD, kg = it / AD;
+    __align__(16) __half vh[8], vl[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = j0 + kg * 8 + e;
+      const float v = j < T ? qkv[((size_t)b * T + j) * 3 * H + 2 * H + h * AD + c] : 0.f;
+      split_f16(v, &vh[e], &vl[e]);
+    }
+    const size_t vo = ((size_t)kg * AD + c) * 16;
+    *reinterpret_cast<uint4*>(v_blk + vo) = *reinterpret_cast<const uint4*>(vh);
+    *reinterpret_cast<uint4*>(v_blk + UV_TERM + vo) = *reinterpret_cast<const uint4*>(vl);
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
+    const __half* __restrict__ qb, const __half* __restrict__ kb, const __half* __restrict__ vb,
+    const float* __restrict__ qkv, const float* __restrict__ rel_k, const int* __restrict__ lens,
+    float* __restrict__ part_o, float* __restrict__ part_m, float* __restrict__ part_l, float* __restrict__ band_s,
+    int B, int T, int Tp, int H, int heads, int window, int splits, float qscale, uint32_t idesc_s,
+    uint32_t idesc_o) {
+  using namespace umma;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.z / splits, sp = blockIdx.z - b * splits, h = blockIdx.y, q0 = blockIdx.x * UQ;
+  const int len = lens[b];
+  if (q0 >= len) return;       // see the mma.sync kernel: nothing reads these rows
+  const int R = 2 * window + 1;
+  const size_t bh = (size_t)b * heads + h;
+  const size_t rows_all = (size_t)B * heads * Tp;
+  const int nblk = Tp / UK;
+  const int kb_begin = (int)((long long)sp * nblk / splits);
+  const int kb_end = min((int)((long long)(sp + 1) * nblk / splits), (len + UK - 1) / UK);
+  if (kb_begin >= kb_end) {    // no live key in this split: a neutral partial
+    for (int i = tid; i < UQ; i += U_THREADS) {
+      part_m[(size_t)sp * rows_all + bh * Tp + q0 + i] = -INFINITY;
+      part_l[(size_t)sp * rows_all + bh * Tp + q0 + i] = 0.f;
+    }
+    for (int i = tid; i < UQ * AD; i += U_THREADS) part_o[((size_t)sp * rows_all + bh * Tp + q0) * AD + i] = 0.f;
+    return;
+  }
+  const int n = kb_end - kb_begin;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + U_OFF_BAR);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* k_full = bars + 1;             // 2
+  uint64_t* k_empty = bars + 3;            // 2
+  uint64_t* v_full = bars + 5;             // 3
+  uint64_t* v_empty = bars + 8;            // 3
+  uint64_t* s_full = bars + 11;            // 2
+  uint64_t* o_full = bars + 13;            // 2
+  uint64_t* p_full = bars + 15;            // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  if (tid == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&o_full[i], 1); }
+    mbar_init(p_full, UQ);
+    fence_barrier_init();
+  }
+  if (warp == 4) tcgen05_alloc(tmem_slot, U_TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 5) {
+    // ------------------------------------------------ loader: one bulk copy per Q tile / K block / V block
+    if (elect_one()) {
+      const char* q_src = reinterpret_cast<const char*>(qb) + (bh * (Tp / UQ) + (size_t)blockIdx.x) * (2 * UQ_TERM);
+      mbar_expect_tx(q_full, 2 * UQ_TERM);
+      bulk_g2s(smem + U_OFF_Q, q_src, 2 * UQ_TERM, q_full);
+      const char* k_src = reinterpret_cast<const char*>(kb) + bh * nblk * (size_t)(2 * UK_TERM);
+      const char* v_src = reinterpret_cast<const char*>(vb) + bh * nblk * (size_t)(2 * UV_TERM);
+      for (int jj = 0; jj < n; ++jj) {
+        const int ks = jj % U_KSTAGES, vs = jj % U_VSTAGES;
+        mbar_wait(&k_empty[ks], ((jj / U_KSTAGES) & 1) ^ 1);
+        mbar_expect_tx(&k_full[ks], 2 * UK_TERM);
+        bulk_g2s(smem + U_OFF_K + ks * 2 * UK_TERM, k_src + (size_t)(kb_begin + jj) * (2 * UK_TERM), 2 * UK_TERM,
+                 &k_full[ks]);
+        mbar_wait(&v_empty[vs], ((jj / U_VSTAGES) & 1) ^ 1);
+        mbar_expect_tx(&v_full[vs], 2 * UV_TERM);
+        bulk_g2s(smem + U_OFF_V + vs * 2 * UV_TERM, v_src + (size_t)(kb_begin + jj) * (2 * UV_TERM), 2 * UV_TERM,
+                 &v_full[vs]);
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------ MMA issue
+    if (elect_one()) {
+      const uint32_t q_s = smem_u32(smem + U_OFF_Q), k_s = smem_u32(smem + U_OFF_K), v_s = smem_u32(smem + U_OFF_V),
+                     p_s = smem_u32(smem + U_OFF_P);
+      auto issue_s = [&](int jj) {      // S(jj) = Qh Kh^T + Qh Kl^T + Ql Kh^T  ->  TMEM columns (jj & 1) * 64
+        const int ks = jj % U_KSTAGES;
+        mbar_wait(&k_full[ks], (jj / U_KSTAGES) & 1);
+        tcgen05_fence_after();
+        const uint32_t kbase = k_s + ks * 2 * UK_TERM, d = tmem + (uint32_t)(jj & 1) * UK;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t qa = q_s + (term == 2 ? UQ_TERM : 0), ka = kbase + (term == 1 ? UK_TERM : 0);
+#pragma unroll
+          for (int k16 = 0; k16 < AD / 16; ++k16) {
+            umma_f16(d, make_desc(qa + k16 * 2 * (UQ * 16), UQ * 16, 128, LAYOUT_NONE),
+                     make_desc(ka + k16 * 2 * (UK * 16), UK * 16, 128, LAYOUT_NONE), idesc_s, acc);
+            acc = 1;
+          }
+        }
+        tcgen05_commit(&s_full[jj & 1]);
+        tcgen05_commit(&k_empty[ks]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      if (n > 1) issue_s(1);
+      for (int jj = 0; jj < n; ++jj) {
+        const int vs = jj % U_VSTAGES;
+        mbar_wait(p_full, jj & 1);
+        mbar_wait(&v_full[vs], (jj / U_VSTAGES) & 1);
+        tcgen05_fence_after();
+        // O(jj) = Ph Vh + Ph Vl + Pl Vh  ->  TMEM columns 128 + (jj & 1) * 128
+        const uint32_t vbase = v_s + vs * 2 * UV_TERM, d = tmem + 128u + (uint32_t)(jj & 1) * 128u;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t pa = p_s + (term == 2 ? UP_TERM : 0), va = vbase + (term == 1 ? UV_TERM : 0);
+#pragma unroll
+          for (int k16 = 0; k16 < UK / 16; ++k16) {
+            umma_f16(d, make_desc(pa + k16 * 2 * (UQ * 16), UQ * 16, 128, LAYOUT_NONE),
+                     make_desc(va + k16 * 2 * (AD * 16), AD * 16, 128, LAYOUT_NONE), idesc_o, acc);
+            acc = 1;
+          }
+        }
+        tcgen05_commit(&o_full[jj & 1]);
+        tcgen05_commit(&v_empty[vs]);
+        if (jj + 2 < n) issue_s(jj + 2);
+      }
+    }
+  } else {
+    // ------------------------------------------------ softmax: thread = query row = TMEM lane
+    const int r = tid, i = q0 + r;
+    float* rl = reinterpret_cast<float*>(smem + U_OFF_RL);
+    // rel-key logits q_i . Ek[rel] in fp32 when this CTA's keys touch the band of its queries
+    const bool any_band = kb_begin * UK < q0 + UQ + window && kb_end * UK > q0 - window;
+    if (any_band) {
+      float* ek = reinterpret_cast<float*>(smem + U_OFF_P);
+      for (int t = tid; t < R * AD; t += UQ) ek[t] = rel_k[t];
+      float q[AD];
+      if (i < T) {
+        const float4* row = reinterpret_cast<const float4*>(qkv + ((size_t)b * T + i) * 3 * H + h * AD);
+#pragma unroll
+        for (int c4 = 0; c4 < AD / 4; ++c4) {
+          const float4 v = row[c4];
+          q[4 * c4] = v.x * qscale; q[4 * c4 + 1] = v.y * qscale; q[4 * c4 + 2] = v.z * qscale; q[4 * c4 + 3] = v.w * qscale;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < AD; ++c) q[c] = 0.f;
+      }
+      named_bar_sync(1, UQ);
+      for (int rel = 0; rel < R; ++rel) {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < AD; ++c) s = fmaf(q[c], ek[rel * AD + c], s);
+        rl[r * URL + rel] = s;
+      }
+      named_bar_sync(1, UQ);     // the table's shared memory becomes the P buffer
+    }
+    float* band_row = band_s + (bh * Tp + i) * RP;
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    uint8_t* p_row = smem + U_OFF_P + r * 16;
+    float o[AD];
+#pragma unroll
+    for (int c = 0; c < AD; ++c) o[c] = 0.f;
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+
+    auto fold_o = [&](int jj, float alpha) {     // o = o * alpha + O(jj)
+      const uint32_t t0 = lane_addr + 128u + (uint32_t)(jj & 1) * 128u;
+#pragma unroll
+      for (int c0 = 0; c0 < AD; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t0 + c0, v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o[c0 + c] = fmaf(o[c0 + c], alpha, __uint_as_float(v[c]));
+      }
+    };
+
+    for (int jj = 0; jj < n; ++jj) {
+      const int k0 = (kb_begin + jj) * UK;
+      mbar_wait(&s_full[jj & 1], (jj >> 1) & 1);
+      tcgen05_fence_after();
+      float s[UK];
+      {
+        const uint32_t t0 = lane_addr + (uint32_t)(jj & 1) * UK;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(t0, v0);
+        tmem_ld32(t0 + 32, v1);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          s[c] = __uint_as_float(v0[c]);
+          s[32 + c] = __uint_as_float(v1[c]);
+        }
+      }
+      const bool band = (k0 < q0 + UQ + window) && (k0 + UK > q0 - window);
+      const bool edge = (k0 + UK > len) || (q0 + UQ > len) || (k0 + UK > T);   // CTA-uniform: some mask applies
+      if (band || edge) {
+#pragma unroll
+        for (int c = 0; c < UK; ++c) {
+          const int j = k0 + c;
+          float v = s[c];
+          const int rel = j - i + window;
+          const bool inband = band && rel >= 0 && rel < R;
+          if (inband) v += rl[r * URL + rel];
+          if (!(i < len && j < len)) v = -1e4f;
+          if (j >= T) v = -INFINITY;
+          if (inband && j < T) band_row[rel] = v;      // each (i, j) of the band has one owner CTA
+          s[c] = v;
+        }
+      }
+      float mx = s[0];
+#pragma unroll
+      for (int c = 1; c < UK; ++c) mx = fmaxf(mx, s[c]);
+      const float mn = fmaxf(m, mx);
+      const float alpha = __expf(m - mn);
+      float rs = 0.f;
+      uint4 hi[UK / 8], lo[UK / 8];
+#pragma unroll
+      for (int g = 0; g < UK / 8; ++g) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = __expf(s[g * 8 + 2 * e] - mn);       // same form as the alpha / merge weights
+          const float p1 = __expf(s[g * 8 + 2 * e + 1] - mn);
+          rs += p0 + p1;
+          const __half2 h2 = __floats2half2_rn(p0, p1);
+          const float2 hf = __half22float2(h2);
+          const __half2 l2 = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+          hw[e] = *reinterpret_cast<const uint32_t*>(&h2);
+          lw[e] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        hi[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        lo[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+      l = fmaf(l, alpha, rs);
+      m = mn;
+      if (jj > 0) {                     // PV(jj-1) has finished reading the P buffer (and O(jj-1) is complete)
+        mbar_wait(&o_full[(jj - 1) & 1], ((jj - 1) >> 1) & 1);
+        tcgen05_fence_after();
+      }
+#pragma unroll
+      for (int g = 0; g < UK / 8; ++g) {
+        *reinterpret_cast<uint4*>(p_row + g * (UQ * 16)) = hi[g];
+        *reinterpret_cast<uint4*>(p_row + UP_TERM + g * (UQ * 16)) = lo[g];
+      }
+      fence_proxy_async_smem();         // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      tcgen05_fence_before();           // orders this thread's tcgen05.ld of S(jj) / O(jj-2) before the arrive
+      mbar_arrive(p_full);
+      if (jj > 0) fold_o(jj - 1, alpha_prev);
+      alpha_prev = alpha;
+    }
+    mbar_wait(&o_full[(n - 1) & 1], ((n - 1) >> 1) & 1);
+    tcgen05_fence_after();
+    fold_o(n - 1, alpha_prev);
+    // this split's running max / sum and unnormalised output
+    const size_t row = (size_t)sp * rows_all + bh * Tp + i;
+    part_m[row] = m;
+    part_l[row] = l;
+    float4* dst = reinterpret_cast<float4*>(part_o + row * AD);
+#pragma unroll
+    for (int c4 = 0; c4 < AD / 4; ++c4) dst[c4] = make_float4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) tcgen05_dealloc(tmem, U_TMEM_COLS);
+}
+
+// split count of the tcgen05 kernel: 128-query tiles, one CTA per SM, a CTA's time ~ (its key blocks + 2)
+int attn_splits_umma(int T, int heads) {
+  const int nblk = (T + UQ - 1) / UQ * (UQ / UK);
+  const int tiles = (T + UQ - 1) / UQ * heads, slots = device_sm_count();
+  int best = 1, best_cost = 1 << 30;
+  for (int ns = 1; ns <= 16 && ns <= nblk; ++ns) {
+    const int waves = (tiles * ns + slots - 1) / slots;
+    const int cost = waves * ((nblk + ns - 1) / ns + 2);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = ns;
+    }
+  }
+  return best;
+}
+
 // Key-range splits per query tile.  The grid is tiles*splits CTAs on 2 resident slots per SM and a CTA's
 // time is ~(its key blocks + 1 for prologue/epilogue): pick the split count with the fewest
 // wave-steps, e.g. T = 3435 (108 tiles, 54 key blocks): 5 splits = 2 waves x 12 instead of 3 splits =
@@ -404,18 +779,53 @@ int attn_splits(int T, int heads) {
 }  // namespace
 
 size_t rel_attention_scratch_bytes(int B, int T, int H) {
-  const int Tp = (T + AK - 1) / AK * AK;
   const int heads = H / AD > 0 ? H / AD : 1;
-  const size_t rows = (size_t)B * heads * Tp;
-  const size_t ns = (size_t)attn_splits(T, heads);
-  // q/k/v hi+lo (f16), then per split: partial output, max, sum (f32), then the band scores (f32)
-  return (size_t)6 * B * H * Tp * sizeof(__half) + (ns * rows * (AD + 2) + rows * RP) * sizeof(float) + 512;
+  // q/k/v hi+lo (f16), then per split: partial output, max, sum (f32), then the band scores (f32); sized for
+  // whichever kernel needs more (tcgen05: Tp rounded to 128; mma.sync twin: to 64, possibly more splits)
+  size_t best = 0;
+  for (int legacy = 0; legacy < 2; ++legacy) {
+    const int q = legacy ? AK : UQ;
+    const int Tp = (T + q - 1) / q * q;
+    const size_t rows = (size_t)B * heads * Tp;
+    const size_t ns = (size_t)(legacy ? attn_splits(T, heads) : attn_splits_umma(T, heads));
+    const size_t bytes = (size_t)6 * B * H * Tp * sizeof(__half) + (ns * rows * (AD + 2) + rows * RP) * sizeof(float) + 512;
+    best = bytes > best ? bytes : best;
+  }
+  return best;
 }
 
 cudaError_t launch_rel_attention_mma(const float* qkv, const float* rel_k, const float* rel_v, const int* lens,
                                      float* out, void* scratch, int B, int T, int H, int n_heads, int window,
-                                     cudaStream_t s) {
+                                     int legacy, cudaStream_t s) {
   if (H / n_heads != AD || H % n_heads || 2 * window + 1 > RP) return cudaErrorInvalidValue;
+  if (!legacy) {
+    const int Tp = (T + UQ - 1) / UQ * UQ;
+    const size_t n = (size_t)B * H * Tp;
+    __half* base = reinterpret_cast<__half*>(scratch);
+    __half *qb = base, *kb = base + 2 * n, *vb = base + 4 * n;
+    const int ns = attn_splits_umma(T, n_heads);
+    const size_t rows = (size_t)B * n_heads * Tp;
+    float* part_o = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + ((6 * n * sizeof(__half) + 255) & ~size_t(255)));
+    float* part_m = part_o + (size_t)ns * rows * AD;
+    float* part_l = part_m + (size_t)ns * rows;
+    float* band_s = part_l + (size_t)ns * rows;
+    const float qscale = rsqrtf((float)AD);
+    attn_prep_umma_kernel<<<dim3(Tp / UK, n_heads, B), 256, 0, s>>>(qkv, qb, kb, vb, T, Tp, H, n_heads, qscale);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    static DeviceOnce once;
+    e = ensure_dyn_smem(rel_attention_umma_kernel, once, U_SMEM);
+    if (e != cudaSuccess) return e;
+    rel_attention_umma_kernel<<<dim3(Tp / UQ, n_heads, B * ns), U_THREADS, U_SMEM, s>>>(
+        qb, kb, vb, qkv, rel_k, lens, part_o, part_m, part_l, band_s, B, T, Tp, H, n_heads, window, ns, qscale,
+        umma::make_idesc(UQ, UK), umma::make_idesc(UQ, AD));
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const size_t warps = (size_t)B * n_heads * T;
+    attn_merge_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(part_o, part_m, part_l, band_s, rel_v, lens, out, B, T,
+                                                                 Tp, H, n_heads, window, ns);
+    return cudaGetLastError();
+  }
   const int Tp = (T + AK - 1) / AK * AK;
   const size_t n = (size_t)B * H * Tp;
   __half* base = reinterpret_cast<__half*>(scratch);

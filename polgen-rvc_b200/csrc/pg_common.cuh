@@ -110,6 +110,7 @@ struct PlaneConvArgs {
   const float* nz_src = nullptr; const float* nz_w = nullptr; const float* nz_b = nullptr;
   int nz_k = 0, nz_stride = 1, nz_pad = 0, nz_len = 0;
   __half* out_lo = nullptr;   // with out16: the value leaves as the hi/lo f16 pair (last decoder stage)
+  int grid_cap = 0;   // > 0: at most this many persistent CTAs (pg_set_decoder_sms: SMs left free for another lane's small kernels)
   int swap = 1;   // operand-swapped MMA where the shape qualifies (C = 128, MT = 2); 0: PG_FLAG_NO_PLANES_SWAP twin
 };
 bool plane_conv_supported(const PlaneConvArgs& a);
@@ -133,6 +134,7 @@ struct PairConvArgs {
   const __half* accin16 = nullptr; const float* accin32 = nullptr;
   __half* out16 = nullptr; float out16_slope = 1.f; float* out32 = nullptr;
   float out_scale = 1.f;
+  int grid_cap = 0;   // see PlaneConvArgs::grid_cap
 };
 bool pair_conv_supported(const PairConvArgs& a);
 int pair_conv_mt(const PairConvArgs& a);
@@ -191,12 +193,13 @@ cudaError_t launch_add_layernorm(float* x, const float* y, const float* gamma, c
 cudaError_t launch_rel_attention(const float* qkv, const float* rel_k, const float* rel_v,
                                  const int* lens, float* out, int B, int T, int H, int n_heads,
                                  int window, cudaStream_t s);
-// same on tensor cores (pg_attention.cu): mma.sync f16 with two-term operand splitting (fp32-class
-// accuracy); scratch holds the split Q/K/V^T copies (rel_attention_scratch_bytes)
+// same on tensor cores (pg_attention.cu) with two-term f16 operand splitting (fp32-class accuracy): tcgen05 / TMEM
+// kernel (legacy = 0, the product path) or its mma.sync validation twin (legacy = 1, PG_FLAG_LEGACY_ATTENTION);
+// scratch holds the split, pre-tiled Q / K / V copies and the split-key partials (rel_attention_scratch_bytes)
 size_t rel_attention_scratch_bytes(int B, int T, int H);
 cudaError_t launch_rel_attention_mma(const float* qkv, const float* rel_k, const float* rel_v,
                                      const int* lens, float* out, void* scratch, int B, int T, int H,
-                                     int n_heads, int window, cudaStream_t s);
+                                     int n_heads, int window, int legacy, cudaStream_t s);
 // z_p = (m + exp(logs) * eps * 0.66666) * mask ; stats [B][T][2C] -> m, logs, z_p, z(copy)
 // eps (nullable) is [B][eps_T][C] (rows >= eps_T draw 0); otherwise Philox(seeds[b] | row_seed(seed, b)),
 // subsequence t*C + c: a row's noise does not depend on the batch around it or on the padded T

@@ -890,6 +890,7 @@ cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
   static DeviceOnce once;
   if (cudaError_t e = ensure_dyn_smem(conv_planes_kernel<MT, KC16, EPI, DBG, SWAP>, once, 227 * 1024)) return e;
   int grid = device_sm_count();
+  if (a.grid_cap > 0 && grid > a.grid_cap) grid = a.grid_cap;
   if (grid > p.total_tiles) grid = p.total_tiles;
   if (p.debug & 8) {
     unsigned int zero = 0;

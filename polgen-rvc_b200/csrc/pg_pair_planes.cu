@@ -795,6 +795,7 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
   static DeviceOnce once;
   if (cudaError_t e = ensure_dyn_smem(pair_planes_kernel<MT, C, RES_X, EPIM, HL>, once, 227 * 1024)) return e;
   int grid = device_sm_count();
+  if (a.grid_cap > 0 && grid > a.grid_cap) grid = a.grid_cap;
   if (grid > p.total_tiles) grid = p.total_tiles;
   static const int dbg_sync = [] { const char* e = getenv("PG_PAIR_SYNC"); return e ? atoi(e) : 0; }();
   if (dbg_sync & 1) cudaStreamSynchronize(s);

@@ -155,6 +155,10 @@ class Engine:
     def set_graph_cache(self, max_graphs: int):
         _lib.check(self.lib.pg_set_graph_cache(self._h, int(max_graphs)), "pg_set_graph_cache")
 
+    def set_decoder_sms(self, sms: int):
+        """cap the CTAs of the decoder's persistent kernels (0 = one per SM); see pg_set_decoder_sms"""
+        _lib.check(self.lib.pg_set_decoder_sms(self._h, int(sms)), "pg_set_decoder_sms")
+
     def infer(self, phone, lengths, pitch, f0, sid, eps_zp=None, eps_src=None, seed: int = 0,
               want_aux: bool = True, wave_out=None):
         """Time-major tensors on this engine's GPU.  Returns (wave [B][L], aux [4][B][T][C] | None).
@@ -546,12 +550,17 @@ class SynthesizerTrnMs256NSFsid(Synthesizer):
 # --------------------------------------------------------------------------
 class SegmentScheduler:
     def __init__(self, cfg: SynthConfig, weights: Dict[str, torch.Tensor], device: int = 0, lanes: int = 2,
-                 flags: int = 0, max_batch: int = 64, max_batch_frames: int = 36000):
+                 flags: int = 0, max_batch: int = 64, max_batch_frames: int = 36000, decoder_sms: int = 0):
         self.cfg = cfg
         self.device = int(device)
         self.max_batch = int(max_batch)
         self.max_batch_frames = int(max_batch_frames)     # ~430 KB of workspace per frame
         self.engines = [Engine(cfg, weights, device, flags) for _ in range(max(1, lanes))]
+        if decoder_sms > 0 and len(self.engines) > 1:
+            # leave a few SMs outside the decoder's persistent grids: the short TextEncoder / flow kernels of
+            # one lane's next clip then run beside the other lane's decoder instead of queueing behind it
+            for e in self.engines:
+                e.set_decoder_sms(decoder_sms)
         with torch.cuda.device(self.device):
             self.streams = [torch.cuda.Stream(device=self.device) for _ in self.engines]
         self._next_lane = 0

@@ -581,3 +581,37 @@ def test_f16_range_headroom_with_large_activations():
     assert bool(torch.isfinite(wave).all())
     assert snr_db(wave, o[:, 0]) >= WAVE_SNR_DB
     assert (wave - o[:, 0]).abs().max().item() <= WAVE_MAXABS
+
+
+@pytest.mark.parametrize("case", [(1, 24, None), (1, 257, None), (2, 300, [300, 171]), (1, 1000, None),
+                                  (2, 3435, [3435, 2965]), (3, 700, [700, 64, 1])],
+                         ids=lambda c: f"B{c[0]}T{c[1]}")
+def test_tcgen05_attention_vs_mma_twin_and_oracle(case):
+    """TextEncoder attention on tcgen05 / TMEM (128-query tiles, S and O accumulators in TMEM, softmax threads
+    own one row each, split keys + merge) against its mma.sync twin (PG_FLAG_LEGACY_ATTENTION) on the same
+    inputs -- same split-precision products, so the latents agree far inside the 1e-3 bound -- and against the
+    oracle's TextEncoder.  Sizes cover a single partial tile, several key splits, ragged rows (a row shorter
+    than one tile, a row that ends inside a key block) and the bench clip's two segments as one batch."""
+    import polgen_rvc_b200 as pg
+    from polgen_rvc_b200 import _lib
+    from oracle import rvc_oracle as orc
+    B, T, lens = case
+    cfg = pg.CONFIGS["v2-48k"]
+    sd = pg.synth_weights(cfg, seed=5)
+    phone, lengths, pitch, f0, sid = pg.synth_inputs(cfg, B, T, seed=5)
+    if lens is not None:
+        lengths = torch.tensor(lens)
+    d = _dev()
+    new = _engine(cfg, sd)
+    m_new, l_new = new.text_encoder(phone.to(d), lengths.to(d), pitch.to(d))
+    twin = _engine(cfg, sd, _lib.PG_FLAG_LEGACY_ATTENTION)
+    m_old, l_old = twin.text_encoder(phone.to(d), lengths.to(d), pitch.to(d))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(m_new).all()) and bool(torch.isfinite(l_new).all())
+    assert latent_err(m_new.cpu(), m_old.cpu()) <= 2e-5
+    assert latent_err(l_new.cpu(), l_old.cpu()) <= 2e-5
+    if T <= 1000:      # the CPU oracle's O(T^2) attention: seconds at T = 1000
+        W = orc.fold_weight_norm(sd)
+        om, ol, _ = orc.text_encoder(W, cfg, phone, pitch, lengths)
+        assert latent_err(m_new.cpu().transpose(1, 2), om) <= LATENT_REL
+        assert latent_err(l_new.cpu().transpose(1, 2), ol) <= LATENT_REL
