@@ -64,6 +64,7 @@ struct StageW {
   int up_pad = 0;      // left pad (frames) of the polyphase conv
   float *noise_w = nullptr, *noise_b = nullptr;   // [k][C], [C]
   int noise_k = 1, noise_stride = 1, noise_pad = 0;
+  ConvW noise_tc;      // long noise conv (k > 8 taps) as a tensor-core conv over strided source frames: [taps][C][192] f16
   int C = 0, u = 1;
   std::vector<ConvW> c1, c2;   // [n_kernels * n_dil]
 };
@@ -877,9 +878,19 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
         }
         PG_TRY(run_plane_conv(h, s, a, S.up));
       }
-      if (!fuse_noise(h, S))
-        PG_LAUNCH(h, launch_noise_inject_planes(x0, DT_F16, x0, nullptr, source, S.noise_w, S.noise_b, B, (int)L, C,
-                                                (int)Lsrc, S.noise_k, S.noise_stride, S.noise_pad, SL, s));
+      if (!fuse_noise(h, S)) {
+        if (S.noise_tc.w16 && !(h->cfg.flags & (PG_FLAG_NO_NOISE_FUSION | PG_FLAG_KEEP_TAPS))) {
+          // long noise conv on the tensor cores: strided source frames (split operands) -> conv accumulated onto x0
+          PG_LAUNCH(h, launch_source_frames(source, tmp, B, (int)L, (int)Lsrc, S.noise_stride, S.noise_pad, s));
+          PlaneConvArgs a;
+          a.x = tmp; a.B = B; a.L = (int)L; a.pad = 0; a.tlen = tlen; a.len_mul = mul;
+          a.accin16 = x0; a.out16 = x0; a.out16_slope = SL;
+          PG_TRY(run_plane_conv(h, s, a, S.noise_tc));
+        } else {
+          PG_LAUNCH(h, launch_noise_inject_planes(x0, DT_F16, x0, nullptr, source, S.noise_w, S.noise_b, B, (int)L, C,
+                                                  (int)Lsrc, S.noise_k, S.noise_stride, S.noise_pad, SL, s));
+        }
+      }
       PG_TRY(record_tap_planes(h, s, "dec.ups" + std::to_string(i), x0, DT_F16, INV, B, L, C));
       for (int j = 0; j < nk; ++j) {
         const int ksz = c.resblock_kernel_sizes[j];
@@ -1233,6 +1244,29 @@ int pg_finalize(pg_handle h) {
         for (int j = 0; j < S.noise_k; ++j) wn[(size_t)j * cout + co] = W->data[(size_t)co * S.noise_k + j];
       PG_TRY(upload(h, wn, &S.noise_w));
       PG_TRY(upload_named(h, nc + "bias", {cout}, &S.noise_b));
+      // Tensor-core form of a long noise conv (stage 0: 64 / 80 taps; on CUDA cores it was the slowest non-GEMM
+      // kernel of the decode): `taps` taps over frames of `stride` source samples, operands split into two f16
+      // terms -- channel segments [hi(src) | lo(src) | hi(src)] x weights [hi(w) | hi(w) | lo(w)].
+      if (S.noise_k > 8 && stride <= NOISE_TC_SEG && cout % 32 == 0) {
+        const int taps = (S.noise_k + stride - 1) / stride, CI = 3 * NOISE_TC_SEG;
+        std::vector<__half> w16((size_t)taps * cout * CI, __float2half_rn(0.f));
+        for (int tap = 0; tap < taps; ++tap)
+          for (int co = 0; co < cout; ++co)
+            for (int ci = 0; ci < stride && tap * stride + ci < S.noise_k; ++ci) {
+              const float wv = wn[(size_t)(tap * stride + ci) * cout + co];
+              const __half hi = __float2half_rn(wv), lo = __float2half_rn(wv - __half2float(hi));
+              __half* row = &w16[((size_t)tap * cout + co) * CI];
+              row[ci] = hi;
+              row[NOISE_TC_SEG + ci] = hi;
+              row[2 * NOISE_TC_SEG + ci] = lo;
+            }
+        PG_TRY(upload(h, w16, &S.noise_tc.w16));
+        S.noise_tc.bias = S.noise_b;
+        S.noise_tc.Cin = CI;
+        S.noise_tc.Cout = cout;
+        S.noise_tc.K = taps;
+        S.noise_tc.algo_taps = (double)S.noise_k / CI;   // algorithmic FLOPs: 2 * L * C * k
+      }
     }
     const int nk = c.n_resblock_kernels, nd = c.n_dilations;
     S.c1.resize(nk * nd);

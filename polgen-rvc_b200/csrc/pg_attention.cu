@@ -626,10 +626,16 @@ __global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
       }
       named_bar_sync(1, UQ);
       for (int rel = 0; rel < R; ++rel) {
-        float s = 0.f;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // four chains: a single 96-term chain is latency-bound
+        const float* e = ek + rel * AD;
 #pragma unroll
-        for (int c = 0; c < AD; ++c) s = fmaf(q[c], ek[rel * AD + c], s);
-        rl[r * URL + rel] = s;
+        for (int c = 0; c < AD; c += 4) {
+          s0 = fmaf(q[c], e[c], s0);
+          s1 = fmaf(q[c + 1], e[c + 1], s1);
+          s2 = fmaf(q[c + 2], e[c + 2], s2);
+          s3 = fmaf(q[c + 3], e[c + 3], s3);
+        }
+        rl[r * URL + rel] = (s0 + s1) + (s2 + s3);
       }
       named_bar_sync(1, UQ);     // the table's shared memory becomes the P buffer
     }
@@ -684,12 +690,12 @@ __global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
           s[c] = v;
         }
       }
-      float mx = s[0];
+      float mx4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-      for (int c = 1; c < UK; ++c) mx = fmaxf(mx, s[c]);
-      const float mn = fmaxf(m, mx);
+      for (int c = 4; c < UK; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], s[c]);
+      const float mn = fmaxf(m, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
       const float alpha = __expf(m - mn);
-      float rs = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
       uint4 hi[UK / 8], lo[UK / 8];
 #pragma unroll
       for (int g = 0; g < UK / 8; ++g) {
@@ -698,7 +704,7 @@ __global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
         for (int e = 0; e < 4; ++e) {
           const float p0 = __expf(s[g * 8 + 2 * e] - mn);       // same form as the alpha / merge weights
           const float p1 = __expf(s[g * 8 + 2 * e + 1] - mn);
-          rs += p0 + p1;
+          rs4[e] += p0 + p1;
           const __half2 h2 = __floats2half2_rn(p0, p1);
           const float2 hf = __half22float2(h2);
           const __half2 l2 = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
@@ -708,7 +714,7 @@ __global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
         hi[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         lo[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
-      l = fmaf(l, alpha, rs);
+      l = fmaf(l, alpha, (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       m = mn;
       if (jj > 0) {                     // PV(jj-1) has finished reading the P buffer (and O(jj-1) is complete)
         mbar_wait(&o_full[(jj - 1) & 1], ((jj - 1) >> 1) & 1);

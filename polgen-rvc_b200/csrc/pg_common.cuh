@@ -155,6 +155,11 @@ cudaError_t launch_planes_to_nlc_f16(const __half* x, __half* y, int B, int L, i
 cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, __half* lo16, const float* src,
                                        const float* wn, const float* bn, int B, int L, int C, int Lsrc, int k,
                                        int stride, int pad, float slope, cudaStream_t s);
+// strided source frames as split f16 operand planes [B][3*NOISE_TC_SEG/8][L][8] (hi | lo | hi segments) for the
+// tensor-core form of a long noise conv (pg_planes.cu)
+constexpr int NOISE_TC_SEG = 64;
+cudaError_t launch_source_frames(const float* src, __half* xs, int B, int L, int Lsrc, int stride, int pad,
+                                 cudaStream_t s);
 // wave = tanh(conv_post(lrelu(x, in_slope))) over planes (f16 or f32)
 // tlen (nullable): rows >= tlen[b]*len_mul read as zero (hard end of row b)
 cudaError_t launch_conv_post_planes(const void* x, DType dt, const float* w /*[K][C]*/, float* wave, int B,

@@ -49,7 +49,8 @@ constexpr int EPI_GROUPS = EPI_WARPS / 4;   // warps per TMEM lane quarter
 constexpr int EPI_COLS = 16;                // accumulator columns per epilogue item
 // epilogue specialisations: the two shapes that make up 5/6 of the ResBlock convs get straight-line code
 constexpr int EPI_GENERIC = 0, EPI_C1 = 1 /* y16 = lrelu(acc + bias) */, EPI_C2 = 2 /* y16 = lrelu(acc + bias + raw(res16)) */,
-              EPI_C3 = 3 /* last conv2 of a ResBlock: y16 = lrelu((acc + bias + raw(res16)) * scale [+ accin16]) */;
+              EPI_C3 = 3 /* last conv2 of a ResBlock: y16 = lrelu((acc + bias + raw(res16)) * scale [+ accin16]) */,
+              EPI_UPS = 4 /* polyphase upsampler / plain conv over several Cout tiles: y16 = lrelu(acc + bias [+ accin16]) at row t*row_mul + phase */;
 constexpr int NTHREADS = (EPI_WARP0 + EPI_WARPS) * 32;
 constexpr int GROUP_PLANES = 16;   // 128 channels per activation-ring slot
 constexpr int NZ_MAXK = 8;         // longest noise conv fused into an upsampler epilogue (taps)
@@ -481,6 +482,73 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       if (lane == 0) mbar_arrive(&acc_empty[accb]);
       ++t_cnt;
     }
+  } else if (warp >= EPI_WARP0 && EPI == EPI_UPS) {
+    // ===== straight-line epilogue of the polyphase upsamplers (and of any bias-only conv with several Cout tiles):
+    // per item tcgen05.ld 16 columns -> + bias (shared memory) [+ accin16] -> leaky-ReLU -> 2 x 16 B stores at output
+    // row t*row_mul + phase.  The generic epilogue spent ~340 instructions per item on run-time switches and fetched
+    // the bias of a > 1024-column layer through __ldg (ncu: 6.8 warps stalled on long scoreboard per issue).
+    const int quarter = warp & 3, grp = (warp - EPI_WARP0) >> 2;
+    const int n_cb = p.NT / EPI_COLS, items = MT * n_cb, cb_shift = 31 - __clz(n_cb);
+    const int CP = p.Cout_real / 8;
+    const int cout_shift = 31 - __clz(p.Cout_real);
+    const float slope = p.out16_slope;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t t_cnt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(tile, p);
+      const int t0 = tc.rt * (BM * MT);
+      if (t0 >= row_end(p, tc.b)) continue;
+      const int n0 = tc.ntile * p.NT;
+      const uint32_t accb = t_cnt & 1u;
+      const size_t plane0 = (size_t)tc.b * CP;
+      const int qbase = t0 + quarter * 32 + lane;
+      mbar_wait(&acc_full[accb], (t_cnt >> 1) & 1u);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int it = grp; it < items; it += EPI_GROUPS) {
+        const int m = it >> cb_shift, cb = it & (n_cb - 1);
+        const int q = qbase + m * BM;
+        const int c0 = cb * EPI_COLS;
+        const int n = n0 + c0;                             // GEMM column -> (phase r, channel co)
+        const int r = n >> cout_shift, co = n & (p.Cout_real - 1);
+        const size_t off0 = (plane0 + (co >> 3)) * p.L_out + (size_t)(q < p.L ? q : 0) * p.row_mul + r;
+        uint4 ain[2];
+        if (p.accin16 && q < p.L) {
+          ain[0] = *(reinterpret_cast<const uint4*>(p.accin16) + off0);
+          ain[1] = *(reinterpret_cast<const uint4*>(p.accin16) + off0 + p.L_out);
+        }
+        float bv[EPI_COLS];
+#pragma unroll
+        for (int i = 0; i < EPI_COLS / 4; ++i) {
+          const float4 b4 = *(reinterpret_cast<const float4*>(bias_s + n) + i);
+          bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
+        }
+        uint32_t acc[EPI_COLS];
+        tmem_ld16(lane_taddr + accb * (uint32_t)(MT * p.NT) + (uint32_t)(m * p.NT + c0), acc);
+        if (q < p.L) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out16) + off0;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[j * 8 + i]) + bv[j * 8 + i];
+            if (p.accin16) {
+              float av[8];
+              unpack8(ain[j], av);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += av[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * slope);     // slope <= 1 (1: raw)
+            dst[(size_t)j * p.L_out] = pack8(v);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[accb]);
+      ++t_cnt;
+    }
   } else if (warp >= EPI_WARP0 && EPI != EPI_GENERIC) {
     // ===== specialised epilogue (EPI_C1 / EPI_C2): one Cout tile, row_mul == 1, bias in shared memory,
     // f16 L-form output; per item: tcgen05.ld 16 columns -> + bias (+ residual) -> leaky-ReLU -> 2 x 16 B.
@@ -808,7 +876,7 @@ bool make_plan(const PlaneConvArgs& a, Plan* out) {
   static const int forced_mt = env_int("PG_PLANES_MT", 0), forced_res = env_int("PG_PLANES_RESIDENT", -1),
                    forced_stages = env_int("PG_PLANES_STAGES", 0), forced_slots = env_int("PG_PLANES_SLOTS", 0);
   const bool can_reside = a.N == NT && !a.tapmask && forced_res != 0;
-  const int bias_smem = a.bias && a.N <= 1024 ? 1 : 0;
+  const int bias_smem = a.bias && a.N <= 4096 ? 1 : 0;
   const size_t fixed = 1024 + 1024 + (bias_smem ? 4 * (size_t)a.N + 16 : 0) +      // alignment slack, barriers, bias
                        (a.nz_src ? 4 * (size_t)(a.nz_k + 1) * a.Cout_real : 0);     // fused noise conv: bias + [k][C] weights
   const size_t budget = (size_t)227 * 1024;
@@ -950,6 +1018,10 @@ cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s) {
     if (!a.accin16 && a.out_scale == 1.f) epi = a.res16 ? EPI_C2 : EPI_C1;
     else if (a.res16) epi = EPI_C3;
   }
+  // polyphase upsamplers / bias-only convs over several Cout tiles (also the tensor-core noise conv: + accin16)
+  if (epi == EPI_GENERIC && !dbg && pl.bias_smem && !a.bbias && !a.res16 && !a.res32 && !a.accin32 && !a.nz_src &&
+      !a.out_lo && !a.out32 && a.out16 && a.out16_slope <= 1.f && a.out_scale == 1.f)
+    epi = EPI_UPS;
   // operand-swapped variant for the C = 128 ResBlock convs: +13 % on the conv1 shapes (1190 -> 1345 TFLOP/s at
   // k = 11, profiles/r02b), neutral on conv2 -- on by default, PG_FLAG_NO_PLANES_SWAP / PG_PLANES_SWAP=0 is the twin
   static const bool swap_on = env_int("PG_PLANES_SWAP", 1) != 0;
@@ -961,7 +1033,8 @@ cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s) {
              : (epi == EPI_C1 ? launch_t<MT_, KC16_, EPI_C1, false>(a, pl, s)          \
                               : (epi == EPI_C2 ? launch_t<MT_, KC16_, EPI_C2, false>(a, pl, s) \
                               : (epi == EPI_C3 ? launch_t<MT_, KC16_, EPI_C3, false>(a, pl, s) \
-                                               : launch_t<MT_, KC16_, EPI_GENERIC, false>(a, pl, s))))
+                              : (epi == EPI_UPS ? launch_t<MT_, KC16_, EPI_UPS, false>(a, pl, s) \
+                                               : launch_t<MT_, KC16_, EPI_GENERIC, false>(a, pl, s)))))
   if (pl.KC == 64) {
     switch (pl.MT) {
       case 1: PG_DISPATCH(1, 4);

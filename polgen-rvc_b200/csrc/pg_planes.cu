@@ -223,17 +223,13 @@ cudaError_t launch_noise_tiled(__half* x, const float* src, const float* wn, con
   return cudaGetLastError();
 }
 
-// nsf.py:142-143  wave = tanh(conv_post(leaky_relu(x)))  (Cout = 1, no bias).  One block = 256 output samples: the
-// (256 + K - 1)-row window of every plane is staged RAW in shared memory by 16-byte cp.async copies (all in flight at
-// once, no register staging; rows outside [0, hard row end) are zero-filled by the copy itself), then one thread per
-// sample walks the K x C taps from shared memory, applying the leaky-ReLU on the way.  (The round-1 kernel re-read
-// every row K times through L1.)
+// nsf.py:142-143  wave = tanh(conv_post(leaky_relu(x)))  (Cout = 1, no bias).  One block = 256 output samples.
+// Row-wise form: wave[t] = sum_j d_j[t + j - K/2] with d_j[n] = sum_c w[j][c] * lrelu(x[n][c]), so a thread reads ITS
+// row once from global memory (plane rows of consecutive lanes are contiguous: coalesced, no staging), applies the
+// leaky-ReLU once per element and keeps K running dot products; the K partials per row go through shared memory and
+// a second step adds the K shifted ones.  (The round-2 kernel staged the raw window in shared memory and re-applied
+// the activation for every tap: 3x the instructions and bank-conflicted 32 B row reads -- 232 us for 393 MB.)
 constexpr int CPB = 256;
-__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
-  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  const int n = valid ? 16 : 0;       // src-size 0: the 16 destination bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
 template <typename T, int K>
 __global__ void __launch_bounds__(CPB) conv_post_planes_kernel(const T* __restrict__ x,
                                                                const float* __restrict__ w /*[K][C]*/,
@@ -241,40 +237,47 @@ __global__ void __launch_bounds__(CPB) conv_post_planes_kernel(const T* __restri
                                                                float in_slope, const int* __restrict__ tlen,
                                                                int len_mul) {
   extern __shared__ __align__(16) float cps[];
-  constexpr int RB = 8 * (int)sizeof(T);          // bytes per (row, plane): 32 (f32) / 16 (f16)
-  constexpr int PIECES = RB / 16;
   const int CP = C / 8, ROWS = CPB + K - 1;
-  float* ws = cps;                                // [K][C]
-  uint8_t* xs = reinterpret_cast<uint8_t*>(cps + K * C);   // [CP][ROWS] x RB bytes, raw
+  float* ws = cps;                 // [K][C]
+  float* ds = cps + K * C;         // [K][ROWS]
   const int b = blockIdx.y, t0 = blockIdx.x * CPB;
   const int t_hi = tlen ? min(L, tlen[b] * len_mul) : L;   // hard end of the row
-  const uint8_t* xb = reinterpret_cast<const uint8_t*>(x) + (size_t)b * CP * (size_t)L * RB;
-  for (int i = threadIdx.x; i < CP * ROWS * PIECES; i += CPB) {
-    const int piece = i % PIECES, rr = i / PIECES;
-    const int pl = rr / ROWS, r = rr - pl * ROWS;
-    const int n = t0 + r - K / 2;
-    const bool valid = n >= 0 && n < t_hi;
-    cp_async16_zfill(xs + (size_t)rr * RB + piece * 16, xb + ((size_t)pl * L + (valid ? n : 0)) * RB + piece * 16, valid);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = threadIdx.x; i < K * C; i += CPB) ws[i] = w[i];
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const T* xb = x + (size_t)b * CP * (size_t)L * 8;
+  for (int rr = threadIdx.x; rr < ROWS; rr += CPB) {
+    const int n = t0 + rr - K / 2;
+    float acc[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] = 0.f;
+    if (n >= 0 && n < t_hi) {
+#pragma unroll 4
+      for (int pl = 0; pl < CP; ++pl) {
+        float v[8];
+        load8(xb + ((size_t)pl * L + n) * 8, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], v[q] * in_slope);   // slope <= 1
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const float4 w0 = *reinterpret_cast<const float4*>(ws + j * C + pl * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(ws + j * C + pl * 8 + 4);
+          float a = acc[j];
+          a = fmaf(w0.x, v[0], a); a = fmaf(w0.y, v[1], a); a = fmaf(w0.z, v[2], a); a = fmaf(w0.w, v[3], a);
+          a = fmaf(w1.x, v[4], a); a = fmaf(w1.y, v[5], a); a = fmaf(w1.z, v[6], a); a = fmaf(w1.w, v[7], a);
+          acc[j] = a;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) ds[j * ROWS + rr] = acc[j];
+  }
   __syncthreads();
   const int t = t0 + threadIdx.x;
   if (t >= L) return;
-  float acc = 0.f;
-  for (int pl = 0; pl < CP; ++pl) {
-    const T* row = reinterpret_cast<const T*>(xs + ((size_t)pl * ROWS + threadIdx.x) * RB);
+  float out = 0.f;
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-      float v[8];
-      load8(row + j * 8, v);
-      const float* wj = ws + j * C + pl * 8;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc = fmaf(wj[q], fmaxf(v[q], v[q] * in_slope), acc);   // slope <= 1
-    }
-  }
-  wave[(size_t)b * L + t] = t < t_hi ? tanhf(acc) : 0.f;
+  for (int j = 0; j < K; ++j) out += ds[j * ROWS + threadIdx.x + j];
+  wave[(size_t)b * L + t] = t < t_hi ? tanhf(out) : 0.f;
 }
 
 unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
@@ -341,11 +344,48 @@ cudaError_t launch_noise_inject_planes(void* x, DType dt, __half* a16, __half* l
   return cudaGetLastError();
 }
 
+// Operand planes of the long noise convs on the tensor cores (noise_convs[0]: k = 2*stride = 64 / 80 taps).
+//   x[t][co] += b[co] + sum_j w[j][co] * src[t*stride + j - pad]
+// is a `taps`-tap conv (taps = k / stride) over the strided frames  X[t][ci] = src[t*stride + ci - pad], ci < stride.
+// The frames are written as f16 planes [B][3*SEG/8][L][8] in three segments of SEG = 64 channels: hi(src), lo(src)
+// (the f16 rounding remainder) and hi(src) again -- multiplied by the weight segments (hi(w), hi(w), lo(w)) the three
+// products of a two-term split, so the noise term keeps fp32-class accuracy (~2^-22) like the CUDA-core kernel it
+// replaces.  One thread = one 16 B store; t is the fastest index.
+__global__ void __launch_bounds__(256) source_frames_kernel(const float* __restrict__ src, __half* __restrict__ xs,
+                                                            int B, int L, int Lsrc, int stride, int pad) {
+  constexpr int PL = 3 * NOISE_TC_SEG / 8;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * PL * L) return;
+  const int t = (int)(i % L);
+  const int p = (int)((i / L) % PL);
+  const int b = (int)(i / ((size_t)L * PL));
+  const int seg = p / (NOISE_TC_SEG / 8), c0 = (p % (NOISE_TC_SEG / 8)) * 8;
+  const float* sp = src + (size_t)b * Lsrc;
+  __align__(16) __half out[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int ci = c0 + e;
+    const long long n = (long long)t * stride + ci - pad;
+    const float v = (ci < stride && n >= 0 && n < Lsrc) ? sp[n] : 0.f;
+    const __half hi = __float2half_rn(v);
+    out[e] = seg == 1 ? __float2half_rn(v - __half2float(hi)) : hi;
+  }
+  *reinterpret_cast<uint4*>(xs + i * 8) = *reinterpret_cast<const uint4*>(out);
+}
+
+cudaError_t launch_source_frames(const float* src, __half* xs, int B, int L, int Lsrc, int stride, int pad,
+                                 cudaStream_t s) {
+  if (stride < 1 || stride > NOISE_TC_SEG) return cudaErrorInvalidValue;
+  const size_t n = (size_t)B * (3 * NOISE_TC_SEG / 8) * L;
+  source_frames_kernel<<<blocks_for(n), 256, 0, s>>>(src, xs, B, L, Lsrc, stride, pad);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_conv_post_planes(const void* x, DType dt, const float* w, float* wave, int B, int L, int C,
                                     int K, float in_slope, const int* tlen, int len_mul, cudaStream_t s) {
   if (K != 7 || C % 8 || C > 256) return cudaErrorInvalidValue;
   dim3 grid((L + CPB - 1) / CPB, B);
-  const size_t smem = sizeof(float) * (size_t)K * C + (size_t)(C / 8) * (CPB + K - 1) * (dt == DT_F32 ? 32 : 16);
+  const size_t smem = sizeof(float) * ((size_t)K * C + (size_t)K * (CPB + K - 1));
   if (in_slope > 1.f) return cudaErrorInvalidValue;
   if (smem > 48 * 1024) {
     static DeviceOnce o32, o16;
