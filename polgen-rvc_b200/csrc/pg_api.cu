@@ -788,15 +788,14 @@ int run_pair_conv(pg_handle h, cudaStream_t s, PairConvArgs a, const ConvW& w1, 
   return PG_OK;
 }
 
-// NSF source injection inside the upsampler's epilogue (the kernel supports noise convs of up to 8 taps).
-// Measured on the bench clip (profiles/r02_noise_fusion.md): the polyphase upsamplers are epilogue-bound (K = 3
-// taps of MMA per 64 .. 1280 output columns, stores scattered over the u output phases), so every fused tap costs
-// about what the separate bandwidth kernel did: k = 1 (last stage, where fusion also removes the fp32 round trip
-// in front of the hi/lo split) wins 0.02 ms per step, k = 4 is even, k = 8 loses 0.04 ms, k = 80 keeps its
-// shared-memory tiled kernel.  Default: fuse k <= 1; PG_NOISE_FUSE_MAXK=4|8 fuses the other stages too.
+// NSF source injection inside the upsampler's epilogue (noise convs of up to 8 taps; the 64 / 80-tap conv of stage 0
+// runs as a tensor-core conv over strided source frames, see StageW::noise_tc).  Round 2 measured fusion as a wash
+// for k = 4 / 8 because the generic epilogue was already issue-bound; with the straight-line EPI_UPS epilogue
+// (profiles/r03_*) every fused stage wins: per clip k = 8: 272 + 196 -> 378 us, k = 4: 99 + 128 -> 191 us, and the
+// step goes 11.47 -> 11.16 ms.  Default: fuse k <= 8; PG_NOISE_FUSE_MAXK=1|4 restricts it (A/B aid).
 bool fuse_noise(pg_handle h, const StageW& S) {
   const char* e = getenv("PG_NOISE_FUSE_MAXK");   // read per call: tests flip it inside one process
-  const int max_k = e ? atoi(e) : 1;
+  const int max_k = e ? atoi(e) : 8;
   return !(h->cfg.flags & (PG_FLAG_KEEP_TAPS | PG_FLAG_NO_NOISE_FUSION)) && S.noise_k <= max_k;
 }
 

@@ -35,6 +35,36 @@ inline cudaError_t ensure_dyn_smem(Kernel kernel, DeviceOnce& once, int bytes) {
 // SM count of the CURRENT device (cached per device)
 int device_sm_count();
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------
+// A decode is ~185 short launches in one stream.  The tensor-core kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: every CTA executes griddepcontrol.launch_dependents first thing,
+// so the NEXT kernel of the stream is launched while this one runs; its CTAs get an SM as soon as one of ours exits,
+// run their prologue (barrier init, TMEM allocation, tensor-map prefetch, bias staging, weight TMA -- constants only)
+// and block in griddepcontrol.wait until this grid has completed and flushed.  Only the roles that touch activations
+// in global memory wait; the weight producer and the MMA issuer never do.  Launch latency and prologue of every
+// kernel thus overlap the tail of its predecessor.  Kernels launched the plain way remain full barriers, and
+// griddepcontrol.wait is a no-op in a kernel launched without the attribute.  PG_PDL=0 disables the attribute.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // thread-local error string behind pg_last_error()
 void set_error(const std::string& msg);
 

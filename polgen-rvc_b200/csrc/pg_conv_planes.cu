@@ -75,6 +75,7 @@ struct PlaneParams {
   int r_slots, r_slot_bytes, res_cols;  // residual ring: one slot = 128 rows x res_cols columns
   int bias_smem;                        // bias[N] staged in shared memory (N <= 1024)
   uint32_t idesc;
+  int nz_prefetch;                      // EPI_UPS: fetch the noise conv's source samples one item ahead (PG_NZ_PREFETCH, A/B aid)
   int debug;   // PG_PLANES_DEBUG bitmask (timing experiments only): 1 no A copies, 2 no epilogue I/O, 4 no MMA,
                // 8 trace, 16 consumers skip their waits (free-running roles), 32 epilogue idle, 64 no producers
 };
@@ -133,6 +134,7 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 template <int MT, int KC16, int EPI, bool DBG, bool SWAP = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p) {
+  pdl_launch_dependents();     // the next kernel of the stream may launch and run its prologue (pg_common.cuh)
   const int dbg = DBG ? p.debug : 0;   // production instantiation: every debug switch folds away
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -189,6 +191,9 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) trace(dbg, 4, 0, 0);
+  // activations in global memory belong to the predecessor until it has completed; the weight producer and the MMA
+  // issuer touch constants / shared memory / TMEM only and run ahead
+  if (warp != TMA_WARP && warp != MMA_WARP) pdl_wait();
 
   const int chunks_per_group = p.PG * 8 / p.KC;
   const int n_chunks = p.Cin / p.KC;
@@ -502,6 +507,21 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
       const uint32_t accb = t_cnt & 1u;
       const size_t plane0 = (size_t)tc.b * CP;
       const int qbase = t0 + quarter * 32 + lane;
+      // source samples under the noise conv's taps of item `it` (this lane's output row); fetched one item ahead --
+      // the first one before the accumulator wait -- so their L2 latency hides behind the previous item
+      const float* nz_sp = p.nz_src ? p.nz_src + (size_t)tc.b * p.nz_len : nullptr;
+      auto load_sv = [&](int it, float (&sv)[NZ_MAXK]) {
+        const int q = qbase + (it >> cb_shift) * BM;
+        const int r = (n0 + (it & (n_cb - 1)) * EPI_COLS) >> cout_shift;
+        const int s0 = (q * p.row_mul + r) * p.nz_stride - p.nz_pad;
+#pragma unroll
+        for (int jj = 0; jj < NZ_MAXK; ++jj) {
+          const int sn = s0 + jj;
+          sv[jj] = (jj < p.nz_k && q < p.L && sn >= 0 && sn < p.nz_len) ? __ldg(nz_sp + sn) : 0.f;
+        }
+      };
+      float sv_next[NZ_MAXK];
+      if (nz_sp && p.nz_prefetch && grp < items) load_sv(grp, sv_next);
       mbar_wait(&acc_full[accb], (t_cnt >> 1) & 1u);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -512,6 +532,14 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         const int n = n0 + c0;                             // GEMM column -> (phase r, channel co)
         const int r = n >> cout_shift, co = n & (p.Cout_real - 1);
         const size_t off0 = (plane0 + (co >> 3)) * p.L_out + (size_t)(q < p.L ? q : 0) * p.row_mul + r;
+        float sv[NZ_MAXK];
+        if (nz_sp && p.nz_prefetch) {
+#pragma unroll
+          for (int jj = 0; jj < NZ_MAXK; ++jj) sv[jj] = sv_next[jj];
+          if (it + EPI_GROUPS < items) load_sv(it + EPI_GROUPS, sv_next);
+        } else if (nz_sp) {
+          load_sv(it, sv);
+        }
         uint4 ain[2];
         if (p.accin16 && q < p.L) {
           ain[0] = *(reinterpret_cast<const uint4*>(p.accin16) + off0);
@@ -532,6 +560,24 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[j * 8 + i]) + bv[j * 8 + i];
+            if (p.nz_src) {     // x + noise_convs[i](har_source): [bias | k x C] weights in shared memory
+              const float* wb = nz_s + co + j * 8;
+              const float4 b0 = *reinterpret_cast<const float4*>(wb), b1 = *reinterpret_cast<const float4*>(wb + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+#pragma unroll
+              for (int jj = 0; jj < NZ_MAXK; ++jj) {
+                if (jj < p.nz_k) {
+                  const float4 w0 = *reinterpret_cast<const float4*>(wb + (size_t)(jj + 1) * p.Cout_real);
+                  const float4 w1 = *reinterpret_cast<const float4*>(wb + (size_t)(jj + 1) * p.Cout_real + 4);
+                  const float x = sv[jj];
+                  v[0] = fmaf(w0.x, x, v[0]); v[1] = fmaf(w0.y, x, v[1]);
+                  v[2] = fmaf(w0.z, x, v[2]); v[3] = fmaf(w0.w, x, v[3]);
+                  v[4] = fmaf(w1.x, x, v[4]); v[5] = fmaf(w1.y, x, v[5]);
+                  v[6] = fmaf(w1.z, x, v[6]); v[7] = fmaf(w1.w, x, v[7]);
+                }
+              }
+            }
             if (p.accin16) {
               float av[8];
               unpack8(ain[j], av);
@@ -540,7 +586,15 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * slope);     // slope <= 1 (1: raw)
-            dst[(size_t)j * p.L_out] = pack8(v);
+            const uint4 hi = pack8(v);
+            dst[(size_t)j * p.L_out] = hi;
+            if (p.out_lo) {       // hi/lo stream of the last stage: the f16 rounding remainder
+              float hv[8];
+              unpack8(hi, hv);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] -= hv[i];
+              *(reinterpret_cast<uint4*>(p.out_lo) + off0 + (size_t)j * p.L_out) = pack8(v);
+            }
           }
         }
       }
@@ -955,6 +1009,8 @@ cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
   p.idesc = SWAP ? make_idesc(pl.NT, BM * MT) : make_idesc(BM, pl.NT);
   static const int dbg = env_int("PG_PLANES_DEBUG", 0);
   p.debug = dbg;
+  static const int nz_prefetch = env_int("PG_NZ_PREFETCH", 1);
+  p.nz_prefetch = nz_prefetch;
   static DeviceOnce once;
   if (cudaError_t e = ensure_dyn_smem(conv_planes_kernel<MT, KC16, EPI, DBG, SWAP>, once, 227 * 1024)) return e;
   int grid = device_sm_count();
@@ -964,7 +1020,7 @@ cudaError_t launch_t(const PlaneConvArgs& a, const Plan& pl, cudaStream_t s) {
     unsigned int zero = 0;
     cudaMemcpyToSymbol(g_ptrace_n, &zero, sizeof(zero));
   }
-  conv_planes_kernel<MT, KC16, EPI, DBG, SWAP><<<grid, NTHREADS, pl.smem, s>>>(wmap, p);
+  if (cudaError_t e = launch_pdl(conv_planes_kernel<MT, KC16, EPI, DBG, SWAP>, dim3(grid), dim3(NTHREADS), pl.smem, s, wmap, p)) return e;
   if (p.debug & 8) {
     cudaDeviceSynchronize();
     static unsigned long long host[4096];
@@ -1019,9 +1075,9 @@ cudaError_t launch_conv_planes(const PlaneConvArgs& a, cudaStream_t s) {
     else if (a.res16) epi = EPI_C3;
   }
   // polyphase upsamplers / bias-only convs over several Cout tiles (also the tensor-core noise conv: + accin16)
-  if (epi == EPI_GENERIC && !dbg && pl.bias_smem && !a.bbias && !a.res16 && !a.res32 && !a.accin32 && !a.nz_src &&
-      !a.out_lo && !a.out32 && a.out16 && a.out16_slope <= 1.f && a.out_scale == 1.f)
-    epi = EPI_UPS;
+  if (epi == EPI_GENERIC && !dbg && pl.bias_smem && !a.bbias && !a.res16 && !a.res32 && !a.accin32 && !a.out32 &&
+      a.out16 && a.out16_slope <= 1.f && a.out_scale == 1.f)
+    epi = EPI_UPS;     // optional: fused noise conv (nz_*), accin16, hi/lo output
   // operand-swapped variant for the C = 128 ResBlock convs: +13 % on the conv1 shapes (1190 -> 1345 TFLOP/s at
   // k = 11, profiles/r02b), neutral on conv2 -- on by default, PG_FLAG_NO_PLANES_SWAP / PG_PLANES_SWAP=0 is the twin
   static const bool swap_on = env_int("PG_PLANES_SWAP", 1) != 0;

@@ -31,6 +31,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 
 #include "pg_common.cuh"
 #include "pg_umma.cuh"
@@ -149,6 +150,7 @@ __device__ __forceinline__ TileCoord decode_tile(int id, const UmmaParams& p) {
 template <int MT, typename TIn, typename TOut>
 __global__ void __launch_bounds__(NTHREADS)
 conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
+  pdl_launch_dependents();     // the next kernel of the stream may launch and run its prologue (pg_common.cuh)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_ring = smem;
@@ -192,6 +194,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) trace(p, 4, 0, 0);
+  // activations in global memory belong to the predecessor until it has completed; the weight producer and the MMA
+  // issuer touch constants / shared memory / TMEM only and run ahead
+  if (warp != TMA_WARP && warp != MMA_WARP) pdl_wait();
 
   const int chunks_per_group = p.PG * 8 / p.KC;
   const int n_chunks = p.Cin / p.KC;
@@ -332,6 +337,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
     const int ltid = tid - EPI_THREADS;
     const int rows = BM * MT + (p.K - 1) * p.dil;
     const float slope = p.in_slope;
+    // vectors (8 channels each) in flight per thread.  (Round 3 tried U = 8 for fp32 inputs so that a 128-row x
+    // 16-plane group is one round trip instead of two: the 64 staging registers spill under the 96-register cap of
+    // this 18-warp CTA and the step got 2 % slower -- tools/umma_trace.py shows the role timeline.)
     constexpr int U = VecIO<TIn>::RAW == 1 ? 8 : 4;
     uint32_t a_cnt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -801,7 +809,7 @@ cudaError_t launch_t(const ConvArgs& a, const Plan& pl, cudaStream_t s) {
     unsigned int zero = 0;
     cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero));
   }
-  conv_umma_kernel<MT, TIn, TOut><<<grid, NTHREADS, pl.smem, s>>>(wmap, p);
+  if (cudaError_t e = launch_pdl(conv_umma_kernel<MT, TIn, TOut>, dim3(grid), dim3(NTHREADS), pl.smem, s, wmap, p)) return e;
   if (p.debug & 8) {
     cudaDeviceSynchronize();
     static unsigned long long host[8192];
@@ -836,6 +844,10 @@ bool get_weight_map(const void* w16, int cin, int cout, int k, int kc, int nt, C
   return get_wmap(w16, cin, cout, k, kc, nt, out);
 }
 int device_sm_count() { return num_sms(); }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("PG_PDL"); return !e || atoi(e) != 0; }();
+  return on;
+}
 
 int umma_pick_nt(int cout) { return pick_nt(cout); }
 

@@ -100,6 +100,7 @@ template <int MT, int C, bool RES_X, int EPIM, bool HL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_constant__ CUtensorMap wmap2,
                    const PairParams p) {
+  pdl_launch_dependents();     // the next kernel of the stream may launch and run its prologue (pg_common.cuh)
   constexpr int PLANES = C / 8;
   constexpr int KC16 = C / 16;                 // one K chunk = all C input channels
   constexpr int NCB = C / ECOLS, ITEMS = MT * NCB;
@@ -162,6 +163,9 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // activations in global memory belong to the predecessor until it has completed; the weight producer and the MMA
+  // issuer touch constants / shared memory / TMEM only and run ahead
+  if (warp != TMA_WARP && warp != MMA_WARP) pdl_wait();
   const int rows = BM * MT + (p.K - 1) * p.dil;        // input window rows
   const uint32_t acc1_col = 0u, acc2_col = D * MT * C;  // TMEM columns of the two accumulator sets
 
@@ -799,7 +803,7 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
   if (grid > p.total_tiles) grid = p.total_tiles;
   static const int dbg_sync = [] { const char* e = getenv("PG_PAIR_SYNC"); return e ? atoi(e) : 0; }();
   if (dbg_sync & 1) cudaStreamSynchronize(s);
-  pair_planes_kernel<MT, C, RES_X, EPIM, HL><<<grid, NTHREADS, pl.smem, s>>>(m1, m2, p);
+  if (cudaError_t e = launch_pdl(pair_planes_kernel<MT, C, RES_X, EPIM, HL>, dim3(grid), dim3(NTHREADS), pl.smem, s, m1, m2, p)) return e;
   if (dbg_sync & 2) cudaStreamSynchronize(s);
   return cudaGetLastError();
 }
