@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "audio-seconds synthesized/sec @48 kHz (1/2/4/8 B200) vs host-CPU reference"
 UNIT = "audio-s/s"
-CLIP_SECONDS = 60
+CLIP_SECONDS = int(os.environ.get("PG_BENCH_CLIP_SECONDS", "60"))   # BASELINE configs[1]: 60 s (the override is a tuning aid)
 CPU_SAMPLE_FRAMES = 1000     # BASELINE.json's 10 s row: the CPU arms time one such segment per step
 N_VARIANTS = 4               # clips with different segment lengths cycled through the timed steps
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
@@ -132,12 +132,13 @@ def peaks():
 def ncu_traffic():
     """DRAM bytes per launch of the top decoder conv, from this round's `ncu --set full` capture
     (written by tools/ncu_summary.py --traffic; bench.py cannot run ncu on itself)."""
-    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p))
-        except ValueError:
-            pass
+    for name in ("r03_traffic.json", "r02_traffic.json"):     # newest capture first
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            try:
+                return json.load(open(p))
+            except ValueError:
+                pass
     return None
 
 
