@@ -57,6 +57,11 @@ struct FlowW {
   ConvW pre, post;
   float *cond_w = nullptr, *cond_b = nullptr;   // [2H*nl][gin]
   std::vector<ConvW> in_layers, res, skip;     // res.size() == nl-1, skip.size() == nl
+  // fused WaveNet-layer form (tcgen05 path): the stream h and the skip sum live side by side in one [T][2H] buffer
+  ConvW pre_hs;                                // pre padded to 2H columns (the skip half gets zero weights: it starts at 0)
+  std::vector<ConvW> in_gate;                  // in_layers with (tanh, sigmoid) output columns interleaved (ACT_GATE epilogue)
+  std::vector<ConvW> res_skip;                 // the reference's one [2H][H] res_skip conv (last layer: [H][H], skip only)
+  float *cond_w_g = nullptr, *cond_b_g = nullptr;   // cond_layer rows in the interleaved column order
 };
 
 struct StageW {
@@ -240,6 +245,28 @@ int pack_conv(pg_handle h, const std::string& wname, const std::string& bname, i
   return PG_OK;
 }
 
+// Conv1d weight W[Cout][Cin][K] with an arbitrary output-column map: column j of the packed layer is output channel
+// perm[j] of the reference conv (perm[j] < 0: a zero column with zero bias); flip_ci reverses the input channels.
+int pack_conv_perm(pg_handle h, const std::string& wname, const std::string& bname, int Cout, int Cin, int K,
+                   const std::vector<int>& perm, bool flip_ci, bool split, ConvW* out) {
+  const HostTensor* W = find(h, wname, {Cout, Cin, K});
+  const HostTensor* Bv = find(h, bname, {Cout});
+  if (!W || !Bv) return PG_ERR_INVALID;
+  const int n = (int)perm.size();
+  std::vector<float> w((size_t)K * Cin * n, 0.f), b(n, 0.f);
+  for (int j = 0; j < n; ++j) {
+    if (perm[j] < 0) continue;
+    b[j] = Bv->data[perm[j]];
+    for (int ci = 0; ci < Cin; ++ci) {
+      const int src_ci = flip_ci ? Cin - 1 - ci : ci;
+      for (int k = 0; k < K; ++k) w[((size_t)k * Cin + ci) * n + j] = W->data[((size_t)perm[j] * Cin + src_ci) * K + k];
+    }
+  }
+  int rc = upload_conv(h, w, K, Cin, n, out, split);
+  if (rc) return rc;
+  return upload(h, b, &out->bias);
+}
+
 int upload_named(pg_handle h, const std::string& name, std::initializer_list<int64_t> shape,
                  float** out) {
   const HostTensor* t = find(h, name, shape);
@@ -315,7 +342,7 @@ struct Plan {
 struct Ws {
   // offsets into the workspace
   size_t lens, pitch, sid, x, y, qkv, att, ffn, stats, m_p, logs_p, z_p, z, fh, fa, facts, fskip,
-      gcond, dcond, source, phase, stage[5], zpl, h16[4], attn, tlen;
+      gcond, dcond, source, phase, stage[5], zpl, h16[4], attn, tlen, fhs;
   size_t stage_elems = 0;
   size_t total = 0;
 };
@@ -343,6 +370,7 @@ Ws plan_ws(const pg_config& c, int B, int T) {
   w.fa = p.take(sizeof(float) * BT * 2 * H);
   w.facts = p.take(sizeof(float) * BT * H);
   w.fskip = p.take(sizeof(float) * BT * H);
+  w.fhs = p.take(sizeof(float) * BT * 2 * H);      // fused WaveNet-layer form: [T][h | skip]
   w.gcond = p.take(sizeof(float) * c.flow_n_flows * B * 2 * H * c.flow_wn_layers);
   w.dcond = p.take(sizeof(float) * B * c.upsample_initial_channel);
   size_t L = T;
@@ -486,6 +514,7 @@ int run_conv(pg_handle h, cudaStream_t s, ConvArgs a, const ConvW& w, DType in_d
   a.tapmask = w.tapmask;
   a.out_f32 = out_dt == DT_F32 ? 1 : 0;
   const bool umma = !force_simt && w.w16 && umma_conv_supported(a);
+  if (a.act == ACT_GATE && !umma) return fail(PG_ERR_UNSUPPORTED, "gated in-layer shape not supported by the tcgen05 GEMM");
   const bool prof = (h->cfg.flags & PG_FLAG_PROFILE) != 0;
   pg_handle_s::ProfRec rec;
   if (prof) {
@@ -579,7 +608,42 @@ int run_flow(pg_handle h, cudaStream_t s, const Ws& w, int B, int T, float* z) {
   float* acts = at<float>(h, w.facts);
   float* skip = at<float>(h, w.fskip);
   const int gl = 2 * H * nl;
-  for (int f = c.flow_n_flows - 1; f >= 0; --f) {
+  // Fused WaveNet-layer form (tcgen05 path): 2 launches per layer instead of 4 -- the gate runs in the in-layer
+  // GEMM's epilogue over interleaved (tanh, sigmoid) columns, and the reference's ONE res_skip conv writes
+  // [h + res | skip + skip'] into the side-by-side buffer hs (its residual input is hs itself; pre fills the skip
+  // half with zeros through zero weight columns).  PG_FLAG_FORCE_SIMT keeps the four-launch twin below.
+  const bool fused = !(h->cfg.flags & PG_FLAG_FORCE_SIMT) && H % 32 == 0;
+  float* hs = at<float>(h, w.fhs);
+  for (int f = c.flow_n_flows - 1; f >= 0 && fused; --f) {
+    const FlowW& F = h->flows[f];
+    float* gc = at<float>(h, w.gcond) + (size_t)f * B * gl;
+    PG_LAUNCH(h, launch_cond_gemv(h->emb_g, at<int>(h, w.sid), F.cond_w_g, F.cond_b_g, gc, B, c.gin_channels, gl, s));
+    const int x0_off = F.flipped ? half : 0, x1_off = F.flipped ? 0 : half;
+    ConvArgs a;
+    a.B = B; a.L_in = T; a.L_out = T; a.lens = lens;
+    ConvArgs pre = a;      // [h | 0] = pre(x0) * mask
+    pre.x = z; pre.x_ld = C; pre.x_coff = x0_off; pre.y = hs; pre.y_ld = 2 * H; pre.out_mask = 1;
+    PG_TRY(run_conv(h, s, pre, F.pre_hs, DT_F32, DT_F32, true));
+    for (int l = 0; l < nl; ++l) {
+      ConvArgs in = a;     // acts = gate(in_layer(h) + cond)
+      in.x = hs; in.x_ld = 2 * H; in.y = acts; in.y_ld = H; in.pad = (c.flow_wn_kernel - 1) / 2;
+      in.bbias = gc + (size_t)l * 2 * H; in.bbias_ld = gl; in.act = ACT_GATE;
+      PG_TRY(run_conv(h, s, in, F.in_gate[l], DT_F32, DT_F32, true));
+      ConvArgs rs = a;     // [h | skip] = ([h | skip] + res_skip(acts)) * mask   (last layer: the skip half only)
+      const int off = l < nl - 1 ? 0 : H;
+      rs.x = acts; rs.x_ld = H; rs.y = hs; rs.y_ld = 2 * H; rs.y_coff = off;
+      rs.res = hs; rs.res_ld = 2 * H; rs.res_coff = off; rs.out_mask = 1;
+      PG_TRY(run_conv(h, s, rs, F.res_skip[l], DT_F32, DT_F32, true));
+    }
+    ConvArgs po = a;       // x1 = (x1 - post(skip * mask) * mask) * mask
+    po.x = hs; po.x_ld = 2 * H; po.x_coff = H; po.in_mask = 1;
+    po.y = z; po.y_ld = C; po.y_coff = x1_off;
+    po.res = z; po.res_ld = C; po.res_coff = x1_off; po.res_scale = -1.f; po.out_scale = -1.f;
+    po.out_mask = 1;
+    PG_TRY(run_conv(h, s, po, F.post, DT_F32, DT_F32, true));
+    PG_TRY(record_tap(h, s, "flow." + std::to_string(f), z, DT_F32, B, T, C));
+  }
+  for (int f = c.flow_n_flows - 1; f >= 0 && !fused; --f) {
     const FlowW& F = h->flows[f];
     float* gc = at<float>(h, w.gcond) + (size_t)f * B * gl;
     PG_LAUNCH(h, launch_cond_gemv(h->emb_g, at<int>(h, w.sid), F.cond_w, F.cond_b, gc, B,
@@ -1204,6 +1268,40 @@ int pg_finalize(pg_handle h) {
       } else {
         PG_TRY(pack_conv(h, r + "weight", r + "bias", H, H, 1, 0, H, false, false, true, &Fw.skip[l]));
       }
+    }
+    // fused WaveNet-layer form: gate inside the in-layer GEMM, one res_skip GEMM, h | skip in one buffer
+    {
+      std::vector<int> gate_perm(2 * H), pre_perm(2 * H, -1), full(2 * H), skip_only(H);
+      for (int i = 0; i < H; ++i) {
+        gate_perm[2 * i] = i;
+        gate_perm[2 * i + 1] = H + i;
+        pre_perm[i] = i;
+        skip_only[i] = i;
+      }
+      for (int i = 0; i < 2 * H; ++i) full[i] = i;
+      PG_TRY(pack_conv_perm(h, p + "pre.weight", p + "pre.bias", H, half, 1, pre_perm, Fw.flipped, true, &Fw.pre_hs));
+      Fw.in_gate.resize(nl);
+      Fw.res_skip.resize(nl);
+      for (int l = 0; l < nl; ++l) {
+        const std::string q = p + "enc.in_layers." + std::to_string(l) + ".";
+        PG_TRY(pack_conv_perm(h, q + "weight", q + "bias", 2 * H, H, c.flow_wn_kernel, gate_perm, false, true,
+                              &Fw.in_gate[l]));
+        const std::string r = p + "enc.res_skip_layers." + std::to_string(l) + ".";
+        if (l < nl - 1) PG_TRY(pack_conv_perm(h, r + "weight", r + "bias", 2 * H, H, 1, full, false, true, &Fw.res_skip[l]));
+        else PG_TRY(pack_conv_perm(h, r + "weight", r + "bias", H, H, 1, skip_only, false, true, &Fw.res_skip[l]));
+      }
+      const HostTensor* cw = find(h, p + "enc.cond_layer.weight", {2 * H * nl, c.gin_channels, 1});
+      const HostTensor* cb = find(h, p + "enc.cond_layer.bias", {2 * H * nl});
+      if (!cw || !cb) return PG_ERR_INVALID;
+      std::vector<float> wg(cw->data.size()), bg(cb->data.size());
+      for (int l = 0; l < nl; ++l)
+        for (int j = 0; j < 2 * H; ++j) {
+          const size_t dst = (size_t)l * 2 * H + j, src = (size_t)l * 2 * H + gate_perm[j];
+          bg[dst] = cb->data[src];
+          for (int k = 0; k < c.gin_channels; ++k) wg[dst * c.gin_channels + k] = cw->data[src * c.gin_channels + k];
+        }
+      PG_TRY(upload(h, wg, &Fw.cond_w_g));
+      PG_TRY(upload(h, bg, &Fw.cond_b_g));
     }
   }
   // --- decoder ---

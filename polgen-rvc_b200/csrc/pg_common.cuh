@@ -77,7 +77,9 @@ void set_error(const std::string& msg);
     }                                                                               \
   } while (0)
 
-enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_TANH = 3 };
+// ACT_GATE (tcgen05 time-major kernel, f32 output only): output columns come in (tanh, sigmoid) pairs --
+//   y[:, j] = tanh(v[2j]) * sigmoid(v[2j+1]), Cout / 2 columns are written (commons.py:79-86 fused into the in-layer GEMM)
+enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_TANH = 3, ACT_GATE = 4 };
 
 // One conv / GEMM layer over time-major activations.
 //   in row (b, t + tap*dil - pad), channel x_coff + ci, row pitch x_ld elements

@@ -548,6 +548,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
               *reinterpret_cast<uint4*>(stg + lane * EP + q8 * 16) = q;
+            } else if (p.act == ACT_GATE) {
+              // WaveNet gate on (tanh, sigmoid) column pairs: 8 accumulator columns -> 4 outputs (same arithmetic as
+              // the stand-alone gate kernel)
+              float g[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) g[i] = tanhf(v[2 * i]) * (1.f / (1.f + __expf(-v[2 * i + 1])));
+              *reinterpret_cast<float4*>(stg + lane * EP + q8 * 16) = make_float4(g[0], g[1], g[2], g[3]);
             } else {
               // f32 outputs: stage the row's 32 B so the block leaves as full 128 B rows (below)
               *reinterpret_cast<float4*>(stg + lane * EP + q8 * 32) = make_float4(v[0], v[1], v[2], v[3]);
@@ -556,6 +563,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const UmmaParams p) {
           }
           if constexpr (!STAGED) {
             __syncwarp();
+            if (p.act == ACT_GATE) {      // 16 outputs (64 B) per row and block
+              if (!(p.debug & 2)) {
+                TOut* yb = reinterpret_cast<TOut*>(p.y) + ((size_t)tc.b * p.L + wrow0) * p.y_ld + p.y_coff + (n0 + c0) / 2;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int id = i * 32 + lane, r = id >> 2, c16 = id & 3;
+                  if (wrow0 + r < p.L)
+                    *reinterpret_cast<float4*>(yb + (size_t)r * p.y_ld + c16 * 4) =
+                        *reinterpret_cast<const float4*>(stg + r * EP + c16 * 16);
+                }
+              }
+            } else
             if (!(p.debug & 2)) {
               TOut* yb = reinterpret_cast<TOut*>(p.y) + ((size_t)tc.b * p.L + wrow0) * p.y_ld + p.y_coff + n0 + c0;
 #pragma unroll
@@ -859,6 +878,7 @@ bool umma_conv_supported(const ConvArgs& a) {
   if (a.res && (a.res_ld % 8 || a.res_coff % 8)) return false;
   if (a.L_in != a.L_out) return false;
   if (a.act == ACT_TANH) return false;
+  if (a.act == ACT_GATE && (!a.out_f32 || a.accumulate || a.res || a.out_mask || a.Cout % 64)) return false;
   if (a.K < 1 || a.K > 32) return false;
   if ((a.in_mask || a.out_mask) && !a.lens) return false;
   Plan pl;
