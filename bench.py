@@ -462,6 +462,14 @@ def run_ours(args):
             "measured_in": "sequential single-engine pass after the timed region (CUDA events around every "
                            "conv launch on its stream); the timed region itself overlaps clips on %d lanes" % args.lanes,
             "sequential_ms_per_step": seq_ms / n_seq,
+            # the five conv shapes with the largest share of the sequential step (class 0 = decoder plane convs; N < 0:
+            # fused ResBlock pair), each with its own fraction of the peak: the class figure above is their FLOP-weighted mean
+            "top_shapes": [
+                {"Cin": int(cin), "N": int(n), "K": int(k), "dil": int(dil), "MT": int(mt), "launches": int(cnt),
+                 "ms_per_launch": ms / cnt, "tflops": fl / (ms * 1e-3) / 1e12, "frac": fl / (ms * 1e-3) / 1e12 / tf_peak,
+                 "share_of_step": ms / seq_ms}
+                for cls, cin, n, k, dil, mt, cnt, ms, fl in sorted((r for r in table if int(r[0]) == 0 and r[7] > 0),
+                                                                    key=lambda r: -r[7])[:5]],
         }
         wl = (f"RVC {args.config} synthesizer decode, {args.segments} x 10 s segments (T=1000) sharded over the ranks by "
               f"plan_shards, equal-length sub-batches of <= {args.max_batch}, waveforms gathered on rank 0"

@@ -617,3 +617,29 @@ def test_tcgen05_attention_vs_mma_twin_and_oracle(case):
         om, ol, _ = orc.text_encoder(W, cfg, phone, pitch, lengths)
         assert latent_err(m_new.cpu().transpose(1, 2), om) <= LATENT_REL
         assert latent_err(l_new.cpu().transpose(1, 2), ol) <= LATENT_REL
+
+
+def test_decoder_sm_cap_is_bit_identical():
+    """pg_set_decoder_sms caps the CTAs of the decoder's persistent kernels (SegmentScheduler(decoder_sms=...)); the
+    tile walk is grid-stride and a tile's result does not depend on the CTA that computes it, so the waveform must
+    not change by a bit -- also through a replayed CUDA graph (the setter drops the captured graphs)."""
+    import polgen_rvc_b200 as pg
+    cfg = pg.CONFIGS["v2-48k"]
+    sd = pg.synth_weights(cfg, seed=9)
+    d = _dev()
+    rows = []
+    for i, T in enumerate((700, 333)):
+        phone, _, pitch, f0, _ = pg.synth_inputs(cfg, 1, T, seed=40 + i)
+        rows.append({"phone": phone[0].to(d), "pitch": pitch[0].to(d), "f0": f0[0].to(d), "sid": 0})
+    eng = _engine(cfg, sd)
+    st = torch.cuda.Stream()
+    outs = []
+    for cap in (0, 0, 100, 100, 37, 0):      # repeated: second call of a setting replays the captured graph
+        eng.set_decoder_sms(cap)
+        with torch.cuda.stream(st):
+            w, _ = eng.infer_segments(rows, seed=3)
+        st.synchronize()
+        outs.append(torch.cat([x.reshape(-1) for x in w]).clone())
+    assert bool(torch.isfinite(outs[0]).all())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
