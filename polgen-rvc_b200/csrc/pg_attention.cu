@@ -411,14 +411,15 @@ constexpr int UV_TERM = (UK / 8) * AD * 16;         // 12288 B: one term of a V 
 constexpr int UP_TERM = (UK / 8) * UQ * 16;         // 16384 B: one term of P          [key group][row][8 keys]
 constexpr int U_KSTAGES = 2, U_VSTAGES = 3;
 constexpr int URL = 22;                             // rel-logit row pitch (floats): 21*i + j + w is conflict-free
-constexpr int U_THREADS = 192;
+constexpr int U_MAX_THREADS = 320;                  // NH = 2: 8 softmax warps + MMA-issue warp + loader warp (NH = 1: 192)
 constexpr int U_OFF_Q = 0;
 constexpr int U_OFF_K = U_OFF_Q + 2 * UQ_TERM;
 constexpr int U_OFF_V = U_OFF_K + U_KSTAGES * 2 * UK_TERM;
 constexpr int U_OFF_P = U_OFF_V + U_VSTAGES * 2 * UV_TERM;      // prologue: aliased by the fp32 rel-key table
 constexpr int U_OFF_RL = U_OFF_P + 2 * UP_TERM;
 constexpr int U_OFF_BAR = U_OFF_RL + UQ * URL * 4;
-constexpr int U_SMEM = U_OFF_BAR + 256;
+constexpr int U_OFF_XM = U_OFF_BAR + 256;           // NH = 2: row-max exchange between the two column halves [2][2][128] f32
+constexpr int U_SMEM = U_OFF_XM + 2 * 2 * UQ * 4;
 constexpr uint32_t U_TMEM_COLS = 512;               // S0 @0, S1 @64, O0 @128, O1 @256
 static_assert(RP * AD * 4 <= 2 * UP_TERM, "rel-key table must fit the P buffer it aliases");
 static_assert(U_SMEM <= 227 * 1024, "attention tile set exceeds shared memory");
@@ -480,13 +481,22 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-__global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
+// NH = softmax threads per query row.  NH = 1: four softmax warps, a thread owns its row's 64 scores and 96 outputs.
+// NH = 2: eight softmax warps -- warps w and w + 4 share TMEM lane quarter w and split the row's columns (32 scores,
+// 48 outputs each); the only per-block exchange is the row maximum (one float through shared memory + a 64-thread named
+// barrier), the row sums stay per-thread partials until the end.  Two warps per scheduler hide the latency one warp
+// exposes (ncu on NH = 1: 4.7 cycles per issued instruction), and a thread's 80 live values fit the 168 registers
+// ten warps leave it.
+template <int NH>
+__global__ void __launch_bounds__(128 * NH + 64, 1) rel_attention_umma_kernel(
     const __half* __restrict__ qb, const __half* __restrict__ kb, const __half* __restrict__ vb,
     const float* __restrict__ qkv, const float* __restrict__ rel_k, const int* __restrict__ lens,
     float* __restrict__ part_o, float* __restrict__ part_m, float* __restrict__ part_l, float* __restrict__ band_s,
     int B, int T, int Tp, int H, int heads, int window, int splits, float qscale, uint32_t idesc_s,
     uint32_t idesc_o) {
   using namespace umma;
+  constexpr int U_THREADS = 128 * NH + 64, U_SOFT = 128 * NH, MMA_W = 4 * NH, LOAD_W = 4 * NH + 1;
+  constexpr int NC = UK / NH, NO = AD / NH;     // score columns / output columns per softmax thread
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.z / splits, sp = blockIdx.z - b * splits, h = blockIdx.y, q0 = blockIdx.x * UQ;
@@ -524,16 +534,16 @@ __global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
     for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < 3; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&o_full[i], 1); }
-    mbar_init(p_full, UQ);
+    mbar_init(p_full, U_SOFT);
     fence_barrier_init();
   }
-  if (warp == 4) tcgen05_alloc(tmem_slot, U_TMEM_COLS);
+  if (warp == MMA_W) tcgen05_alloc(tmem_slot, U_TMEM_COLS);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 5) {
+  if (warp == LOAD_W) {
     // ------------------------------------------------ loader: one bulk copy per Q tile / K block / V block
     if (elect_one()) {
       const char* q_src = reinterpret_cast<const char*>(qb) + (bh * (Tp / UQ) + (size_t)blockIdx.x) * (2 * UQ_TERM);
@@ -553,7 +563,7 @@ __global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
                  &v_full[vs]);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == MMA_W) {
     // ------------------------------------------------ MMA issue
     if (elect_one()) {
       const uint32_t q_s = smem_u32(smem + U_OFF_Q), k_s = smem_u32(smem + U_OFF_K), v_s = smem_u32(smem + U_OFF_V),
@@ -604,14 +614,17 @@ __global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
       }
     }
   } else {
-    // ------------------------------------------------ softmax: thread = query row = TMEM lane
-    const int r = tid, i = q0 + r;
+    // ------------------------------------------------ softmax: thread = (query row = TMEM lane, column half)
+    const int half = warp >> 2, r = tid & (UQ - 1), i = q0 + r;
+    const int cbeg = half * NC, obeg = half * NO;
     float* rl = reinterpret_cast<float*>(smem + U_OFF_RL);
+    float* xm = reinterpret_cast<float*>(smem + U_OFF_XM);
+    const int pair_bar = 2 + (warp & 3);      // named barrier of the two warps that share this lane quarter (NH = 2)
     // rel-key logits q_i . Ek[rel] in fp32 when this CTA's keys touch the band of its queries
     const bool any_band = kb_begin * UK < q0 + UQ + window && kb_end * UK > q0 - window;
     if (any_band) {
       float* ek = reinterpret_cast<float*>(smem + U_OFF_P);
-      for (int t = tid; t < R * AD; t += UQ) ek[t] = rel_k[t];
+      for (int t = tid; t < R * AD; t += U_SOFT) ek[t] = rel_k[t];
       float q[AD];
       if (i < T) {
         const float4* row = reinterpret_cast<const float4*>(qkv + ((size_t)b * T + i) * 3 * H + h * AD);
@@ -624,8 +637,8 @@ __global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
 #pragma unroll
         for (int c = 0; c < AD; ++c) q[c] = 0.f;
       }
-      named_bar_sync(1, UQ);
-      for (int rel = 0; rel < R; ++rel) {
+      named_bar_sync(1, U_SOFT);
+      for (int rel = half; rel < R; rel += NH) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // four chains: a single 96-term chain is latency-bound
         const float* e = ek + rel * AD;
 #pragma unroll
@@ -637,24 +650,30 @@ __global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
         }
         rl[r * URL + rel] = (s0 + s1) + (s2 + s3);
       }
-      named_bar_sync(1, UQ);     // the table's shared memory becomes the P buffer
+      named_bar_sync(1, U_SOFT);     // the table's shared memory becomes the P buffer
     }
     float* band_row = band_s + (bh * Tp + i) * RP;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint8_t* p_row = smem + U_OFF_P + r * 16;
-    float o[AD];
+    float o[NO];
 #pragma unroll
-    for (int c = 0; c < AD; ++c) o[c] = 0.f;
+    for (int c = 0; c < NO; ++c) o[c] = 0.f;
     float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
 
-    auto fold_o = [&](int jj, float alpha) {     // o = o * alpha + O(jj)
-      const uint32_t t0 = lane_addr + 128u + (uint32_t)(jj & 1) * 128u;
+    auto fold_o = [&](int jj, float alpha) {     // o = o * alpha + O(jj)   (this thread's NO columns)
+      const uint32_t t0 = lane_addr + 128u + (uint32_t)(jj & 1) * 128u + (uint32_t)obeg;
 #pragma unroll
-      for (int c0 = 0; c0 < AD; c0 += 32) {
+      for (int c0 = 0; c0 + 32 <= NO; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(t0 + c0, v);
 #pragma unroll
         for (int c = 0; c < 32; ++c) o[c0 + c] = fmaf(o[c0 + c], alpha, __uint_as_float(v[c]));
+      }
+      if constexpr (NO % 32 == 16) {
+        uint32_t v[16];
+        tmem_ld16(t0 + (NO - 16), v);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) o[NO - 16 + c] = fmaf(o[NO - 16 + c], alpha, __uint_as_float(v[c]));
       }
     };
 
@@ -662,43 +681,49 @@ __global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
       const int k0 = (kb_begin + jj) * UK;
       mbar_wait(&s_full[jj & 1], (jj >> 1) & 1);
       tcgen05_fence_after();
-      float s[UK];
+      float s[NC];
       {
-        const uint32_t t0 = lane_addr + (uint32_t)(jj & 1) * UK;
-        uint32_t v0[32], v1[32];
-        tmem_ld32(t0, v0);
-        tmem_ld32(t0 + 32, v1);
+        const uint32_t t0 = lane_addr + (uint32_t)(jj & 1) * UK + (uint32_t)cbeg;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          s[c] = __uint_as_float(v0[c]);
-          s[32 + c] = __uint_as_float(v1[c]);
+        for (int c0 = 0; c0 < NC; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t0 + c0, v);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) s[c0 + c] = __uint_as_float(v[c]);
         }
       }
       const bool band = (k0 < q0 + UQ + window) && (k0 + UK > q0 - window);
       const bool edge = (k0 + UK > len) || (q0 + UQ > len) || (k0 + UK > T);   // CTA-uniform: some mask applies
       if (band || edge) {
 #pragma unroll
-        for (int c = 0; c < UK; ++c) {
-          const int j = k0 + c;
+        for (int c = 0; c < NC; ++c) {
+          const int j = k0 + cbeg + c;
           float v = s[c];
           const int rel = j - i + window;
           const bool inband = band && rel >= 0 && rel < R;
           if (inband) v += rl[r * URL + rel];
           if (!(i < len && j < len)) v = -1e4f;
           if (j >= T) v = -INFINITY;
-          if (inband && j < T) band_row[rel] = v;      // each (i, j) of the band has one owner CTA
+          if (inband && j < T) band_row[rel] = v;      // each (i, j) of the band has one owner
           s[c] = v;
         }
       }
       float mx4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-      for (int c = 4; c < UK; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], s[c]);
-      const float mn = fmaxf(m, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
+      for (int c = 4; c < NC; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], s[c]);
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      if constexpr (NH == 2) {        // the row maximum over both column halves (double-buffered by block parity)
+        float* slot = xm + (jj & 1) * (2 * UQ);
+        slot[half * UQ + r] = mx;
+        named_bar_sync(pair_bar, 64);
+        mx = fmaxf(mx, slot[(half ^ 1) * UQ + r]);
+      }
+      const float mn = fmaxf(m, mx);
       const float alpha = __expf(m - mn);
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      uint4 hi[UK / 8], lo[UK / 8];
+      uint4 hi[NC / 8], lo[NC / 8];
 #pragma unroll
-      for (int g = 0; g < UK / 8; ++g) {
+      for (int g = 0; g < NC / 8; ++g) {
         uint32_t hw[4], lw[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -714,16 +739,17 @@ __global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
         hi[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         lo[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
-      l = fmaf(l, alpha, (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+      l = fmaf(l, alpha, (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));      // NH = 2: this thread's half of the row sum
       m = mn;
       if (jj > 0) {                     // PV(jj-1) has finished reading the P buffer (and O(jj-1) is complete)
         mbar_wait(&o_full[(jj - 1) & 1], ((jj - 1) >> 1) & 1);
         tcgen05_fence_after();
       }
 #pragma unroll
-      for (int g = 0; g < UK / 8; ++g) {
-        *reinterpret_cast<uint4*>(p_row + g * (UQ * 16)) = hi[g];
-        *reinterpret_cast<uint4*>(p_row + UP_TERM + g * (UQ * 16)) = lo[g];
+      for (int g = 0; g < NC / 8; ++g) {
+        const int kg = cbeg / 8 + g;
+        *reinterpret_cast<uint4*>(p_row + kg * (UQ * 16)) = hi[g];
+        *reinterpret_cast<uint4*>(p_row + UP_TERM + kg * (UQ * 16)) = lo[g];
       }
       fence_proxy_async_smem();         // generic-proxy stores -> visible to the tensor core's async-proxy reads
       tcgen05_fence_before();           // orders this thread's tcgen05.ld of S(jj) / O(jj-2) before the arrive
@@ -734,17 +760,25 @@ __global__ void __launch_bounds__(U_THREADS, 1) rel_attention_umma_kernel(
     mbar_wait(&o_full[(n - 1) & 1], ((n - 1) >> 1) & 1);
     tcgen05_fence_after();
     fold_o(n - 1, alpha_prev);
+    if constexpr (NH == 2) {            // the two halves' row sums meet once
+      float* slot = xm + (n & 1) * (2 * UQ);
+      slot[half * UQ + r] = l;
+      named_bar_sync(pair_bar, 64);
+      l += slot[(half ^ 1) * UQ + r];
+    }
     // this split's running max / sum and unnormalised output
     const size_t row = (size_t)sp * rows_all + bh * Tp + i;
-    part_m[row] = m;
-    part_l[row] = l;
-    float4* dst = reinterpret_cast<float4*>(part_o + row * AD);
+    if (half == 0) {
+      part_m[row] = m;
+      part_l[row] = l;
+    }
+    float4* dst = reinterpret_cast<float4*>(part_o + row * AD + obeg);
 #pragma unroll
-    for (int c4 = 0; c4 < AD / 4; ++c4) dst[c4] = make_float4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+    for (int c4 = 0; c4 < NO / 4; ++c4) dst[c4] = make_float4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) tcgen05_dealloc(tmem, U_TMEM_COLS);
+  if (warp == MMA_W) tcgen05_dealloc(tmem, U_TMEM_COLS);
 }
 
 // split count of the tcgen05 kernel: 128-query tiles, one CTA per SM, a CTA's time ~ (its key blocks + 2)
@@ -820,11 +854,21 @@ cudaError_t launch_rel_attention_mma(const float* qkv, const float* rel_k, const
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     static DeviceOnce once;
-    e = ensure_dyn_smem(rel_attention_umma_kernel, once, U_SMEM);
+    static DeviceOnce once1;
+    const char* nh_env = getenv("PG_ATTN_NH");      // A/B aid: 1 = one softmax thread per row, 2 (default) = two
+    const bool two = !nh_env || atoi(nh_env) != 1;
+    e = two ? ensure_dyn_smem(rel_attention_umma_kernel<2>, once, U_SMEM)
+            : ensure_dyn_smem(rel_attention_umma_kernel<1>, once1, U_SMEM);
     if (e != cudaSuccess) return e;
-    rel_attention_umma_kernel<<<dim3(Tp / UQ, n_heads, B * ns), U_THREADS, U_SMEM, s>>>(
-        qb, kb, vb, qkv, rel_k, lens, part_o, part_m, part_l, band_s, B, T, Tp, H, n_heads, window, ns, qscale,
-        umma::make_idesc(UQ, UK), umma::make_idesc(UQ, AD));
+    const dim3 grid(Tp / UQ, n_heads, B * ns);
+    if (two)
+      rel_attention_umma_kernel<2><<<grid, 320, U_SMEM, s>>>(qb, kb, vb, qkv, rel_k, lens, part_o, part_m, part_l, band_s, B,
+                                                            T, Tp, H, n_heads, window, ns, qscale,
+                                                            umma::make_idesc(UQ, UK), umma::make_idesc(UQ, AD));
+    else
+      rel_attention_umma_kernel<1><<<grid, 192, U_SMEM, s>>>(qb, kb, vb, qkv, rel_k, lens, part_o, part_m, part_l, band_s, B,
+                                                            T, Tp, H, n_heads, window, ns, qscale,
+                                                            umma::make_idesc(UQ, UK), umma::make_idesc(UQ, AD));
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const size_t warps = (size_t)B * n_heads * T;
