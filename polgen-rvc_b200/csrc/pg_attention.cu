@@ -411,7 +411,6 @@ constexpr int UV_TERM = (UK / 8) * AD * 16;         // 12288 B: one term of a V 
 constexpr int UP_TERM = (UK / 8) * UQ * 16;         // 16384 B: one term of P          [key group][row][8 keys]
 constexpr int U_KSTAGES = 2, U_VSTAGES = 3;
 constexpr int URL = 22;                             // rel-logit row pitch (floats): 21*i + j + w is conflict-free
-constexpr int U_MAX_THREADS = 320;                  // NH = 2: 8 softmax warps + MMA-issue warp + loader warp (NH = 1: 192)
 constexpr int U_OFF_Q = 0;
 constexpr int U_OFF_K = U_OFF_Q + 2 * UQ_TERM;
 constexpr int U_OFF_V = U_OFF_K + U_KSTAGES * 2 * UK_TERM;
