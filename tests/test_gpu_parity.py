@@ -643,3 +643,21 @@ def test_decoder_sm_cap_is_bit_identical():
     assert bool(torch.isfinite(outs[0]).all())
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
+
+
+def test_f32_stream_twin_matches_hi_lo_stream():
+    """The last decoder stage carries its residual stream as two f16 planes (hi + lo); PG_FLAG_F32_STREAM is the
+    round-1 form with an fp32 stream (separate noise kernel, generic upsampler epilogue).  Same products, fp32-class
+    stream in both: the waveforms agree far inside the tolerance, and both meet it against the oracle."""
+    import polgen_rvc_b200 as pg
+    from polgen_rvc_b200 import _lib
+    from oracle import rvc_oracle as orc
+    cfg = pg.CONFIGS["v2-48k"]
+    sd = pg.synth_weights(cfg, seed=31)
+    inputs = pg.synth_inputs(cfg, 1, 150, seed=31)
+    noise = pg.synth_noise(cfg, 1, 150, seed=31)
+    o, *_ = orc.infer(sd, cfg, *inputs, *noise)
+    a, _ = _run(_engine(cfg, sd, 0), inputs, noise)
+    b, _ = _run(_engine(cfg, sd, _lib.PG_FLAG_F32_STREAM), inputs, noise)
+    assert snr_db(a, o[:, 0]) >= WAVE_SNR_DB and snr_db(b, o[:, 0]) >= WAVE_SNR_DB
+    assert snr_db(a, b) >= 55.0
