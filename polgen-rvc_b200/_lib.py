@@ -27,6 +27,7 @@ PG_FLAG_NO_PAD = 256
 PG_FLAG_F32_STREAM = 512
 PG_FLAG_NO_NOISE_FUSION = 1024
 PG_FLAG_LEGACY_ATTENTION = 2048
+PG_FLAG_NO_POST_FUSION = 4096
 PG_F32 = 0
 PG_F64 = 3
 PG_ABI_VERSION = 2

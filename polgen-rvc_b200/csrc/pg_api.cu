@@ -994,8 +994,12 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
       // Last stage, hi/lo form: the residual stream is carried as two f16 planes (x = hi + lo, 2^-22 relative);
       // hi is the conv operand itself, so a pair moves 256 instead of 384 bytes per sample.  The 1/3-mean that
       // feeds conv_post stays in fp32 planes.
-      float* r0 = reinterpret_cast<float*>(buf[fr[0]]);           // ups output before the source injection
+      float* r0 = reinterpret_cast<float*>(buf[fr[0]]);           // ups output before the source injection; later the conv_post partials
       float* acc = reinterpret_cast<float*>(buf[fr[3]]);
+      // conv_post (nsf.py:142-143) fused into the last pair: its epilogue holds the finished 1/3-mean in fp32 and writes
+      // 2 x 7 partial dot products per sample (56 B) instead of the mean (128 B) that a separate kernel would read back
+      static const bool post_env = [] { const char* e = getenv("PG_POST_FUSION"); return !e || atoi(e) != 0; }();   // A/B aid
+      const bool fuse_post = post_env && !(h->cfg.flags & (PG_FLAG_KEEP_TAPS | PG_FLAG_NO_POST_FUSION)) && C % 16 == 0;
       __half *a0 = h16[0], *aa = h16[1], *ab = h16[2];
       __half *l0 = reinterpret_cast<__half*>(buf[fr[1]]), *la = reinterpret_cast<__half*>(buf[fr[2]]),
              *lb = reinterpret_cast<__half*>(buf[cur]);          // the ups input is dead once r0 exists
@@ -1027,6 +1031,11 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
             pa.out_scale = 1.f / nk;
             pa.accin32 = j > 0 ? acc : nullptr;
             pa.out32 = acc;
+            if (fuse_post && j == nk - 1) {      // the mean is complete in this epilogue: conv_post partials instead of the mean
+              pa.post_w = h->conv_post_w;
+              pa.post_part = r0;
+              pa.post_slope = 0.01f;
+            }
           } else {
             const bool to_b = xc == aa;
             pa.out16 = to_b ? ab : aa;
@@ -1040,7 +1049,10 @@ int run_generator_planes(pg_handle h, cudaStream_t s, const Ws& w, int B, int T,
         }
       }
       PG_TRY(record_tap_planes(h, s, "dec.stage" + std::to_string(i), acc, DT_F32, 1.f, B, L, C));
-      PG_LAUNCH(h, launch_conv_post_planes(acc, DT_F32, h->conv_post_w, wave, B, (int)L, C, 7, 0.01f, tlen, mul, s));
+      if (fuse_post)
+        PG_LAUNCH(h, launch_conv_post_sum(r0, wave, B, (int)L, C / 16, tlen, mul, s));
+      else
+        PG_LAUNCH(h, launch_conv_post_planes(acc, DT_F32, h->conv_post_w, wave, B, (int)L, C, 7, 0.01f, tlen, mul, s));
       return PG_OK;
     } else {
       float* r0 = reinterpret_cast<float*>(buf[fr[0]]);

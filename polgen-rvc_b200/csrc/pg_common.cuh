@@ -167,7 +167,15 @@ struct PairConvArgs {
   __half* out16 = nullptr; float out16_slope = 1.f; float* out32 = nullptr;
   float out_scale = 1.f;
   int grid_cap = 0;   // see PlaneConvArgs::grid_cap
+  // conv_post fused into the LAST pair of the last stage (hi/lo stream, out32 form): instead of storing the fp32 mean,
+  // E2 writes per row the K_POST partial dot products  part[h][j][b][t] = sum_{c in half h} post_w[j][c] * lrelu(v[c], post_slope)
+  // of its 16-channel item (h = channel half); launch_conv_post_sum adds the shifted partials and applies tanh
+  const float* post_w = nullptr; float* post_part = nullptr; float post_slope = 1.f;
 };
+constexpr int K_POST = 7;
+// wave[b][t] = tanh(sum_h sum_j part[h][j][b][t + j - K_POST/2]) over rows inside [0, hard end); n_half = C / 16
+cudaError_t launch_conv_post_sum(const float* part, float* wave, int B, int L, int n_half, const int* tlen, int len_mul,
+                                 cudaStream_t s);
 bool pair_conv_supported(const PairConvArgs& a);
 int pair_conv_mt(const PairConvArgs& a);
 cudaError_t launch_pair_planes(const PairConvArgs& a, cudaStream_t s);

@@ -37,6 +37,7 @@ constexpr int NTHREADS = (E2_WARP0 + E2_WARPS) * 32;
 constexpr int ECOLS = 16;   // accumulator columns per epilogue item
 
 struct PairParams {
+  const float* post_w; float* post_part; float post_slope;   // conv_post partials (PairConvArgs)
   const __half* x; int L, B, K, dil;
   const int* tlen; int len_mul;        // hard end of row b: tlen[b]*len_mul (nullptr = L)
   const float* bias1; const float* bias2;
@@ -154,6 +155,9 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
     fence_barrier_init();
   }
   if (tid < 2 * C) bias_s[tid] = tid < C ? p.bias1[tid] : p.bias2[tid - C];
+  float* post_s = bias_s + 2 * C;      // [K_POST][C] conv_post weights (fused post step)
+  if (p.post_part)
+    for (int i = tid; i < K_POST * C; i += NTHREADS) post_s[i] = p.post_w[i];
   if (warp == MMA_WARP) tcgen05_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   if (warp == TMA_WARP && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap1) : "memory");
@@ -444,6 +448,9 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
         tmem_ld16(lane_taddr + b * (uint32_t)(MT * C) + (uint32_t)(m * C + cb * ECOLS), acc);
         if (o < MO && t < L) {
           uint4* dst = yout + (size_t)(cb * 2) * L + t;
+          float pd[K_POST];       // fused conv_post: this item's partial dot products
+#pragma unroll
+          for (int jp = 0; jp < K_POST; ++jp) pd[jp] = 0.f;
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
             float v[8], rr[8];
@@ -486,7 +493,23 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
                 for (int i = 0; i < 8; ++i) v[i] += av[i];
               }
             }
-            if (OUT32) {      // the 1/3-mean that feeds conv_post stays fp32
+            if (OUT32) {
+              if (p.post_part) {     // conv_post on the finished mean, in fp32: 7 taps x this chunk's 8 channels
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * p.post_slope);     // slope <= 1
+                const float* wp = post_s + cb * ECOLS + jj * 8;
+#pragma unroll
+                for (int jp = 0; jp < K_POST; ++jp) {
+                  const float4 w0 = *reinterpret_cast<const float4*>(wp + jp * C);
+                  const float4 w1 = *reinterpret_cast<const float4*>(wp + jp * C + 4);
+                  float a = pd[jp];
+                  a = fmaf(w0.x, v[0], a); a = fmaf(w0.y, v[1], a); a = fmaf(w0.z, v[2], a); a = fmaf(w0.w, v[3], a);
+                  a = fmaf(w1.x, v[4], a); a = fmaf(w1.y, v[5], a); a = fmaf(w1.z, v[6], a); a = fmaf(w1.w, v[7], a);
+                  pd[jp] = a;
+                }
+                continue;
+              }
+              // the 1/3-mean that feeds conv_post stays fp32
               float4* o4 = reinterpret_cast<float4*>(p.out32) + (plane_base + (size_t)(cb * 2 + jj) * L + t) * 2;
               o4[0] = make_float4(v[0], v[1], v[2], v[3]);
               o4[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -503,6 +526,11 @@ pair_planes_kernel(const __grid_constant__ CUtensorMap wmap1, const __grid_const
               for (int i = 0; i < 8; ++i) v[i] -= hv[i];
               (lout + (size_t)(cb * 2) * L + t)[(size_t)jj * L] = pack8(v);
             }
+          }
+          if (OUT32 && p.post_part) {      // one coalesced 4 B store per tap: part[half cb][tap][batch row][t]
+#pragma unroll
+            for (int jp = 0; jp < K_POST; ++jp)
+              p.post_part[((size_t)(cb * K_POST + jp) * p.B + bb) * L + t] = pd[jp];
           }
         }
       }
@@ -713,7 +741,7 @@ bool make_pair_plan(const PairConvArgs& a, PairPlan* out) {
   if (a.K < 1 || a.K > 16 || !(a.K & 1) || a.dil < 1) return false;
   const int planes = a.C / 8;
   const int w_tile = a.C * a.C * 2;
-  const size_t fixed = 1024 + 1024 + 8 * (size_t)a.C;   // alignment slack, barriers, two bias vectors
+  const size_t fixed = 1024 + 1024 + 8 * (size_t)a.C + (a.post_part ? 4 * (size_t)K_POST * a.C : 0);   // alignment slack, barriers, two bias vectors, conv_post weights
   const size_t budget = (size_t)227 * 1024;
   const size_t w_all = 2 * (size_t)a.K * w_tile;
   static const int forced_mt = [] { const char* e = getenv("PG_PAIR_MT"); return e ? atoi(e) : 0; }();
@@ -776,6 +804,7 @@ cudaError_t launch_pair_t(const PairConvArgs& a, const PairPlan& pl, cudaStream_
     return cudaErrorNotSupported;
   PairParams p;
   p.x = a.x; p.L = a.L; p.B = a.B; p.K = a.K; p.dil = a.dil;
+  p.post_w = a.post_w; p.post_part = a.post_part; p.post_slope = a.post_slope;
   p.tlen = a.tlen; p.len_mul = a.len_mul;
   p.bias1 = a.bias1; p.bias2 = a.bias2; p.res32 = a.res32; p.res_inv = a.res_inv;
   p.x_lo = a.x_lo; p.out_lo = a.out_lo;
@@ -850,6 +879,7 @@ cudaError_t launch_pair_planes(const PairConvArgs& a, cudaStream_t s) {
   if (no_epim) epim = 0;
   static const int epim_mask = [] { const char* e = getenv("PG_PAIR_EPIM_MASK"); return e ? atoi(e) : 14; }();
   if (!((epim_mask >> epim) & 1)) epim = 0;
+  if (a.post_part && !(hl && epim >= 2 && a.post_w && a.post_slope <= 1.f)) return cudaErrorInvalidValue;   // only the straight-line last-pair E2 computes the conv_post partials
 #define PG_PAIR_E(MT_, C_, HL_)                                                      \
   switch (epim) {                                                                   \
     case 1: return launch_pair_t<MT_, C_, true, 1, HL_>(a, pl, s);                   \

@@ -280,6 +280,28 @@ __global__ void __launch_bounds__(CPB) conv_post_planes_kernel(const T* __restri
   wave[(size_t)b * L + t] = t < t_hi ? tanhf(out) : 0.f;
 }
 
+// Second half of the fused post step: the last ResBlock pair left, per row, the K_POST partial dot products of each
+// 16-channel half (part[h][j][b][t], see PairConvArgs::post_part); conv_post's output is the sum of the shifted
+// partials -- wave[t] = tanh(sum_h sum_j part[h][j][t + j - K/2]) -- with rows outside [0, hard end) contributing zero.
+__global__ void __launch_bounds__(256) conv_post_sum_kernel(const float* __restrict__ part, float* __restrict__ wave,
+                                                            int B, int L, int n_half, const int* __restrict__ tlen,
+                                                            int len_mul) {
+  const int b = blockIdx.y, t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= L) return;
+  const int t_hi = tlen ? min(L, tlen[b] * len_mul) : L;
+  float acc = 0.f;
+  if (t < t_hi) {
+    for (int h = 0; h < n_half; ++h) {
+#pragma unroll
+      for (int j = 0; j < K_POST; ++j) {
+        const int n = t + j - K_POST / 2;
+        if (n >= 0 && n < t_hi) acc += part[((size_t)(h * K_POST + j) * B + b) * L + n];
+      }
+    }
+  }
+  wave[(size_t)b * L + t] = t < t_hi ? tanhf(acc) : 0.f;
+}
+
 unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
@@ -378,6 +400,13 @@ cudaError_t launch_source_frames(const float* src, __half* xs, int B, int L, int
   if (stride < 1 || stride > NOISE_TC_SEG) return cudaErrorInvalidValue;
   const size_t n = (size_t)B * (3 * NOISE_TC_SEG / 8) * L;
   source_frames_kernel<<<blocks_for(n), 256, 0, s>>>(src, xs, B, L, Lsrc, stride, pad);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_post_sum(const float* part, float* wave, int B, int L, int n_half, const int* tlen, int len_mul,
+                                 cudaStream_t s) {
+  if (n_half < 1) return cudaErrorInvalidValue;
+  conv_post_sum_kernel<<<dim3((L + 255) / 256, B), 256, 0, s>>>(part, wave, B, L, n_half, tlen, len_mul);
   return cudaGetLastError();
 }
 

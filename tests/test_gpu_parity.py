@@ -661,3 +661,25 @@ def test_f32_stream_twin_matches_hi_lo_stream():
     b, _ = _run(_engine(cfg, sd, _lib.PG_FLAG_F32_STREAM), inputs, noise)
     assert snr_db(a, o[:, 0]) >= WAVE_SNR_DB and snr_db(b, o[:, 0]) >= WAVE_SNR_DB
     assert snr_db(a, b) >= 55.0
+
+
+def test_fused_conv_post_matches_separate_kernel():
+    """conv_post (nsf.py:142-143) runs as partial dot products in the last ResBlock pair's epilogue plus a shifted sum;
+    PG_FLAG_NO_POST_FUSION is the twin with the separate kernel over the fp32 mean.  Same fp32 products in a different
+    summation order: the waveforms agree to rounding -- on ragged rows too (hard row ends, rows shorter than a tile)."""
+    import polgen_rvc_b200 as pg
+    from polgen_rvc_b200 import _lib
+    cfg = pg.CONFIGS["v2-48k"]
+    sd = pg.synth_weights(cfg, seed=17, post_std=0.05)
+    d = _dev()
+    rows = []
+    for i, T in enumerate((333, 40, 7)):
+        phone, _, pitch, f0, _ = pg.synth_inputs(cfg, 1, T, seed=60 + i)
+        rows.append({"phone": phone[0].to(d), "pitch": pitch[0].to(d), "f0": f0[0].to(d), "sid": 0})
+    a = _engine(cfg, sd).infer_segments(rows, seed=5)[0]
+    b = _engine(cfg, sd, _lib.PG_FLAG_NO_POST_FUSION).infer_segments(rows, seed=5)[0]
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert bool(torch.isfinite(x).all())
+        assert snr_db(x.cpu(), y.cpu()) >= 100.0
+        assert float((x - y).abs().max()) <= 1e-5
