@@ -516,8 +516,9 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         const int s0 = (q * p.row_mul + r) * p.nz_stride - p.nz_pad;
 #pragma unroll
         for (int jj = 0; jj < NZ_MAXK; ++jj) {
+          if (jj >= p.nz_k) break;       // uniform early exit: a 1-tap stage issues one load, not eight predicated ones
           const int sn = s0 + jj;
-          sv[jj] = (jj < p.nz_k && q < p.L && sn >= 0 && sn < p.nz_len) ? __ldg(nz_sp + sn) : 0.f;
+          sv[jj] = (q < p.L && sn >= 0 && sn < p.nz_len) ? __ldg(nz_sp + sn) : 0.f;
         }
       };
       float sv_next[NZ_MAXK];
@@ -535,7 +536,10 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
         float sv[NZ_MAXK];
         if (nz_sp && p.nz_prefetch) {
 #pragma unroll
-          for (int jj = 0; jj < NZ_MAXK; ++jj) sv[jj] = sv_next[jj];
+          for (int jj = 0; jj < NZ_MAXK; ++jj) {
+            if (jj >= p.nz_k) break;
+            sv[jj] = sv_next[jj];
+          }
           if (it + EPI_GROUPS < items) load_sv(it + EPI_GROUPS, sv_next);
         } else if (nz_sp) {
           load_sv(it, sv);
@@ -567,15 +571,14 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap wmap, const PlaneParams p
               v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
 #pragma unroll
               for (int jj = 0; jj < NZ_MAXK; ++jj) {
-                if (jj < p.nz_k) {
-                  const float4 w0 = *reinterpret_cast<const float4*>(wb + (size_t)(jj + 1) * p.Cout_real);
-                  const float4 w1 = *reinterpret_cast<const float4*>(wb + (size_t)(jj + 1) * p.Cout_real + 4);
-                  const float x = sv[jj];
-                  v[0] = fmaf(w0.x, x, v[0]); v[1] = fmaf(w0.y, x, v[1]);
-                  v[2] = fmaf(w0.z, x, v[2]); v[3] = fmaf(w0.w, x, v[3]);
-                  v[4] = fmaf(w1.x, x, v[4]); v[5] = fmaf(w1.y, x, v[5]);
-                  v[6] = fmaf(w1.z, x, v[6]); v[7] = fmaf(w1.w, x, v[7]);
-                }
+                if (jj >= p.nz_k) break;
+                const float4 w0 = *reinterpret_cast<const float4*>(wb + (size_t)(jj + 1) * p.Cout_real);
+                const float4 w1 = *reinterpret_cast<const float4*>(wb + (size_t)(jj + 1) * p.Cout_real + 4);
+                const float x = sv[jj];
+                v[0] = fmaf(w0.x, x, v[0]); v[1] = fmaf(w0.y, x, v[1]);
+                v[2] = fmaf(w0.z, x, v[2]); v[3] = fmaf(w0.w, x, v[3]);
+                v[4] = fmaf(w1.x, x, v[4]); v[5] = fmaf(w1.y, x, v[5]);
+                v[6] = fmaf(w1.z, x, v[6]); v[7] = fmaf(w1.w, x, v[7]);
               }
             }
             if (p.accin16) {
