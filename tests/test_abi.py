@@ -123,3 +123,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(text), f"{f} references the oracle"
+
+
+def test_flag_constants_match_header(lib):
+    """every PG_FLAG_* of the header has the same value in the ctypes mirror (the twins the GPU tests select), and no
+    two flags share a bit"""
+    src = open(HEADER).read()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(PG_FLAG_[A-Z0-9_]+)\s+(\d+)", src)}
+    assert len(flags) >= 12
+    for name, value in flags.items():
+        assert getattr(lib, name) == value, name
+        assert value & (value - 1) == 0, f"{name} is not a single bit"
+    assert len(set(flags.values())) == len(flags)
